@@ -1,0 +1,147 @@
+"""ctypes binding of the C ABI declared in include/age_b200.h.
+
+The shared library (asmvar_b200/libage_b200.so) is built in-tree by ``__graft_entry__.build()``
+(nvcc, sm_100a).  There is no Python or CPU fallback for the alignment itself: if the library
+is missing, importing this module raises; if no CUDA device is usable, ``age_create`` fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("AGE_B200_LIB", PKG_DIR / "libage_b200.so"))
+
+# mode flags (AGEaligner.hh:72-76)
+INDEL_FLAG = 0x01
+TDUPLICATION_FLAG = 0x02
+INVERSION_FLAG = 0x04
+INVR_FLAG = 0x08
+INVL_FLAG = 0x10
+MAX_BPOINTS = 100
+
+AGE_OK = 0
+AGE_NOT_ALIGNED = 1
+AGE_ERR_RANGE = -1
+AGE_ERR_CUDA = -2
+AGE_ERR_ARG = -3
+
+
+class AgeJob(C.Structure):
+    _fields_ = [
+        ("seq1", C.c_char_p), ("len1", C.c_int32),
+        ("seq2", C.c_char_p), ("len2", C.c_int32),
+        ("flag", C.c_int32),
+        ("match", C.c_int16), ("mismatch", C.c_int16),
+        ("gap_open", C.c_int16), ("gap_extend", C.c_int16),
+    ]
+
+
+class AgeBlock(C.Structure):
+    _fields_ = [("start1", C.c_int32), ("start2", C.c_int32), ("length", C.c_int32)]
+
+
+class AgeResult(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("score", C.c_int32), ("flag", C.c_int32), ("used_aux", C.c_int32),
+        ("main_score", C.c_int32), ("aux_score", C.c_int32),
+        ("n_bp", C.c_int32), ("bp", (C.c_int32 * 4) * MAX_BPOINTS),
+        ("alt_index", C.c_int32),
+        ("n_left", C.c_int32), ("n_right", C.c_int32),
+        ("n_alt_left", C.c_int32), ("n_alt_right", C.c_int32),
+        ("left", C.POINTER(AgeBlock)), ("right", C.POINTER(AgeBlock)),
+        ("alt_left", C.POINTER(AgeBlock)), ("alt_right", C.POINTER(AgeBlock)),
+    ]
+
+    def bpoints(self):
+        return [tuple(self.bp[i]) for i in range(self.n_bp)]
+
+    def blocks(self, which: str):
+        n = getattr(self, "n_" + which)
+        p = getattr(self, which)
+        return [(p[i].start1, p[i].start2, p[i].length) for i in range(n)]
+
+    def summary(self) -> dict:
+        """Plain-python view used by the parity tests."""
+        return {
+            "status": self.status, "score": self.score, "flag": self.flag, "used_aux": self.used_aux,
+            "main_score": self.main_score, "aux_score": self.aux_score,
+            "bp": self.bpoints(), "alt_index": self.alt_index,
+            "left": self.blocks("left"), "right": self.blocks("right"),
+            "alt_left": self.blocks("alt_left") if self.alt_index >= 1 else [],
+            "alt_right": self.blocks("alt_right") if self.alt_index >= 1 else [],
+        }
+
+
+class AgeSeqView(C.Structure):
+    _fields_ = [("seq", C.c_char_p), ("len", C.c_int32), ("name", C.c_char_p),
+                ("start", C.c_int32), ("reverse", C.c_int32)]
+
+
+class AgeStats(C.Structure):
+    _fields_ = [
+        ("kernel_ms", C.c_double), ("fill_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
+        ("cell_updates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("launches", C.c_uint64), ("fill_launches", C.c_uint64), ("n_aligners", C.c_uint64),
+    ]
+
+
+# every symbol include/age_b200.h declares; tests check the library exports all of them
+EXPORTED_SYMBOLS = [
+    "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged",
+    "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libage_b200.so (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    vp = C.c_void_p
+    lib.age_create.restype = vp
+    lib.age_create.argtypes = [C.POINTER(C.c_int), C.c_int]
+    lib.age_destroy.restype = None
+    lib.age_destroy.argtypes = [vp]
+    lib.age_last_error.restype = C.c_char_p
+    lib.age_last_error.argtypes = [vp]
+    lib.age_align_batch.restype = C.c_int
+    lib.age_align_batch.argtypes = [vp, C.POINTER(AgeJob), C.c_size_t, C.POINTER(AgeResult)]
+    lib.age_stage.restype = C.c_int
+    lib.age_stage.argtypes = [vp, C.POINTER(AgeJob), C.c_size_t]
+    lib.age_run_staged.restype = C.c_int
+    lib.age_run_staged.argtypes = [vp]
+    lib.age_fetch.restype = C.c_int
+    lib.age_fetch.argtypes = [vp, C.POINTER(AgeResult), C.c_size_t]
+    lib.age_get_stats.restype = C.c_int
+    lib.age_get_stats.argtypes = [vp, C.POINTER(AgeStats)]
+    lib.age_format_alignment.restype = C.c_size_t
+    lib.age_format_alignment.argtypes = [C.POINTER(AgeSeqView), C.POINTER(AgeSeqView), C.POINTER(AgeJob),
+                                         C.POINTER(AgeResult), C.c_char_p, C.c_size_t]
+    lib.age_revcom.restype = None
+    lib.age_revcom.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]
+    lib.age_subst_score.restype = C.c_int
+    lib.age_subst_score.argtypes = [C.c_char, C.c_char, C.c_int, C.c_int]
+    lib.age_version.restype = C.c_char_p
+    lib.age_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def format_alignment(s1: AgeSeqView, s2: AgeSeqView, job: AgeJob, res: AgeResult) -> str:
+    lib = load()
+    cap = 4096 + 8 * (s1.len + s2.len)
+    buf = C.create_string_buffer(cap)
+    n = lib.age_format_alignment(C.byref(s1), C.byref(s2), C.byref(job), C.byref(res), buf, cap)
+    if n >= cap:
+        buf = C.create_string_buffer(n + 1)
+        lib.age_format_alignment(C.byref(s1), C.byref(s2), C.byref(job), C.byref(res), buf, n + 1)
+    return buf.raw[:n].decode("latin-1")

@@ -1,0 +1,412 @@
+// age_format.cpp -- host-side `.age` record formatter.
+//
+// Produces byte-for-byte the text that the reference's AGEaligner::printAlignment()
+// (src/AsmvarAGE/src/AGEaligner.cpp:179-380) and AliFragment::printAlignment()
+// (AGEaligner.hh:230-272) write to stdout, from the compact result the GPU returns
+// (score, breakpoints, diagonal block lists) plus the original strings.
+// No iostream: at GPU rates the formatter is on the critical path, so it appends into a
+// flat byte buffer.
+#include "age_b200.h"
+#include "age_host.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace age {
+
+char complement(char c)
+{   // Sequence.hh:138-150
+    switch (c) {
+    case 'a': return 't'; case 'c': return 'g'; case 't': return 'a'; case 'g': return 'c';
+    case 'A': return 'T'; case 'C': return 'G'; case 'T': return 'A'; case 'G': return 'C';
+    case 'u': return 'a'; case 'U': return 'A';
+    default:  return c;
+    }
+}
+
+static inline int up(char c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+bool same_nuc(char a, char b)
+{   // Sequence.hh:182-188
+    int aa = up(a), bb = up(b);
+    if (aa != bb) return false;
+    return aa == 'A' || aa == 'C' || aa == 'T' || aa == 'G' || aa == 'U';
+}
+
+static inline bool is_gap(char c) { return c == ' ' || c == '-'; }   // Sequence.hh:175-180
+
+// ---- flat output buffer --------------------------------------------------------------------
+struct Out {
+    char *buf; size_t cap; size_t n;
+    void put(char c) { if (n + 1 < cap) buf[n] = c; n++; }
+    void put(const char *s) { while (*s) put(*s++); }
+    void put(const char *s, size_t len) { for (size_t i = 0; i < len; i++) put(s[i]); }
+    void num(long v, int width = 0)
+    {   // operator<<(int) with setw(width), right aligned, fill ' '
+        char tmp[24]; int k = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
+        do { tmp[k++] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (neg) tmp[k++] = '-';
+        for (int i = k; i < width; i++) put(' ');
+        while (k) put(tmp[--k]);
+    }
+};
+
+static int calc_width(int v1, int v2)
+{   // AGEaligner.cpp:382-390
+    int w1 = 0; if (v1 < 0) v1++;
+    while (v1 != 0) { w1++; v1 /= 10; }
+    int w2 = 0; if (v2 < 0) v2++;
+    while (v2 != 0) { w2++; v2 /= 10; }
+    return w1 > w2 ? w1 : w2;
+}
+
+// One aligned fragment (class AliFragment, AGEaligner.hh:179-273)
+struct Frag {
+    std::string a1, a2;
+    int start1, start2, end1, end2;
+};
+
+struct SeqHdr { const char *seq; int len; int start; bool reverse; };
+
+static inline char at(const SeqHdr &s, long i) { return (i >= 0 && i < s.len) ? s.seq[i] : '\0'; }
+
+// findAlignment (AGEaligner.cpp:670-750): blocks -> gapped strings + coordinates
+static void build_frags(const SeqHdr &s1, const SeqHdr &s1rc, const SeqHdr &s2, int flag,
+                        const age_block *left, int n_left, const age_block *right, int n_right,
+                        std::vector<Frag> &frags)
+{
+    frags.clear();
+    const age_block *bs[2] = {left, right};
+    const int nb[2] = {n_left, n_right};
+    for (int b = 0; b < 2; b++) {
+        if (nb[b] <= 0 || !bs[b]) continue;
+        bool use_rc1 = ((flag & AGE_INVL_FLAG) && b == 1) || ((flag & AGE_INVR_FLAG) && b == 0);
+        const SeqHdr &q1 = use_rc1 ? s1rc : s1;
+        int inc1 = q1.reverse ? -1 : 1, inc2 = s2.reverse ? -1 : 1;
+        Frag f;
+        const age_block *bl = bs[b];
+        f.start1 = q1.start + inc1 * (bl[0].start1 - 1);
+        f.start2 = s2.start + inc2 * (bl[0].start2 - 1);
+        f.end1 = f.end2 = 0;
+        int ind1 = bl[0].start1 - 1, ind2 = bl[0].start2 - 1;
+        for (int k = 0; k < nb[b]; k++) {
+            f.end1 = q1.start + inc1 * (bl[k].start1 + bl[k].length - 2);
+            f.end2 = s2.start + inc2 * (bl[k].start2 + bl[k].length - 2);
+            int st1 = bl[k].start1 - 1, st2 = bl[k].start2 - 1;
+            while (ind1 < st1) { f.a1 += at(q1, ind1++); f.a2 += '-'; }
+            while (ind2 < st2) { f.a1 += '-'; f.a2 += at(s2, ind2++); }
+            for (int i = 0; i < bl[k].length; i++) { f.a1 += at(q1, ind1++); f.a2 += at(s2, ind2++); }
+        }
+        if (!f.a1.empty() && f.a1.size() == f.a2.size()) frags.push_back(std::move(f));
+    }
+}
+
+// getExcisedRange (AGEaligner.cpp:156-177)
+static bool excised_range(int flag, bool rev1, const Frag &f, const Frag &nx, int &s, int &e,
+                          int add_s = 0, int add_e = 0)
+{
+    int inc1 = rev1 ? -1 : 1;
+    if (flag & AGE_INDEL_FLAG)             { s = f.end1 + inc1;  e = nx.start1 - inc1; }
+    else if (flag & AGE_TDUPLICATION_FLAG) { s = nx.start1;      e = f.end1; }
+    else if (flag & AGE_INVL_FLAG)         { s = f.end1 + inc1;  e = nx.start1; }
+    else if (flag & AGE_INVR_FLAG)         { s = f.end1;         e = nx.start1 - inc1; }
+    else return false;
+    s += inc1 * add_s;
+    e += inc1 * add_e;
+    return true;
+}
+
+// calcOutsideIdentity / calcInsideIdentity / calcIdentity (AGEaligner.cpp:392-447)
+static int outside_identity(const SeqHdr &q, int bp1, int bp2)
+{
+    if (bp1 >= bp2) return 0;
+    int n = q.len, d1 = bp1 + 1, d2 = n - bp2;
+    int n_check = d1 < d2 ? d1 : d2;   // (d2 < d1) ? d2 : d1
+    if (d2 < d1) n_check = d2; else n_check = d1;
+    int start1 = bp1 - n_check + 1;
+    for (int i = 0; i < n_check; i++) {
+        int n_same = 0, start2 = bp2 - i;
+        for (int j = i; j < n_check; j++)
+            if (same_nuc(at(q, (long)start1 + j), at(q, (long)start2 + j))) n_same++;
+            else break;
+        if (n_same == n_check - i) return n_same;
+    }
+    return 0;
+}
+
+static int inside_identity(const SeqHdr &q, int bp1, int bp2)
+{
+    if (bp1 >= bp2) return 0;
+    int n_check = (bp2 - bp1 + 1) / 2, start2 = bp2 - n_check + 1;
+    for (int i = 0; i < n_check; i++) {
+        int n_same = 0, start1 = bp1 - i;
+        for (int j = i; j < n_check; j++)
+            if (same_nuc(at(q, (long)start1 + j), at(q, (long)start2 + j))) n_same++;
+            else break;
+        if (n_same == n_check - i) return n_same;
+    }
+    return 0;
+}
+
+static int at_identity(const SeqHdr &q, int bp1, int bp2, int &left, int &right)
+{
+    if (bp1 >= bp2) return 0;
+    int n = q.len, delta = bp2 - bp1;
+    if (delta == 0) return 0;
+    int start = bp1 - 1;
+    left = right = 0;
+    while (start >= 0 && same_nuc(at(q, start), at(q, (long)start + delta))) { start--; left--; }
+    int end = bp1;
+    while (end < n && same_nuc(at(q, end), at(q, (long)end + delta))) { end++; right++; }
+    return right - left;
+}
+
+static void range_line(Out &o, const char *label, int len, int s, int e)
+{
+    o.put(label); o.num(len, 9); o.put(" nucs");
+    if (len > 0) { o.put(" ["); o.num(s); o.put(','); o.num(e); o.put(']'); }
+    o.put('\n');
+}
+
+// the two lines printed per excised region (AGEaligner.cpp:270-284 and :290-304)
+static void excised_lines(Out &o, int flag, bool rev1, bool rev2, const std::vector<Frag> &fr)
+{
+    int inc1 = rev1 ? -1 : 1, inc2 = rev2 ? -1 : 1;
+    for (size_t i = 0; i + 1 < fr.size(); i++) {
+        int s, e;
+        if (!excised_range(flag, rev1, fr[i], fr[i + 1], s, e)) continue;
+        range_line(o, " first  seq => ", std::abs(s - e - inc1), s, e);
+        s = fr[i].end2 + inc2;
+        e = fr[i + 1].start2 - inc2;
+        range_line(o, " second seq => ", std::abs(s - e - inc2), s, e);
+    }
+}
+
+// AliFragment::printAlignment (AGEaligner.hh:230-272)
+static void print_frag(Out &o, const Frag &f)
+{
+    const int WIDTH = 60, MARGIN = 9;
+    int inc1 = f.end1 < f.start1 ? -1 : 1;
+    int inc2 = f.end2 < f.start2 ? -1 : 1;
+    int n = (int)(f.a1.size() < f.a2.size() ? f.a1.size() : f.a2.size());
+    int ind1 = f.start1, ind2 = f.start2;
+    char match[WIDTH];
+    for (int i = 0; i < n; i += WIDTH) {
+        int st1 = ind1, st2 = ind2;
+        int w = n - i < WIDTH ? n - i : WIDTH;
+        const char *a1 = f.a1.data() + i, *a2 = f.a2.data() + i;
+        int nuc1 = 0, nuc2 = 0;
+        for (int j = 0; j < w; j++) {
+            if (same_nuc(a1[j], a2[j])) match[j] = '|';
+            else if (!is_gap(a1[j]) && !is_gap(a2[j])) match[j] = '.';
+            else match[j] = ' ';
+            if (!is_gap(a1[j])) { nuc1++; ind1 += inc1; }
+            if (!is_gap(a2[j])) { nuc2++; ind2 += inc2; }
+        }
+        o.put('\n');
+        if (nuc1 > 0) { o.num(st1, MARGIN); o.put(' '); o.put(a1, w); o.put(' '); o.num(ind1 - inc1); o.put('\n'); }
+        else { for (int k = 0; k <= MARGIN; k++) o.put(' '); o.put(a1, w); o.put('\n'); }
+        for (int k = 0; k <= MARGIN; k++) o.put(' ');
+        o.put(match, w); o.put('\n');
+        if (nuc2 > 0) { o.num(st2, MARGIN); o.put(' '); o.put(a2, w); o.put(' '); o.num(ind2 - inc2); o.put('\n'); }
+        else { for (int k = 0; k <= MARGIN; k++) o.put(' '); o.put(a2, w); o.put('\n'); }
+    }
+}
+
+size_t format_alignment(const age_seqview *v1, const age_seqview *v2, const age_job *job,
+                        const age_result *res, char *buf, size_t cap)
+{
+    Out o{buf, cap, 0};
+    const int flag = res->flag;
+    SeqHdr s1{v1->seq, v1->len, v1->start, v1->reverse != 0};
+    SeqHdr s2{v2->seq, v2->len, v2->start, v2->reverse != 0};
+    // _s1_rc = clone + revcom (AGEaligner.cpp:20,27; Sequence.hh:190-198); only INVL/INVR read it
+    std::string rc;
+    SeqHdr s1rc = s1;
+    if (flag & (AGE_INVL_FLAG | AGE_INVR_FLAG)) {
+        rc.resize((size_t)s1.len);
+        for (int i = 0; i < s1.len; i++) rc[(size_t)i] = complement(s1.seq[s1.len - 1 - i]);
+        s1rc.seq = rc.data();
+        s1rc.start = s1.reverse ? s1.start - (s1.len - 1) : s1.start + (s1.len - 1);
+        s1rc.reverse = !s1.reverse;
+    }
+
+    o.put("\nMATCH = ");    o.num(job->match);
+    o.put(", MISMATCH = "); o.num(job->mismatch);
+    o.put(", GAP OPEN = "); o.num(job->gap_open);
+    o.put(", GAP EXTEND = "); o.num(job->gap_extend);
+    if (flag & AGE_INDEL_FLAG)             o.put(", INDEL");
+    else if (flag & AGE_INVL_FLAG)         o.put(", INVERSION");
+    else if (flag & AGE_INVR_FLAG)         o.put(", INVERSION");
+    else if (flag & AGE_TDUPLICATION_FLAG) o.put(", TDUPLICATION");
+    o.put("\n\n");
+
+    int inc1 = s1.reverse ? -1 : 1, inc2 = s2.reverse ? -1 : 1;
+    int b1 = s1.start, b2 = s2.start;
+    int e1 = b1 + inc1 * (s1.len - 1), e2 = b2 + inc2 * (s2.len - 1);
+    int wb = calc_width(b1, b2), we = calc_width(e1, e2);
+    o.put("First  seq ["); o.num(b1, wb); o.put(','); o.num(e1, we); o.put("] => ");
+    o.num(s1.len, 9); o.put(" nucs '"); o.put(v1->name ? v1->name : ""); o.put("'\n");
+    o.put("Second seq ["); o.num(b2, wb); o.put(','); o.num(e2, we); o.put("] => ");
+    o.num(s2.len, 9); o.put(" nucs '"); o.put(v2->name ? v2->name : ""); o.put("'\n\n");
+
+    std::vector<Frag> frags;
+    build_frags(s1, s1rc, s2, flag, res->left, res->n_left, res->right, res->n_right, frags);
+    const int n_frg = (int)frags.size();
+    std::vector<int> n_ali(n_frg + 1, 0), n_id(n_frg + 1, 0), n_gap(n_frg + 1, 0);
+    for (int k = 0; k < n_frg; k++) {   // AliFragment::countAligned (AGEaligner.hh:218-228)
+        const Frag &f = frags[k];
+        for (size_t i = 0; i < f.a1.size(); i++) {
+            n_ali[k + 1]++;
+            if (same_nuc(f.a1[i], f.a2[i])) n_id[k + 1]++;
+            if (is_gap(f.a1[i]) || is_gap(f.a2[i])) n_gap[k + 1]++;
+        }
+        n_ali[0] += n_ali[k + 1]; n_id[0] += n_id[k + 1]; n_gap[0] += n_gap[k + 1];
+    }
+    int identic = 0, gap = 0;
+    if (n_ali[0] > 0) {
+        identic = (int)(100. * n_id[0] / n_ali[0] + 0.5);
+        gap     = (int)(100. * n_gap[0] / n_ali[0] + 0.5);
+    }
+    // res->score here is the _max of the printed aligner
+    int printed_max = res->used_aux ? res->aux_score : res->main_score;
+    o.put("Score:   "); o.num(printed_max, 9); o.put('\n');
+    o.put("Aligned: "); o.num(n_ali[0], 9); o.put("        nucs\n");
+    o.put("Identic: "); o.num(n_id[0], 9); o.put(" ("); o.num(identic, 3); o.put("%) nucs");
+    if (n_frg > 1) {
+        o.put(" =>");
+        for (int k = 1; k <= n_frg; k++) {
+            o.put(' '); o.num(n_id[k], 9); o.put(" (");
+            o.num((int)(100. * n_id[k] / n_ali[k] + 0.5), 3); o.put("%)");
+        }
+    }
+    o.put("\nGaps:    "); o.num(n_gap[0], 9); o.put(" ("); o.num(gap, 3); o.put("%) nucs\n\n");
+
+    if (n_ali[0] > 0) {
+        o.put("Alignment:\n");
+        o.put(" first  seq =>  ");
+        for (int k = 0; k < n_frg; k++) {
+            if (k) o.put(" EXCISED REGION ");
+            int ws = calc_width(frags[k].start1, frags[k].start2), wend = calc_width(frags[k].end1, frags[k].end2);
+            o.put('['); o.num(frags[k].start1, ws); o.put(','); o.num(frags[k].end1, wend); o.put(']');
+        }
+        o.put("\n second seq =>  ");
+        for (int k = 0; k < n_frg; k++) {
+            if (k) o.put(" EXCISED REGION ");
+            int ws = calc_width(frags[k].start1, frags[k].start2), wend = calc_width(frags[k].end1, frags[k].end2);
+            o.put('['); o.num(frags[k].start2, ws); o.put(','); o.num(frags[k].end2, wend); o.put(']');
+        }
+        o.put('\n');
+    }
+
+    if (n_frg > 1) {
+        o.put("\nEXCISED REGION(S):\n");
+        excised_lines(o, flag, s1.reverse, s2.reverse, frags);
+
+        if (res->n_bp > 1) { o.put("ALTERNATIVE REGION(S): "); o.num(res->n_bp - 1); o.put('\n'); }
+        if (res->alt_index >= 1) {
+            std::vector<Frag> alt;
+            build_frags(s1, s1rc, s2, flag, res->alt_left, res->n_alt_left, res->alt_right, res->n_alt_right, alt);
+            excised_lines(o, flag, s1.reverse, s2.reverse, alt);
+        }
+
+        o.put("\nIdentity at breakpoints: \n");
+        for (int k = 0; k + 1 < n_frg; k++) {
+            int s, e, left = 0, right = 0;
+            if (!excised_range(flag, s1.reverse, frags[k], frags[k + 1], s, e, 0, 1)) continue;
+            int bp1 = inc1 * (s - s1.start), bp2 = inc1 * (e - s1.start);
+            int n_hom = at_identity(s1, bp1, bp2, left, right);
+            o.put(" first  seq => "); o.num(n_hom, 9); o.put(" nucs");
+            if (n_hom > 0) {
+                o.put(" ["); o.num(s + inc1 * left); o.put(','); o.num(s + inc1 * (right - 1)); o.put("] to");
+                o.put(" ["); o.num(e + inc1 * left); o.put(','); o.num(e + inc1 * (right - 1)); o.put(']');
+            }
+            o.put('\n');
+            s = frags[k].end2 + inc2; e = frags[k + 1].start2;
+            bp1 = inc2 * (s - s2.start); bp2 = inc2 * (e - s2.start);
+            left = right = 0;
+            n_hom = at_identity(s2, bp1, bp2, left, right);
+            o.put(" second seq => "); o.num(n_hom, 9); o.put(" nucs");
+            if (n_hom > 0) {
+                o.put(" ["); o.num(s + inc2 * left); o.put(','); o.num(s + inc2 * (right - 1)); o.put("] to");
+                o.put(" ["); o.num(e + inc2 * left); o.put(','); o.num(e + inc2 * (right - 1)); o.put(']');
+            }
+            o.put('\n');
+        }
+
+        o.put("Identity outside breakpoints: \n");
+        for (int k = 0; k + 1 < n_frg; k++) {
+            int s, e;
+            if (!excised_range(flag, s1.reverse, frags[k], frags[k + 1], s, e, -1, 1)) continue;
+            int bp1 = inc1 * (s - s1.start), bp2 = inc1 * (e - s1.start);
+            int n_hom = outside_identity(s1, bp1, bp2);
+            o.put(" first  seq => "); o.num(n_hom, 9); o.put(" nucs");
+            if (n_hom > 0) {
+                o.put(" ["); o.num(s - inc1 * (n_hom - 1)); o.put(','); o.num(s); o.put("] to");
+                o.put(" ["); o.num(e); o.put(','); o.num(e + inc1 * (n_hom - 1)); o.put(']');
+            }
+            o.put('\n');
+            s = frags[k].end2; e = frags[k + 1].start2;
+            bp1 = inc2 * (s - s2.start); bp2 = inc2 * (e - s2.start);
+            n_hom = outside_identity(s2, bp1, bp2);
+            o.put(" second seq => "); o.num(n_hom, 9); o.put(" nucs");
+            if (n_hom > 0) {
+                o.put(" ["); o.num(s - inc2 * (n_hom - 1)); o.put(','); o.num(s); o.put("] to");
+                o.put(" ["); o.num(e); o.put(','); o.num(e + inc2 * (n_hom - 1)); o.put(']');
+            }
+            o.put('\n');
+        }
+
+        o.put("Identity inside breakpoints: \n");
+        for (int k = 0; k + 1 < n_frg; k++) {
+            int s, e;
+            if (!excised_range(flag, s1.reverse, frags[k], frags[k + 1], s, e)) continue;
+            int bp1 = inc1 * (s - s1.start), bp2 = inc1 * (e - s1.start);
+            int n_hom = inside_identity(s1, bp1, bp2);
+            o.put(" first  seq => "); o.num(n_hom, 9); o.put(" nucs");
+            if (n_hom > 0) {
+                o.put(" ["); o.num(s); o.put(','); o.num(s + inc1 * (n_hom - 1)); o.put("] to");
+                o.put(" ["); o.num(e - inc1 * (n_hom - 1)); o.put(','); o.num(e); o.put(']');
+            }
+            o.put('\n');
+            s = frags[k].end2 + inc2; e = frags[k + 1].start2 - inc2;
+            bp1 = inc2 * (s - s2.start); bp2 = inc2 * (e - s2.start);
+            n_hom = inside_identity(s2, bp1, bp2);
+            o.put(" second seq => "); o.num(n_hom, 9); o.put(" nucs");
+            if (n_hom > 0) {
+                o.put(" ["); o.num(s); o.put(','); o.num(s + inc2 * (n_hom - 1)); o.put("] to");
+                o.put(" ["); o.num(e - inc2 * (n_hom - 1)); o.put(','); o.num(e); o.put(']');
+            }
+            o.put('\n');
+        }
+    }
+
+    for (int k = 0; k < n_frg; k++) {
+        if (k) o.put("\nEXCISED REGION\n");
+        print_frag(o, frags[k]);
+    }
+    if (o.n < cap) buf[o.n] = '\0'; else if (cap) buf[cap - 1] = '\0';
+    return o.n;
+}
+
+} // namespace age
+
+extern "C" size_t age_format_alignment(const age_seqview *s1, const age_seqview *s2, const age_job *job,
+                                       const age_result *res, char *buf, size_t cap)
+{
+    if (!s1 || !s2 || !job || !res) return 0;
+    return age::format_alignment(s1, s2, job, res, buf, cap);
+}
+
+extern "C" void age_revcom(const char *in, int32_t n, char *out)
+{
+    for (int32_t i = 0; i < n; i++) out[i] = age::complement(in[n - 1 - i]);
+}
+
+extern "C" int age_subst_score(char a, char b, int match, int mismatch)
+{   // Scorer.hh:24-39
+    if (age::complement(a) == a || age::complement(b) == b) return 0;
+    return age::same_nuc(a, b) ? match : mismatch;
+}

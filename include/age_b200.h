@@ -1,0 +1,124 @@
+/*
+ * age_b200.h -- C ABI of the B200-native AGE (Alignment with Gap Excision) realigner.
+ *
+ * This is the drop-in boundary for the hot path of bioinformatics-centre/AsmVar's
+ * src/AsmvarAGE.  The reference has no FFI of its own; the path sits behind the C++ class
+ * AGEaligner and the age_align process.  Every entry point below names the reference
+ * interface it replaces (paths relative to the reference root, src/AsmvarAGE/src/...).
+ *
+ * Plain C, plain pointers and sizes, no C++ / torch types.  All CUDA work happens behind
+ * this boundary in hand-written sm_100a kernels; there is no CPU fallback: if no CUDA
+ * device is usable, age_create() fails and age_align_batch() returns an error.
+ */
+#ifndef AGE_B200_H
+#define AGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Alignment modes -- the values of AGEaligner::*_FLAG (AGEaligner.hh:72-76). */
+#define AGE_INDEL_FLAG        0x01
+#define AGE_TDUPLICATION_FLAG 0x02
+#define AGE_INVERSION_FLAG    0x04
+#define AGE_INVR_FLAG         0x08
+#define AGE_INVL_FLAG         0x10
+#define AGE_MAX_BPOINTS       100   /* AGEaligner.hh:94 */
+
+/* Status codes of age_result.status */
+#define AGE_OK              0
+#define AGE_NOT_ALIGNED     1   /* AGEaligner::align() would return false (AGEaligner.cpp:68-69) */
+#define AGE_ERR_RANGE      -1   /* scores do not fit the 16-bit DP range */
+#define AGE_ERR_CUDA       -2
+#define AGE_ERR_ARG        -3
+
+typedef struct age_ctx age_ctx;
+
+/* One AGEaligner(s1,s2) + align(scr,flag) call (AGEaligner.hh:101-103, AGEaligner.cpp:16-42,65-147;
+ * scoring = Scorer(match,mismatch,gap_open,gap_extend), Scorer.hh:24-39).
+ * seq1/seq2 are the nucleotide strings exactly as the reference's Sequence objects hold them
+ * after substr()/revcom() (Sequence.hh:190-215); case is preserved, any byte < 0x80 is allowed. */
+typedef struct {
+    const char *seq1; int32_t len1;     /* first sequence  = target / reference window */
+    const char *seq2; int32_t len2;     /* second sequence = query / assembly contig    */
+    int32_t flag;                       /* exactly one AGE_*_FLAG                       */
+    int16_t match, mismatch, gap_open, gap_extend;
+} age_job;
+
+/* A gap-free diagonal run; 1-based positions in seq1 / seq2 (class Block, AGEaligner.hh:128-177). */
+typedef struct { int32_t start1, start2, length; } age_block;
+
+/* Everything AGEaligner::score() / printAlignment() need (AGEaligner.cpp:149-154,179-380). */
+typedef struct {
+    int32_t status;
+    int32_t score;          /* AGEaligner::score(): the aux (INVR) score only if strictly greater */
+    int32_t flag;           /* single mode of the aligner whose record is printed (INVL/INVR for -inv) */
+    int32_t used_aux;       /* 1 if the auxiliary INVR aligner is the printed one (AGEaligner.cpp:181-184) */
+    int32_t main_score, aux_score;      /* _max of the main / auxiliary aligner (aux_score = -1 if none) */
+    int32_t n_bp;                       /* _n_bpoints of the printed aligner */
+    int32_t bp[AGE_MAX_BPOINTS][4];     /* _bpoints: lg1, lg2, rg1, rg2 (AGEaligner.cpp:658-661) */
+    int32_t alt_index;                  /* bpoint shown under ALTERNATIVE REGION(S), -1 if none (AGEaligner.cpp:287-306) */
+    int32_t n_left, n_right;            /* findLeftBlocks / findRightBlocks of bpoint 0 (AGEaligner.cpp:752-860) */
+    int32_t n_alt_left, n_alt_right;    /* the same for bpoint alt_index */
+    const age_block *left, *right, *alt_left, *alt_right;  /* owned by the ctx, valid until the next batch call */
+} age_result;
+
+/* A Sequence header: name, 1-based start coordinate and orientation (Sequence.hh:22-31). */
+typedef struct {
+    const char *seq; int32_t len;
+    const char *name;
+    int32_t start;
+    int32_t reverse;
+} age_seqview;
+
+/* Device timing / accounting of the last age_align_batch call. */
+typedef struct {
+    double   kernel_ms;        /* CUDA-event time of all kernels of the batch (on the ctx stream) */
+    double   fill_ms;          /* time of the DP sweep kernels alone */
+    double   h2d_ms, d2h_ms;
+    uint64_t cell_updates;     /* sum over executed aligners of 2*len1*len2 */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t launches;         /* kernels launched */
+    uint64_t fill_launches;
+    uint64_t n_aligners;       /* single-mode aligner runs executed (a -inv job is two) */
+} age_stats;
+
+/* Replaces: process start-up of age_align (age_align.cpp:194-229).  device_ids may be NULL
+ * (= device 0); n_dev > 1 shards batches over several GPUs with no collective (host gather only). */
+age_ctx *age_create(const int *device_ids, int n_dev);
+void     age_destroy(age_ctx *ctx);
+const char *age_last_error(const age_ctx *ctx);   /* ctx may be NULL: error of the failed age_create */
+
+/* Replaces: the serial candidate loop of age_align.cpp:231-293 / VarUnit.cpp:271-299 --
+ * n independent AGEaligner::align() calls executed as length-binned GPU batches.
+ * jobs and out are HOST arrays; returns 0 or a negative AGE_ERR_* (per-job status in out[i].status). */
+int age_align_batch(age_ctx *ctx, const age_job *jobs, size_t n, age_result *out);
+
+/* Split form of age_align_batch for measurement with inputs resident in HBM:
+ * stage = host packing + host->device copy; run = kernels only (repeatable); fetch = device->host + result assembly. */
+int age_stage(age_ctx *ctx, const age_job *jobs, size_t n);
+int age_run_staged(age_ctx *ctx);
+int age_fetch(age_ctx *ctx, age_result *out, size_t n);
+
+int age_get_stats(const age_ctx *ctx, age_stats *st);
+
+/* Replaces: AGEaligner::printAlignment() (AGEaligner.cpp:179-380) incl. AliFragment::printAlignment
+ * (AGEaligner.hh:230-272).  Writes the record (starting with the blank line before "MATCH = ...") into
+ * buf; returns the number of bytes needed (excluding the terminating NUL); if that is >= cap the output
+ * was truncated.  s1/s2 are the headers of job->seq1/seq2. */
+size_t age_format_alignment(const age_seqview *s1, const age_seqview *s2, const age_job *job,
+                            const age_result *res, char *buf, size_t cap);
+
+/* Replaces: Sequence::revcom() string part (Sequence.hh:195-197) and Scorer lookup (Scorer.hh:24-39). */
+void age_revcom(const char *in, int32_t n, char *out);
+int  age_subst_score(char a, char b, int match, int mismatch);
+
+const char *age_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGE_B200_H */

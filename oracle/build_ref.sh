@@ -1,0 +1,53 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- not part of the shipped product path.
+#
+# Builds the *unmodified* reference AGE (bioinformatics-centre/AsmVar, src/AsmvarAGE)
+# from the sources where they lie under /root/reference into oracle/_ref/ (git-ignored).
+# No reference source is copied into the repository: sources are staged in a scratch
+# directory under oracle/_ref/stage, compiled, and the stage is deleted again.
+#
+# One build-only patch is applied to the staged copy: `traceBackMaxima` is declared
+# `int` but has no return statement (AGEaligner.cpp:615-642); g++ >= 8 emits `ud2`
+# there and the binary dies with SIGILL.  We append `return 0;` (the caller ignores
+# the value, AGEaligner.cpp:563,597).
+#
+# Outputs:
+#   oracle/_ref/age_align_ref        batch CLI (src/AsmvarAGE/src/age_align.cpp),  -O2, no OpenMP
+#   oracle/_ref/age_align_ref_orig   original CLI (src/AsmvarAGE/src/Trash/age_align.cpp), -O2, no OpenMP
+#   oracle/_ref/age_align_ref_omp    batch CLI with -fopenmp -DOMP (2 threads / alignment, as shipped)
+set -euo pipefail
+REF=${AGE_REFERENCE_ROOT:-/root/reference}
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/_ref"
+SRC="$REF/src/AsmvarAGE/src"
+if [ ! -d "$SRC" ]; then
+  echo "build_ref.sh: reference sources not found at $SRC (fine on the GPU box: prebuilt oracle/_ref is used)" >&2
+  exit 0
+fi
+mkdir -p "$OUT"
+STAGE="$OUT/stage"
+rm -rf "$STAGE"; mkdir -p "$STAGE/batch" "$STAGE/orig"
+patch_tbm() {  # insert 'return 0;' before the closing brace of traceBackMaxima
+  python3 - "$1" <<'PY'
+import re, sys
+p = sys.argv[1]
+s = open(p).read()
+i = s.index('int AGEaligner::traceBackMaxima')
+j = s.index('int AGEaligner::addBpoints')
+body = s[i:j]
+k = body.rindex('}')
+body = body[:k] + '\treturn 0;\n' + body[k:]
+open(p, 'w').write(s[:i] + body + s[j:])
+PY
+}
+cp "$SRC"/{AGEaligner.cpp,AGEaligner.hh,Sequence.hh,Scorer.hh,age_align.cpp,Join.cpp,Join.h} "$STAGE/batch/"
+cp "$SRC"/Backup/{Fa.h,Region.h,gzstream.cpp,gzstream.h} "$STAGE/batch/"
+cp "$SRC"/Trash/{AGEaligner.cpp,AGEaligner.hh,Sequence.hh,Scorer.hh,age_align.cpp} "$STAGE/orig/"
+patch_tbm "$STAGE/batch/AGEaligner.cpp"
+patch_tbm "$STAGE/orig/AGEaligner.cpp"
+FLAGS='-DAGE_VERSION="v0.8" -DAGE_TIME -w -O2'
+( cd "$STAGE/batch" && g++ $FLAGS AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref" )
+( cd "$STAGE/batch" && g++ $FLAGS -fopenmp -DOMP AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref_omp" )
+( cd "$STAGE/orig"  && g++ $FLAGS AGEaligner.cpp age_align.cpp -o "$OUT/age_align_ref_orig" )
+rm -rf "$STAGE"
+echo "built: $(ls "$OUT")"
