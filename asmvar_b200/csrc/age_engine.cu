@@ -1,0 +1,631 @@
+// age_engine.cu -- host side of the C ABI declared in include/age_b200.h.
+//
+// Replaces the serial candidate loop of the reference (age_align.cpp:231-293, VarUnit.cpp:271-299) with
+// batched GPU execution: jobs are validated, expanded into single-mode aligners (-inv = INVL + auxiliary
+// INVR, AGEaligner.cpp:72-77,136-144), paired by shape, packed, swept and enumerated on the device(s), and
+// the compact results (score, breakpoints, diagonal blocks) are gathered on the host in input order.
+// There is no CPU implementation of the alignment here: without a usable CUDA device age_create() fails.
+#include "age_b200.h"
+#include "age_device.cuh"
+#include "age_host.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace age;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// nucleotide code of the reference's Scorer (Scorer.hh:24-39, Sequence.hh:138-150,182-188):
+// A C G T U score among themselves (U only matches U), everything else scores 0 against everything.
+inline int nuc_code(char ch)
+{
+    switch (ch) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    case 'U': case 'u': return 4;
+    default: return 5;
+    }
+}
+
+struct Arena {
+    char *ptr = nullptr; size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; cap = 0;
+        if (cudaMalloc(&ptr, n) != cudaSuccess) { cudaGetLastError(); return false; }
+        cap = n; return true;
+    }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
+};
+struct PinnedBuf {
+    char *ptr = nullptr; size_t cap = 0;
+    bool ensure(size_t n) {
+        if (n <= cap) return true;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr; cap = 0;
+        if (cudaMallocHost(&ptr, n) != cudaSuccess) { cudaGetLastError(); return false; }
+        cap = n; return true;
+    }
+    void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
+};
+
+struct Aligner {                 // one single-mode AGEaligner run
+    int job, role;               // role 0 = main, 1 = auxiliary INVR aligner of an -inv job
+    int flag;
+    int out;                     // index into the AlignerOut array of its sub-batch
+};
+
+struct HostPair {
+    int a[2];                    // aligner indices (second may be -1)
+    int len1, len2, nstrips, P;
+    size_t in_bytes, scratch_bytes;
+    double cells;
+};
+
+struct Device {
+    int id = 0;
+    cudaStream_t st = nullptr;
+    Arena in, scratch, outbuf;
+    PinnedBuf hin, hout;
+    cudaEvent_t ev[6] = {};
+    // the sub-batch currently resident on this device
+    std::vector<int> pair_ids;
+    std::vector<PairTask> tasks;
+    int n_outs = 0, pool_cap = 0;
+    size_t in_bytes = 0;
+    std::string err;
+};
+
+} // namespace
+
+struct age_ctx {
+    std::vector<Device> devs;
+    std::string err;
+    age_stats stats{};
+    // plan of the current batch
+    const age_job *jobs = nullptr; size_t n_jobs = 0;
+    std::vector<int> job_status;
+    std::vector<Aligner> aligners;
+    std::vector<HostPair> pairs;
+    std::vector<AlignerOut> outs;                 // per aligner (global index)
+    std::vector<std::vector<age_block>> blocks;   // per aligner: left | right | alt_left | alt_right
+    std::vector<std::string> rc1;                 // per job: revcom of seq1 when an inversion mode needs it
+    bool staged = false;
+    int host_threads = 1;
+};
+
+namespace {
+
+template <class F> void parallel_for(int nthreads, size_t n, F f)
+{
+    if (nthreads <= 1 || n < 64) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t)
+        th.emplace_back([&] { for (;;) { size_t i = next.fetch_add(16); if (i >= n) break; for (size_t k = i; k < std::min(n, i + 16); ++k) f(k); } });
+    for (auto &x : th) x.join();
+}
+
+bool single_mode(int flag) { return flag == F_INDEL || flag == F_TDUP || flag == F_INVL || flag == F_INVR; }
+
+// 16-bit range of the packed (2*score + tag) representation; see DESIGN.md "score range"
+int check_range(const age_job &j)
+{
+    const int m = j.match, mm = j.mismatch, go = j.gap_open, ge = j.gap_extend;
+    if (m > 63 || m < -63 || mm > 63 || mm < -63) return AGE_ERR_RANGE;
+    if (go >= 0 || ge >= 0 || go < -4000 || ge < -4000) return AGE_ERR_RANGE;
+    const long k = 2L * (ge - go) - 1;
+    const long kabs = k < 0 ? -k : k;
+    const long top = 2L * std::max(m, 0) * std::min(j.len1, j.len2);
+    if (top + kabs + 2L * (-go) + 2L * (-ge) + 8 > 32767) return AGE_ERR_RANGE;
+    return AGE_OK;
+}
+
+void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
+{
+    ctx->jobs = jobs; ctx->n_jobs = n;
+    ctx->job_status.assign(n, AGE_OK);
+    ctx->aligners.clear(); ctx->pairs.clear();
+    ctx->rc1.assign(n, std::string());
+    for (size_t i = 0; i < n; ++i) {
+        const age_job &j = jobs[i];
+        int st = AGE_OK;
+        const bool inv = j.flag == F_INV;
+        if (!j.seq1 || !j.seq2 || j.len1 <= 0 || j.len2 <= 0) st = AGE_NOT_ALIGNED;        // AGEaligner.cpp:68
+        else if (!inv && !single_mode(j.flag)) st = AGE_NOT_ALIGNED;                         // AGEaligner.cpp:69
+        else st = check_range(j);
+        ctx->job_status[i] = st;
+        if (st != AGE_OK) continue;
+        if (inv) {
+            ctx->aligners.push_back({(int)i, 0, F_INVL, -1});
+            ctx->aligners.push_back({(int)i, 1, F_INVR, -1});
+        } else ctx->aligners.push_back({(int)i, 0, j.flag, -1});
+    }
+    // revcom of seq1 for the inversion modes (AGEaligner.cpp:27, :1000, :1050)
+    parallel_for(ctx->host_threads, n, [&](size_t i) {
+        if (ctx->job_status[i] != AGE_OK) return;
+        const age_job &j = jobs[i];
+        if (j.flag & (F_INV | F_INVL | F_INVR)) {
+            ctx->rc1[i].resize(j.len1);
+            age_revcom(j.seq1, j.len1, &ctx->rc1[i][0]);
+        }
+    });
+    // pair aligners of identical shape
+    std::vector<int> order(ctx->aligners.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    struct Key { int32_t v[6]; };
+    auto key = [&](int a) {
+        const age_job &j = jobs[ctx->aligners[a].job];
+        return Key{{j.len1, j.len2, j.match, j.mismatch, j.gap_open, j.gap_extend}};
+    };
+    auto less = [&](int x, int y) { const Key a = key(x), b = key(y); return std::lexicographical_compare(a.v, a.v + 6, b.v, b.v + 6); };
+    auto same = [&](int x, int y) { return memcmp(key(x).v, key(y).v, sizeof(Key)) == 0; };
+    std::stable_sort(order.begin(), order.end(), less);
+    for (size_t i = 0; i < order.size();) {
+        HostPair hp{};
+        hp.a[0] = order[i]; hp.a[1] = -1;
+        if (i + 1 < order.size() && same(order[i + 1], order[i])) { hp.a[1] = order[i + 1]; i += 2; } else i += 1;
+        const age_job &j = jobs[ctx->aligners[hp.a[0]].job];
+        hp.len1 = j.len1; hp.len2 = j.len2;
+        hp.nstrips = (j.len2 + STRIP - 1) / STRIP; hp.P = hp.nstrips * STRIP;
+        const size_t cols = (size_t)j.len1 + 2;
+        hp.in_bytes = align_up(cols * 4, 16) * 2 + align_up((size_t)hp.P * 8, 16) + align_up((size_t)hp.P, 16);
+        hp.scratch_bytes = 2 * align_up(cols * hp.P * 4, 256) + 2 * align_up(cols * (hp.P / RPT) * 8, 256) +
+                           2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256) + align_up(((size_t)j.len2 + 2) * 4, 256);
+        hp.cells = (double)j.len1 * j.len2;
+        ctx->pairs.push_back(hp);
+    }
+    ctx->outs.assign(ctx->aligners.size(), AlignerOut{});
+    ctx->blocks.assign(ctx->aligners.size(), {});
+}
+
+// per-column PRMT selector of a pair (see age_device.cuh) for the strings xa / xb (either may be null)
+void fill_xsel(uint32_t *dst, int len1, const char *xa, const char *xb)
+{
+    dst[0] = 0; dst[len1 + 1] = 0;
+    for (int c = 1; c <= len1; ++c) {
+        const int a = xa ? nuc_code(xa[c - 1]) : 5, b = xb ? nuc_code(xb[c - 1]) : 5;
+        uint32_t w;
+        if (a < 4 && b < 4) w = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + b) << 8) | ((uint32_t)((4 + b) | 8) << 12);
+        else w = XSEL_SPECIAL | ((uint32_t)a << 20) | ((uint32_t)b << 24);
+        dst[c] = w;
+    }
+}
+
+uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+// pack the inputs of pair `pi` into host memory at `h`, device addresses based at `d`
+void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
+{
+    const HostPair &hp = ctx->pairs[pi];
+    const size_t cols = (size_t)hp.len1 + 2;
+    const size_t xs = align_up(cols * 4, 16);
+    uint32_t *xf = (uint32_t *)h, *xr = (uint32_t *)(h + xs);
+    uint2 *ytab = (uint2 *)(h + 2 * xs);
+    uint8_t *ycode = (uint8_t *)(h + 2 * xs + align_up((size_t)hp.P * 8, 16));
+    memset(&T, 0, sizeof(T));
+    T.len1 = hp.len1; T.len2 = hp.len2; T.nstrips = hp.nstrips; T.P = hp.P;
+    const char *xfwd[2] = {nullptr, nullptr}, *xrev[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr};
+    int sc[2][4] = {{1, -1, -1, -1}, {1, -1, -1, -1}};
+    for (int k = 0; k < 2; ++k) {
+        T.flag[k] = 0; T.out[k] = -1;
+        if (hp.a[k] < 0) continue;
+        const Aligner &al = ctx->aligners[hp.a[k]];
+        const age_job &j = ctx->jobs[al.job];
+        T.flag[k] = al.flag; T.out[k] = al.out;
+        const char *rc = ctx->rc1[al.job].empty() ? nullptr : ctx->rc1[al.job].data();
+        xfwd[k] = (al.flag & F_INVR) ? rc : j.seq1;           // AGEaligner.cpp:1000
+        xrev[k] = (al.flag & F_INVL) ? rc : j.seq1;           // AGEaligner.cpp:1050
+        y[k] = j.seq2;
+        sc[k][0] = j.match; sc[k][1] = j.mismatch; sc[k][2] = j.gap_open; sc[k][3] = j.gap_extend;
+    }
+    if (hp.a[1] < 0) { for (int q = 0; q < 4; ++q) sc[1][q] = sc[0][q]; }
+    fill_xsel(xf, hp.len1, xfwd[0], xfwd[1]);
+    const bool same = xfwd[0] == xrev[0] && xfwd[1] == xrev[1];
+    if (!same) fill_xsel(xr, hp.len1, xrev[0], xrev[1]);
+    for (int q = 0; q < hp.P; ++q) {
+        uint32_t tab[2] = {0, 0}; int code[2] = {5, 5};
+        for (int k = 0; k < 2; ++k) {
+            if (!y[k] || q >= hp.len2) continue;
+            const int yc = nuc_code(y[k][q]);
+            code[k] = yc;
+            if (yc >= 5) continue;
+            for (int x = 0; x < 4; ++x) {
+                const int s2 = 2 * (x == yc ? sc[k][0] : sc[k][1]);
+                tab[k] |= ((uint32_t)s2 & 0xFFu) << (8 * x);
+            }
+        }
+        ytab[q] = make_uint2(tab[0], tab[1]);
+        ycode[q] = (uint8_t)(code[0] | (code[1] << 4));
+    }
+    int c0x[2], kabs[2], flip[2], gb[2];
+    for (int k = 0; k < 2; ++k) {
+        const int go = sc[k][2], ge = sc[k][3];
+        const int K = 2 * (ge - go) - 1;
+        gb[k] = 2 * go + 1;
+        if (K >= 0) { flip[k] = 0; kabs[k] = K; c0x[k] = 2 * go + 1; }
+        else        { flip[k] = 1; kabs[k] = -K; c0x[k] = 2 * ge; }
+    }
+    // kabs multiplies a packed 0/1 word, so both halves share it: build_plan only pairs aligners with
+    // identical scoring
+    T.c0x = pack2(c0x[0], c0x[1]); T.kabs = (uint32_t)kabs[0]; T.flip = pack2(flip[0], flip[1]); T.gborder = pack2(gb[0], gb[1]);
+    T.m2 = pack2(2 * sc[0][0], 2 * sc[1][0]); T.mm2 = pack2(2 * sc[0][1], 2 * sc[1][1]);
+    T.xsel_f = (const uint32_t *)d;
+    T.xsel_r = same ? T.xsel_f : (const uint32_t *)(d + xs);
+    T.ytab = (const uint2 *)(d + 2 * xs);
+    T.ycode = (const uint8_t *)(d + 2 * xs + align_up((size_t)hp.P * 8, 16));
+}
+
+void assign_scratch(const HostPair &hp, char *s, PairTask &T)
+{
+    const size_t cols = (size_t)hp.len1 + 2;
+    const size_t msz = align_up(cols * hp.P * 4, 256), tsz = align_up(cols * (hp.P / RPT) * 8, 256);
+    const size_t bsz = align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256);
+    T.Mf = (uint32_t *)s; s += msz;
+    T.Mr = (uint32_t *)s; s += msz;
+    T.Tf = (uint2 *)s; s += tsz;
+    T.Tr = (uint2 *)s; s += tsz;
+    T.bnd_f = (uint4 *)s; s += bsz;
+    T.bnd_r = (uint4 *)s; s += bsz;
+    T.rowmask = (uint32_t *)s;
+}
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
+
+// stage one sub-batch (pair ids) on a device: pack, copy inputs, lay out scratch
+bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids)
+{
+    CK(cudaSetDevice(dev.id));
+    dev.pair_ids = pair_ids;
+    const size_t np = pair_ids.size();
+    dev.tasks.assign(np, PairTask{});
+    std::vector<size_t> in_off(np + 1, 0), sc_off(np + 1, 0);
+    int n_outs = 0;
+    for (size_t i = 0; i < np; ++i) {
+        HostPair &hp = ctx->pairs[pair_ids[i]];
+        in_off[i + 1] = in_off[i] + hp.in_bytes;
+        sc_off[i + 1] = sc_off[i] + hp.scratch_bytes;
+        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) ctx->aligners[hp.a[k]].out = n_outs++;
+    }
+    dev.n_outs = n_outs;
+    const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
+    dev.in_bytes = task_bytes + in_off[np];
+    if (!dev.hin.ensure(dev.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
+    if (!dev.in.ensure(dev.in_bytes)) { dev.err = "device allocation failed (inputs)"; return false; }
+    if (!dev.scratch.ensure(sc_off[np] + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
+    dev.pool_cap = n_outs * 96 + 4096;
+    const size_t out_bytes = align_up((size_t)n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
+    if (!dev.outbuf.ensure(out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
+    if (!dev.hout.ensure(out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
+    parallel_for(ctx->host_threads, np, [&](size_t i) {
+        pack_pair(ctx, pair_ids[i], dev.hin.ptr + task_bytes + in_off[i], dev.in.ptr + task_bytes + in_off[i], dev.tasks[i]);
+        assign_scratch(ctx->pairs[pair_ids[i]], dev.scratch.ptr + sc_off[i], dev.tasks[i]);
+    });
+    memcpy(dev.hin.ptr, dev.tasks.data(), np * sizeof(PairTask));
+    CK(cudaEventRecord(dev.ev[0], dev.st));
+    CK(cudaMemcpyAsync(dev.in.ptr, dev.hin.ptr, dev.in_bytes, cudaMemcpyHostToDevice, dev.st));
+    CK(cudaEventRecord(dev.ev[1], dev.st));
+    return true;
+}
+
+struct OutLayout { AlignerOut *outs; Block *pool; int32_t *counters; };
+OutLayout out_layout(Device &dev, char *base)
+{
+    OutLayout L;
+    L.outs = (AlignerOut *)base;
+    L.pool = (Block *)(base + align_up((size_t)dev.n_outs * sizeof(AlignerOut), 256));
+    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)dev.pool_cap * sizeof(Block), 256));
+    return L;
+}
+
+bool run_on_device(age_ctx *, Device &dev)
+{
+    CK(cudaSetDevice(dev.id));
+    const int np = (int)dev.tasks.size();
+    OutLayout L = out_layout(dev, dev.outbuf.ptr);
+    CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
+    CK(cudaEventRecord(dev.ev[2], dev.st));
+    launch_sweeps((const PairTask *)dev.in.ptr, np, L.counters + 0, dev.st);
+    CK(cudaEventRecord(dev.ev[3], dev.st));
+    Pass2Params p{};
+    p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = np; p.outs = L.outs;
+    p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 1;
+    launch_pass2(p, dev.st);
+    CK(cudaEventRecord(dev.ev[4], dev.st));
+    CK(cudaGetLastError());
+    return true;
+}
+
+bool fetch_from_device(age_ctx *ctx, Device &dev)
+{
+    CK(cudaSetDevice(dev.id));
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        const size_t out_bytes = align_up((size_t)dev.n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
+        CK(cudaMemcpyAsync(dev.hout.ptr, dev.outbuf.ptr, out_bytes, cudaMemcpyDeviceToHost, dev.st));
+        CK(cudaEventRecord(dev.ev[5], dev.st));
+        CK(cudaStreamSynchronize(dev.st));
+        OutLayout H = out_layout(dev, dev.hout.ptr);
+        if (H.counters[2] <= dev.pool_cap) {
+            for (size_t i = 0; i < dev.pair_ids.size(); ++i) {
+                const HostPair &hp = ctx->pairs[dev.pair_ids[i]];
+                for (int k = 0; k < 2; ++k) {
+                    if (hp.a[k] < 0) continue;
+                    const Aligner &al = ctx->aligners[hp.a[k]];
+                    const AlignerOut &o = H.outs[al.out];
+                    ctx->outs[hp.a[k]] = o;
+                    std::vector<age_block> &b = ctx->blocks[hp.a[k]];
+                    b.clear();
+                    for (int q = 0; q < 4; ++q)
+                        for (int x = 0; x < o.n_blk[q]; ++x) {
+                            const Block &s = H.pool[o.blk_off[q] + x];
+                            b.push_back(age_block{s.start1, s.start2, s.length});
+                        }
+                }
+            }
+            ctx->stats.d2h_bytes += out_bytes;
+            return true;
+        }
+        // block pool overflow: enlarge and repeat pass 2 (the sweep outputs are still resident)
+        dev.pool_cap = H.counters[2] + 4096;
+        const size_t nb = align_up((size_t)dev.n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
+        if (!dev.outbuf.ensure(nb) || !dev.hout.ensure(nb)) { dev.err = "allocation failed (block pool)"; return false; }
+        OutLayout L = out_layout(dev, dev.outbuf.ptr);
+        CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
+        Pass2Params p{};
+        p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = (int)dev.tasks.size(); p.outs = L.outs;
+        p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 1;
+        launch_pass2(p, dev.st);
+    }
+    dev.err = "block pool overflow";
+    return false;
+}
+
+void add_timing(age_ctx *ctx, Device &dev)
+{
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, dev.ev[0], dev.ev[1]) == cudaSuccess) ctx->stats.h2d_ms += ms;
+    if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) ctx->stats.fill_ms += ms;
+    if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) ctx->stats.kernel_ms += ms;
+    if (cudaEventElapsedTime(&ms, dev.ev[4], dev.ev[5]) == cudaSuccess) ctx->stats.d2h_ms += ms;
+}
+
+// split the pairs of the plan into per-device sub-batches that fit the scratch budget
+std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
+{
+    const int nd = (int)ctx->devs.size();
+    std::vector<std::vector<std::vector<int>>> res(nd);
+    std::vector<size_t> budget(nd);
+    for (int d = 0; d < nd; ++d) {
+        cudaSetDevice(ctx->devs[d].id);
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap;
+        budget[d] = (size_t)(0.80 * (double)fr);
+    }
+    // longest-processing-time-first deal across devices
+    std::vector<int> order(ctx->pairs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::vector<std::vector<int>> per_dev(nd);
+    if (nd == 1) per_dev[0] = order;
+    else {
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->pairs[a].cells > ctx->pairs[b].cells; });
+        std::vector<double> load(nd, 0.0);
+        for (int pi : order) {
+            int best = 0;
+            for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
+            per_dev[best].push_back(pi); load[best] += ctx->pairs[pi].cells;
+        }
+        for (auto &v : per_dev) std::sort(v.begin(), v.end());
+    }
+    for (int d = 0; d < nd; ++d) {
+        std::vector<int> cur; size_t used = 0;
+        for (int pi : per_dev[d]) {
+            const size_t need = ctx->pairs[pi].scratch_bytes + ctx->pairs[pi].in_bytes + 4096;
+            if (!cur.empty() && used + need > budget[d]) { res[d].push_back(cur); cur.clear(); used = 0; }
+            cur.push_back(pi); used += need;
+        }
+        if (!cur.empty()) res[d].push_back(cur);
+    }
+    return res;
+}
+
+void account(age_ctx *ctx)
+{
+    ctx->stats.n_aligners += ctx->aligners.size();
+    for (const HostPair &hp : ctx->pairs)
+        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) ctx->stats.cell_updates += (uint64_t)(2.0 * hp.cells);
+}
+
+void assemble(age_ctx *ctx, age_result *out, size_t n)
+{
+    std::vector<int> main_of(n, -1), aux_of(n, -1);
+    for (size_t a = 0; a < ctx->aligners.size(); ++a) {
+        const Aligner &al = ctx->aligners[a];
+        (al.role ? aux_of : main_of)[al.job] = (int)a;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        age_result &r = out[i];
+        memset(&r, 0, sizeof(r));
+        r.status = ctx->job_status[i];
+        r.alt_index = -1; r.aux_score = -1;
+        if (r.status != AGE_OK) continue;
+        const int m = main_of[i], x = aux_of[i];
+        const AlignerOut &om = ctx->outs[m];
+        r.main_score = om.score;
+        int pick = m;
+        if (x >= 0) {
+            r.aux_score = ctx->outs[x].score;
+            if (ctx->outs[x].score > om.score) { pick = x; r.used_aux = 1; }       // AGEaligner.cpp:151,181-184
+        }
+        const AlignerOut &o = ctx->outs[pick];
+        if (o.status != 0) { r.status = AGE_ERR_CUDA; continue; }
+        r.score = o.score; r.flag = ctx->aligners[pick].flag;
+        r.n_bp = o.n_bp;
+        memcpy(r.bp, o.bp, sizeof(r.bp));
+        r.alt_index = o.alt_index;
+        r.n_left = o.n_blk[0]; r.n_right = o.n_blk[1]; r.n_alt_left = o.n_blk[2]; r.n_alt_right = o.n_blk[3];
+        const age_block *b = ctx->blocks[pick].data();
+        r.left = b; r.right = b + r.n_left; r.alt_left = r.right + r.n_right; r.alt_right = r.alt_left + r.n_alt_left;
+    }
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
+{
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        g_create_error = "no usable CUDA device (the AGE realigner has no CPU fallback)";
+        return nullptr;
+    }
+    if (n_dev <= 0 || !device_ids) n_dev = 1;
+    age_ctx *ctx = new age_ctx();
+    ctx->host_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    for (int i = 0; i < n_dev; ++i) {
+        Device d;
+        d.id = device_ids ? device_ids[i] : 0;
+        if (d.id < 0 || d.id >= count) { g_create_error = "invalid device id"; delete ctx; return nullptr; }
+        ctx->devs.push_back(d);
+    }
+    for (Device &d : ctx->devs) {
+        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) == cudaSuccess;
+        for (int e = 0; ok && e < 6; ++e) ok = cudaEventCreate(&d.ev[e]) == cudaSuccess;
+        if (!ok) { g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); age_destroy(ctx); return nullptr; }
+    }
+    return ctx;
+}
+
+extern "C" void age_destroy(age_ctx *ctx)
+{
+    if (!ctx) return;
+    for (Device &d : ctx->devs) {
+        cudaSetDevice(d.id);
+        if (d.st) cudaStreamSynchronize(d.st);
+        d.in.release(); d.scratch.release(); d.outbuf.release(); d.hin.release(); d.hout.release();
+        for (auto &e : d.ev) if (e) cudaEventDestroy(e);
+        if (d.st) cudaStreamDestroy(d.st);
+    }
+    delete ctx;
+}
+
+extern "C" const char *age_last_error(const age_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+static int run_plan(age_ctx *ctx, age_result *out, size_t n)
+{
+    auto sub = make_subbatches(ctx);
+    const int nd = (int)ctx->devs.size();
+    std::vector<int> rc(nd, 0);
+    auto worker = [&](int d) {
+        Device &dev = ctx->devs[d];
+        for (auto &ids : sub[d]) {
+            if (!stage_on_device(ctx, dev, ids) || !run_on_device(ctx, dev) || !fetch_from_device(ctx, dev)) { rc[d] = AGE_ERR_CUDA; return; }
+        }
+    };
+    // timing is accumulated after the join (stats are not thread-safe)
+    if (nd == 1) {
+        Device &dev = ctx->devs[0];
+        for (auto &ids : sub[0]) {
+            if (!stage_on_device(ctx, dev, ids) || !run_on_device(ctx, dev) || !fetch_from_device(ctx, dev)) { rc[0] = AGE_ERR_CUDA; break; }
+            ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 2; ctx->stats.fill_launches += 1;
+            add_timing(ctx, dev);
+        }
+    } else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; ++d) th.emplace_back(worker, d);
+        for (auto &t : th) t.join();
+        for (int d = 0; d < nd; ++d) { ctx->stats.launches += 2 * sub[d].size(); ctx->stats.fill_launches += sub[d].size(); }
+    }
+    for (int d = 0; d < nd; ++d)
+        if (rc[d]) { ctx->err = ctx->devs[d].err; return rc[d]; }
+    account(ctx);
+    assemble(ctx, out, n);
+    return 0;
+}
+
+extern "C" int age_align_batch(age_ctx *ctx, const age_job *jobs, size_t n, age_result *out)
+{
+    if (!ctx || (!jobs && n) || (!out && n)) return AGE_ERR_ARG;
+    ctx->stats = age_stats{};
+    ctx->staged = false;
+    build_plan(ctx, jobs, n);
+    return run_plan(ctx, out, n);
+}
+
+extern "C" int age_stage(age_ctx *ctx, const age_job *jobs, size_t n)
+{
+    if (!ctx || (!jobs && n)) return AGE_ERR_ARG;
+    ctx->stats = age_stats{};
+    ctx->staged = false;
+    build_plan(ctx, jobs, n);
+    auto sub = make_subbatches(ctx);
+    for (size_t d = 0; d < ctx->devs.size(); ++d) {
+        if (sub[d].size() > 1) { ctx->err = "batch does not fit in device memory in one piece; use age_align_batch"; return AGE_ERR_ARG; }
+        Device &dev = ctx->devs[d];
+        if (sub[d].empty()) { dev.pair_ids.clear(); dev.tasks.clear(); dev.n_outs = 0; continue; }
+        if (!stage_on_device(ctx, dev, sub[d][0])) { ctx->err = dev.err; return AGE_ERR_CUDA; }
+        ctx->stats.h2d_bytes += dev.in_bytes;
+    }
+    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.st); }
+    ctx->staged = true;
+    return 0;
+}
+
+extern "C" int age_run_staged(age_ctx *ctx)
+{
+    if (!ctx || !ctx->staged) return AGE_ERR_ARG;
+    for (Device &dev : ctx->devs) {
+        if (dev.tasks.empty()) continue;
+        if (!run_on_device(ctx, dev)) { ctx->err = dev.err; return AGE_ERR_CUDA; }
+    }
+    ctx->stats.kernel_ms = 0; ctx->stats.fill_ms = 0;
+    for (Device &dev : ctx->devs) {
+        if (dev.tasks.empty()) continue;
+        cudaSetDevice(dev.id);
+        if (cudaStreamSynchronize(dev.st) != cudaSuccess) { ctx->err = cudaGetErrorString(cudaGetLastError()); return AGE_ERR_CUDA; }
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
+        if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
+    }
+    ctx->stats.launches += 2; ctx->stats.fill_launches += 1;
+    return 0;
+}
+
+extern "C" int age_fetch(age_ctx *ctx, age_result *out, size_t n)
+{
+    if (!ctx || !ctx->staged || n != ctx->n_jobs || (!out && n)) return AGE_ERR_ARG;
+    for (Device &dev : ctx->devs) {
+        if (dev.tasks.empty()) continue;
+        if (!fetch_from_device(ctx, dev)) { ctx->err = dev.err; return AGE_ERR_CUDA; }
+    }
+    ctx->stats.n_aligners = 0; ctx->stats.cell_updates = 0;
+    account(ctx);
+    assemble(ctx, out, n);
+    return 0;
+}
+
+extern "C" int age_get_stats(const age_ctx *ctx, age_stats *st)
+{
+    if (!ctx || !st) return AGE_ERR_ARG;
+    *st = ctx->stats;
+    return 0;
+}
+
+extern "C" const char *age_version(void) { return "age-b200 0.1 (sm_100a)"; }

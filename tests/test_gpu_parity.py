@@ -1,0 +1,156 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the reference's golden records.
+Integer work, so everything is compared bit-exactly: score, breakpoint list, diagonal blocks and the `.age` text."""
+import numpy as np
+import pytest
+
+import ageutil as U
+from asmvar_b200 import capi
+
+pytestmark = pytest.mark.gpu
+
+CASES = U.load_cases()
+KEYS = ("status", "score", "flag", "used_aux", "main_score", "aux_score", "bp", "alt_index", "left", "right", "alt_left", "alt_right")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from asmvar_b200 import engine
+    with engine.Engine() as e:
+        yield e
+
+
+def case_jobs(case):
+    s1, s2 = case["s1"]["seq"].encode(), case["s2"]["seq"].encode()
+    sc = (case["match"], case["mismatch"], case["go"], case["ge"])
+    jobs = [(s1, s2, case["flag"], *sc)]
+    if case["both"]:
+        jobs.append((s1, U.revcom_str(case["s2"]["seq"]).encode(), case["flag"], *sc))
+    return jobs
+
+
+def diff_summary(got, want):
+    return [k for k in KEYS if k in want and got.get(k) != want.get(k)]
+
+
+def test_golden_records_one_batch(eng):
+    """All 247 golden records (the reference's 15 known-answer cases, Test1, Test2, 220 reference-generated
+    random cases) in ONE batch: exercises pairing, mixed shapes and modes."""
+    jobs, owner = [], []
+    for ci, c in enumerate(CASES):
+        for j in case_jobs(c):
+            jobs.append(j); owner.append(ci)
+    res = eng.align(jobs)
+    by_case = {}
+    for r, ci in zip(res, owner):
+        by_case.setdefault(ci, []).append(r)
+    bad = []
+    for ci, c in enumerate(CASES):
+        it = iter(by_case[ci])
+        got = U.candidate_record(c, lambda *a: next(it))
+        if got.rstrip("\n") != c["expected"].rstrip("\n"):
+            bad.append(c["id"])
+    assert not bad, f"{len(bad)} records differ from the reference: {bad[:20]}"
+
+
+def rand_seq(rng, n, alphabet):
+    return "".join(rng.choice(list(alphabet), size=n)).encode()
+
+
+def mutate(rng, s, sub=0.03, indel=0.01):
+    out = []
+    for ch in s.decode():
+        x = rng.random()
+        if x < sub:
+            out.append(rng.choice(list("ACGT")))
+        elif x < sub + indel:
+            continue
+        elif x < sub + 2 * indel:
+            out.append(ch); out.append(rng.choice(list("ACGT")))
+        else:
+            out.append(ch)
+    return "".join(out).encode()
+
+
+def sv_pair(rng, len1, flank, mode, alphabet="ACGT"):
+    """A reference window and a contig carrying one structural event, so the split alignment is non-trivial."""
+    w = rand_seq(rng, len1, alphabet)
+    a = int(rng.integers(flank, len1 - flank - 10))
+    L = int(rng.integers(5, max(6, len1 - a - flank)))
+    left, right = w[a - flank:a], w[a + L:a + L + flank]
+    if mode == "del":
+        q = left + right
+    elif mode == "ins":
+        q = w[a - flank:a] + rand_seq(rng, int(rng.integers(3, 60)), "ACGT") + w[a:a + flank]
+    elif mode == "tdup":
+        q = w[a - flank:a + L][-flank:] + w[a:a + flank]
+    else:  # inversion
+        q = left + U.revcom_str(w[a:a + flank].decode()).encode()
+    q = mutate(rng, q)
+    if rng.random() < 0.3:
+        q = U.revcom_str(q.decode()).encode()
+    return w, q
+
+
+SCORINGS = [(1, -1, -10, -1), (1, -2, -2, -1), (2, -3, -5, -2), (3, -1, -4, -4), (1, -1, -1, -3)]
+FLAGS = [capi.INDEL_FLAG, capi.TDUPLICATION_FLAG, capi.INVERSION_FLAG, capi.INVL_FLAG, capi.INVR_FLAG]
+
+
+def random_jobs(seed, n, len1_range, flank_range, alphabets):
+    rng = np.random.default_rng(seed)
+    jobs = []
+    for i in range(n):
+        len1 = int(rng.integers(*len1_range))
+        flank = int(rng.integers(*flank_range))
+        flank = min(flank, (len1 - 20) // 3)
+        mode = ["del", "ins", "tdup", "inv"][i % 4]
+        w, q = sv_pair(rng, len1, flank, mode, alphabets[i % len(alphabets)])
+        flag = FLAGS[int(rng.integers(0, len(FLAGS)))] if i % 3 else capi.INDEL_FLAG
+        jobs.append((w, q, flag, *SCORINGS[int(rng.integers(0, len(SCORINGS)))]))
+    return jobs
+
+
+def check_against_oracle(eng, jobs):
+    res = eng.align(jobs)
+    bad = []
+    for i, (j, r) in enumerate(zip(jobs, res)):
+        want = U.oracle_aligner(*j)
+        d = diff_summary(r, want)
+        if d:
+            bad.append((i, j[2], len(j[0]), len(j[1]), d, r.get("score"), want.get("score")))
+    assert not bad, f"{len(bad)}/{len(jobs)} jobs differ from the oracle; first: {bad[:8]}"
+
+
+def test_random_small_all_modes(eng):
+    check_against_oracle(eng, random_jobs(11, 160, (60, 400), (15, 80), ["ACGT", "ACGT", "ACGTN", "ACGTacgtNnU"]))
+
+
+def test_random_multi_strip(eng):
+    """contigs longer than one 256-row strip: the strip boundary rows and the masked last strip are exercised"""
+    check_against_oracle(eng, random_jobs(12, 40, (900, 2200), (200, 420), ["ACGT", "ACGTN"]))
+
+
+def test_homopolymer_and_degenerate(eng):
+    jobs = []
+    for flag in FLAGS:
+        jobs.append((b"A" * 90, b"A" * 40, flag, 1, -1, -10, -1))           # every cell ties
+        jobs.append((b"N" * 50, b"N" * 70, flag, 1, -1, -10, -1))           # all scores zero
+        jobs.append((b"ACGT" * 30, b"TTTT" + b"ACGT" * 10, flag, 1, -2, -2, -1))
+        jobs.append((b"A", b"A", flag, 1, -1, -10, -1))
+        jobs.append((b"A", b"C", flag, 1, -1, -10, -1))
+    check_against_oracle(eng, jobs)
+
+
+def test_not_aligned_and_range(eng):
+    res = eng.align([(b"", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1), (b"ACGT", b"ACGT", 0, 1, -1, -10, -1),
+                     (b"ACGT", b"ACGT", capi.INDEL_FLAG, 100, -1, -10, -1), (b"ACGT", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1)])
+    assert [r["status"] for r in res] == [capi.AGE_NOT_ALIGNED, capi.AGE_NOT_ALIGNED, capi.AGE_ERR_RANGE, capi.AGE_OK]
+
+
+def test_batch_order_independent(eng):
+    """the same jobs in another order (hence other pairings) give the same per-job results"""
+    jobs = random_jobs(13, 48, (80, 300), (20, 60), ["ACGT", "ACGTN"])
+    a = eng.align(jobs)
+    perm = list(np.random.default_rng(5).permutation(len(jobs)))
+    b = eng.align([jobs[i] for i in perm])
+    for k, i in enumerate(perm):
+        assert not diff_summary(b[k], a[i])
