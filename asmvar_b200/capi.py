@@ -35,6 +35,7 @@ class AgeJob(C.Structure):
         ("flag", C.c_int32),
         ("match", C.c_int16), ("mismatch", C.c_int16),
         ("gap_open", C.c_int16), ("gap_extend", C.c_int16),
+        ("partner", C.c_int32),
     ]
 
 
@@ -44,7 +45,7 @@ class AgeBlock(C.Structure):
 
 class AgeResult(C.Structure):
     _fields_ = [
-        ("status", C.c_int32), ("score", C.c_int32), ("flag", C.c_int32), ("used_aux", C.c_int32),
+        ("status", C.c_int32), ("detail", C.c_int32), ("score", C.c_int32), ("flag", C.c_int32), ("used_aux", C.c_int32),
         ("main_score", C.c_int32), ("aux_score", C.c_int32),
         ("n_bp", C.c_int32), ("bp", (C.c_int32 * 4) * MAX_BPOINTS),
         ("alt_index", C.c_int32),
@@ -65,7 +66,7 @@ class AgeResult(C.Structure):
     def summary(self) -> dict:
         """Plain-python view used by the parity tests."""
         return {
-            "status": self.status, "score": self.score, "flag": self.flag, "used_aux": self.used_aux,
+            "status": self.status, "detail": self.detail, "score": self.score, "flag": self.flag, "used_aux": self.used_aux,
             "main_score": self.main_score, "aux_score": self.aux_score,
             "bp": self.bpoints(), "alt_index": self.alt_index,
             "left": self.blocks("left"), "right": self.blocks("right"),

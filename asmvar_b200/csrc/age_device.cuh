@@ -42,13 +42,23 @@ struct PairTask {
     const uint2 *ytab;                   // [P] {Ta, Tb}: bytes = 2*S(x in ACGT, y_row) of aligner A / B
     const uint8_t *ycode;                // [P] low nibble = code of A's row, high nibble = B's
     uint4 *bnd_f, *bnd_r;                // strip boundary rows [(nstrips-1)][len1 + 2] {Hc, G2, M, xsel}
-    uint32_t *Mf, *Mr;                   // running maxima, column-major [len1 + 2][P], packed pairs (2*score)
-    uint2 *Tf, *Tr;                      // trace nibbles [len1 + 2][P / 8]: .x = aligner A, .y = aligner B
-    uint32_t *rowmask;                   // [len2 + 2] pass-2 scratch: candidate-row bits
+    int32_t select;                      // 1: only the better-scoring half needs breakpoints (ties -> half 0):
+                                         //    -both partners (age_align.cpp:273) or INVL/INVR of one -inv job (AGEaligner.cpp:151)
+    int32_t nwin;                        // 128-step windows per strip = ceil((len1 + 31) / 128)
+    // The big planes are diagonal-major, [strip][step][lane][k]: what the 32 lanes of the wavefront touch in one
+    // step is one contiguous 1 KB (maxima) or 256 B (trace) block, for the forward and for the reverse sweep alike
+    // (the anti-diagonal of the forward wavefront is the anti-diagonal of the reverse one).
+    uint32_t *D;                         // forward maxima shifted by one row: slot (s, t, l)[k] = 2*Fmax[256s+8l+k][t-l],
+                                         //    which is what the reverse cell (256s+8l+k+1, t-l+1) adds (K6 :545-550)
+    uint32_t *Dtail;                     // [len1 + 2] 2*Fmax[P][c] when len2 == P (row below the last lane)
+    uint32_t *Mr;                        // reverse maxima: slot (s, t, l)[k] = 2*Rmax[256s+8l+k+1][len1+32-t-l]
+    uint2 *Tf, *Tr;                      // trace nibbles (FS | FM << 2), one uint2 per slot: .x = aligner A, .y = B
+    uint32_t *tilemax;                   // [nstrips][nwin][32] max over (lane's 8 rows x 128 steps) of Fmax + Rmax
+    int32_t *rowrange;                   // [2][len2 + 2] pass-2 scratch: hot column range of every row
 };
 
 struct AlignerOut {
-    int32_t status, score, n_bp, alt_index;
+    int32_t status, score, n_bp, alt_index;   // n_bp = -1: score only (the half lost its selection)
     int32_t n_blk[4];                    // left, right, alt_left, alt_right
     int32_t blk_off[4];                  // offsets into the block pool (in blocks)
     int32_t bp[MAX_BP][4];

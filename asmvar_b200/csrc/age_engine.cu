@@ -71,7 +71,8 @@ struct Aligner {                 // one single-mode AGEaligner run
 
 struct HostPair {
     int a[2];                    // aligner indices (second may be -1)
-    int len1, len2, nstrips, P;
+    int select;                  // 1: only the better half needs breakpoints (see PairTask::select)
+    int len1, len2, nstrips, P, nwin;
     size_t in_bytes, scratch_bytes;
     double cells;
 };
@@ -164,9 +165,9 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
             age_revcom(j.seq1, j.len1, &ctx->rc1[i][0]);
         }
     });
-    // pair aligners of identical shape
-    std::vector<int> order(ctx->aligners.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    // pair aligners of identical shape and scoring.  Selection pairs first: INVL+INVR of one -inv job
+    // (AGEaligner.cpp:136-154) and mutual -both partners (age_align.cpp:264-278) share a warp, and only the
+    // half that the reference would print is enumerated and traced back.
     struct Key { int32_t v[6]; };
     auto key = [&](int a) {
         const age_job &j = jobs[ctx->aligners[a].job];
@@ -174,20 +175,42 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
     };
     auto less = [&](int x, int y) { const Key a = key(x), b = key(y); return std::lexicographical_compare(a.v, a.v + 6, b.v, b.v + 6); };
     auto same = [&](int x, int y) { return memcmp(key(x).v, key(y).v, sizeof(Key)) == 0; };
-    std::stable_sort(order.begin(), order.end(), less);
-    for (size_t i = 0; i < order.size();) {
+    auto add_pair = [&](int a0, int a1, int select) {
         HostPair hp{};
-        hp.a[0] = order[i]; hp.a[1] = -1;
-        if (i + 1 < order.size() && same(order[i + 1], order[i])) { hp.a[1] = order[i + 1]; i += 2; } else i += 1;
-        const age_job &j = jobs[ctx->aligners[hp.a[0]].job];
+        hp.a[0] = a0; hp.a[1] = a1; hp.select = select;
+        const age_job &j = jobs[ctx->aligners[a0].job];
         hp.len1 = j.len1; hp.len2 = j.len2;
         hp.nstrips = (j.len2 + STRIP - 1) / STRIP; hp.P = hp.nstrips * STRIP;
+        hp.nwin = (j.len1 + 31 + 127) / 128;
         const size_t cols = (size_t)j.len1 + 2;
         hp.in_bytes = align_up(cols * 4, 16) * 2 + align_up((size_t)hp.P * 8, 16) + align_up((size_t)hp.P, 16);
-        hp.scratch_bytes = 2 * align_up(cols * hp.P * 4, 256) + 2 * align_up(cols * (hp.P / RPT) * 8, 256) +
-                           2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256) + align_up(((size_t)j.len2 + 2) * 4, 256);
+        const size_t slots = (size_t)hp.nstrips * (j.len1 + 31);           // (strip, step) slots of the diagonal-major planes
+        hp.scratch_bytes = 2 * align_up(slots * 1024, 256) + 2 * align_up(slots * 256, 256) + align_up(cols * 4, 256) +
+                           2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256) +
+                           align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256) + align_up(((size_t)j.len2 + 2) * 8, 256);
         hp.cells = (double)j.len1 * j.len2;
         ctx->pairs.push_back(hp);
+    };
+    std::vector<int> first_of(n, -1);
+    for (size_t a = 0; a < ctx->aligners.size(); ++a) if (ctx->aligners[a].role == 0) first_of[ctx->aligners[a].job] = (int)a;
+    std::vector<char> used(ctx->aligners.size(), 0);
+    for (size_t a = 0; a < ctx->aligners.size(); ++a) {
+        const Aligner &al = ctx->aligners[a];
+        if (used[a] || al.role != 0) continue;
+        const age_job &j = jobs[al.job];
+        if (j.flag == F_INV) { add_pair((int)a, (int)a + 1, 1); used[a] = used[a + 1] = 1; continue; }
+        const int pj = j.partner;
+        if (pj > al.job && (size_t)pj < n && jobs[pj].partner == al.job && ctx->job_status[pj] == AGE_OK &&
+            jobs[pj].flag != F_INV && same((int)a, first_of[pj])) {
+            add_pair((int)a, first_of[pj], 1); used[a] = used[first_of[pj]] = 1;
+        }
+    }
+    std::vector<int> order;
+    for (size_t i = 0; i < ctx->aligners.size(); ++i) if (!used[i]) order.push_back((int)i);
+    std::stable_sort(order.begin(), order.end(), less);
+    for (size_t i = 0; i < order.size();) {
+        if (i + 1 < order.size() && same(order[i + 1], order[i])) { add_pair(order[i], order[i + 1], 0); i += 2; }
+        else { add_pair(order[i], -1, 0); i += 1; }
     }
     ctx->outs.assign(ctx->aligners.size(), AlignerOut{});
     ctx->blocks.assign(ctx->aligners.size(), {});
@@ -219,6 +242,7 @@ void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
     uint8_t *ycode = (uint8_t *)(h + 2 * xs + align_up((size_t)hp.P * 8, 16));
     memset(&T, 0, sizeof(T));
     T.len1 = hp.len1; T.len2 = hp.len2; T.nstrips = hp.nstrips; T.P = hp.P;
+    T.select = hp.select; T.nwin = hp.nwin;
     const char *xfwd[2] = {nullptr, nullptr}, *xrev[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr};
     int sc[2][4] = {{1, -1, -1, -1}, {1, -1, -1, -1}};
     for (int k = 0; k < 2; ++k) {
@@ -273,15 +297,18 @@ void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
 void assign_scratch(const HostPair &hp, char *s, PairTask &T)
 {
     const size_t cols = (size_t)hp.len1 + 2;
-    const size_t msz = align_up(cols * hp.P * 4, 256), tsz = align_up(cols * (hp.P / RPT) * 8, 256);
+    const size_t slots = (size_t)hp.nstrips * (hp.len1 + 31);
+    const size_t msz = align_up(slots * 1024, 256), tsz = align_up(slots * 256, 256);
     const size_t bsz = align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256);
-    T.Mf = (uint32_t *)s; s += msz;
+    T.D = (uint32_t *)s; s += msz;
     T.Mr = (uint32_t *)s; s += msz;
     T.Tf = (uint2 *)s; s += tsz;
     T.Tr = (uint2 *)s; s += tsz;
+    T.Dtail = (uint32_t *)s; s += align_up(cols * 4, 256);
     T.bnd_f = (uint4 *)s; s += bsz;
     T.bnd_r = (uint4 *)s; s += bsz;
-    T.rowmask = (uint32_t *)s;
+    T.tilemax = (uint32_t *)s; s += align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256);
+    T.rowrange = (int32_t *)s;
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
@@ -474,6 +501,8 @@ void assemble(age_ctx *ctx, age_result *out, size_t n)
         const AlignerOut &o = ctx->outs[pick];
         if (o.status != 0) { r.status = AGE_ERR_CUDA; continue; }
         r.score = o.score; r.flag = ctx->aligners[pick].flag;
+        if (o.n_bp < 0) continue;                                  // lost the -both selection: score only
+        r.detail = 1;
         r.n_bp = o.n_bp;
         memcpy(r.bp, o.bp, sizeof(r.bp));
         r.alt_index = o.alt_index;

@@ -14,6 +14,7 @@
 // through a small shared-memory ring that is refilled / flushed with coalesced 512-byte transactions.
 #include "age_device.cuh"
 #include <cuda_runtime.h>
+#include <cstdlib>
 
 namespace age {
 
@@ -65,19 +66,21 @@ __device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
 template <int DIR, bool TRACE, bool STOREM>
 __device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, const int lane)
 {
-    const int p = DIR > 0 ? lane : 31 - lane;            // logical lane: 0 leads the wavefront
-    const int len1 = T.len1;
-    const int P = T.P;
+    constexpr bool FWD = DIR > 0;
+    constexpr bool SUM = !FWD;                            // the reverse sweep folds in D = shifted Fmax (K6 :545-550)
+    const int p = FWD ? lane : 31 - lane;                 // logical lane: 0 leads the wavefront
+    const int len1 = T.len1, len2 = T.len2;
     const uint32_t c0x = T.c0x, kabs = T.kabs, flip = T.flip, gborder = T.gborder;
-    const uint32_t *__restrict__ xsel = DIR > 0 ? T.xsel_f : T.xsel_r;
-    uint32_t *__restrict__ Mmat = DIR > 0 ? T.Mf : T.Mr;
-    uint2 *__restrict__ Tmat = DIR > 0 ? T.Tf : T.Tr;
-    uint4 *bnd = DIR > 0 ? T.bnd_f : T.bnd_r;
+    const uint32_t *__restrict__ xsel = FWD ? T.xsel_f : T.xsel_r;
+    uint2 *__restrict__ Tmat = FWD ? T.Tf : T.Tr;
+    uint4 *bnd = FWD ? T.bnd_f : T.bnd_r;
     const int nsteps = len1 + 31;
 
     for (int si = 0; si < T.nstrips; ++si) {
-        const int s = DIR > 0 ? si : T.nstrips - 1 - si;
-        const int q0 = s * STRIP + lane * RPT;           // 0-based first row of this lane
+        const int s = FWD ? si : T.nstrips - 1 - si;
+        const int q0 = s * STRIP + lane * RPT;            // 0-based first row of this lane
+        const int nvalid = min(max(len2 - q0, 0), RPT);   // rows of this lane that exist
+        const size_t sbase = (size_t)s * nsteps;          // first (strip, step) slot of the diagonal-major planes
         uint32_t Ta[RPT], Tb[RPT], Hl[RPT], Gl[RPT], Ml[RPT];
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
@@ -88,14 +91,30 @@ __device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, c
         uint32_t outH = 0, outG = gborder, outM = 0, outS = 0, prevH = 0;
         const uint4 *bin = si == 0 ? nullptr : bnd + (size_t)(si - 1) * (len1 + 2);
         uint4 *bout = (si + 1 < T.nstrips) ? bnd + (size_t)si * (len1 + 2) : nullptr;
+        const bool tail_row = FWD && p == 31 && si + 1 == T.nstrips;   // also stores row q0+8 of D
 
         auto fetch = [&](int u) -> uint4 {
             if (u > len1) return make_uint4(0, gborder, 0, 0);
-            const int c = DIR > 0 ? u : len1 + 1 - u;
-            if (bin) return bin[c];
+            const int c = FWD ? u : len1 + 1 - u;
+            if (bin) return __ldcg(bin + c);
             return make_uint4(0, gborder, 0, xsel[c]);
         };
         uint4 pre = fetch(1 + lane);
+
+        // D of the next column, loaded one step ahead (reverse sweep only)
+        uint4 Dn0 = make_uint4(0, 0, 0, 0), Dn1 = make_uint4(0, 0, 0, 0);
+        auto prefetchD = [&](int un) {
+            if (!SUM) return;
+            if (un >= 1 && un <= len1) {
+                const int c = len1 + 1 - un;
+                if (c >= 2) {                              // slot written by forward lane `lane` in step c-1+lane
+                    const uint4 *src = reinterpret_cast<const uint4 *>(T.D + (sbase + (size_t)(c - 2 + lane)) * 256 + lane * 8);
+                    Dn0 = __ldcg(src); Dn1 = __ldcg(src + 1);
+                } else { Dn0 = make_uint4(0, 0, 0, 0); Dn1 = Dn0; }
+            }
+        };
+        prefetchD(1 - p);
+        uint32_t best = 0;
 
         for (int t = 1; t <= nsteps; ++t) {
             if (((t - 1) & 31) == 0) {
@@ -109,7 +128,13 @@ __device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, c
             if (p == 0) { const uint4 e = ring_in[(t - 1) & 31]; rH = e.x; rG = e.y; rM = e.z; rS = e.w; }
             const int u = t - p;
             if (u >= 1 && u <= len1) {
-                const int c = DIR > 0 ? u : len1 + 1 - u;
+                const int c = FWD ? u : len1 + 1 - u;
+                uint32_t Dc[RPT];
+                if (SUM) {
+                    Dc[0] = Dn0.x; Dc[1] = Dn0.y; Dc[2] = Dn0.z; Dc[3] = Dn0.w;
+                    Dc[4] = Dn1.x; Dc[5] = Dn1.y; Dc[6] = Dn1.z; Dc[7] = Dn1.w;
+                    prefetchD(u + 1);
+                }
                 uint32_t S2[RPT];
                 if (rS & XSEL_SPECIAL) {
                     const int xa = (rS >> 20) & 7, xb = (rS >> 24) & 7;
@@ -129,7 +154,7 @@ __device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, c
                 uint32_t accA = 0, accB = 0;
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
-                    const int k = DIR > 0 ? j : RPT - 1 - j;
+                    const int k = FWD ? j : RPT - 1 - j;
                     const uint32_t g  = __vmaxs2(Gl[k], vG);
                     const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);      // max(2d, 2h+1, 2v+1, 0)
                     const uint32_t tg = (s2 ^ flip) & 0x00010001u;
@@ -145,27 +170,39 @@ __device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, c
                         accA |= na << (4 * k);
                         accB |= nb << (4 * k);
                     }
+                    if (SUM) { if (k < nvalid) best = __vmaxu2(best, __vadd2(Mn, Dc[k])); }
                     dg = Hl[k];
                     Hl[k] = Hc; Gl[k] = G2; Ml[k] = Mn;
                     vG = G2; vM = Mn;
                 }
-                constexpr int last = DIR > 0 ? RPT - 1 : 0;
+                constexpr int last = FWD ? RPT - 1 : 0;
                 outH = Hl[last]; outG = Gl[last]; outM = Ml[last]; outS = rS;
                 if (STOREM) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(Mmat + (size_t)c * P + q0);
-                    dst[0] = make_uint4(Ml[0], Ml[1], Ml[2], Ml[3]);
-                    dst[1] = make_uint4(Ml[4], Ml[5], Ml[6], Ml[7]);
+                    if (FWD) {                             // rows q0 .. q0+7 of Fmax (row q0 came from the lane above)
+                        uint4 *dst = reinterpret_cast<uint4 *>(T.D + (sbase + (t - 1)) * 256 + lane * 8);
+                        dst[0] = make_uint4(rM, Ml[0], Ml[1], Ml[2]);
+                        dst[1] = make_uint4(Ml[3], Ml[4], Ml[5], Ml[6]);
+                        if (tail_row) T.Dtail[c] = Ml[7];
+                    } else {
+                        uint4 *dst = reinterpret_cast<uint4 *>(T.Mr + (sbase + (t - 1)) * 256 + lane * 8);
+                        dst[0] = make_uint4(Ml[0], Ml[1], Ml[2], Ml[3]);
+                        dst[1] = make_uint4(Ml[4], Ml[5], Ml[6], Ml[7]);
+                    }
                 }
-                if (TRACE) Tmat[(size_t)c * (P / RPT) + (q0 / RPT)] = make_uint2(accA, accB);
+                if (TRACE) Tmat[(sbase + (t - 1)) * 32 + lane] = make_uint2(accA, accB);
                 if (p == 31 && bout) ring_out[(u - 1) & 31] = make_uint4(outH, outG, outM, rS);
             }
             prevH = rH;
+            if (SUM && ((t & 127) == 0 || t == nsteps)) {
+                T.tilemax[((size_t)s * T.nwin + ((t - 1) >> 7)) * 32 + lane] = best;
+                best = 0;
+            }
             if (bout) {
                 const int u31 = t - 31;                   // column just finished by the last logical lane
                 if (u31 >= 1 && ((u31 & 31) == 0 || u31 == len1)) {
                     __syncwarp();
                     const int ub = ((u31 - 1) & ~31) + 1 + lane;
-                    if (ub <= u31) bout[DIR > 0 ? ub : len1 + 1 - ub] = ring_out[lane];
+                    if (ub <= u31) bout[FWD ? ub : len1 + 1 - ub] = ring_out[lane];
                     __syncwarp();
                 }
             }
@@ -175,6 +212,7 @@ __device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, c
 
 constexpr int SWEEP_WARPS = 4;
 
+template <bool TRACE>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
 {
@@ -184,10 +222,12 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
         int item = 0;
         if (lane == 0) item = atomicAdd(counter, 1);
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
-        if (item >= 2 * n_pairs) break;
-        const PairTask &T = pairs[item >> 1];
-        if (item & 1) sweep_pair<-1, true, true>(T, rings[w][0], rings[w][1], lane);
-        else          sweep_pair<+1, true, true>(T, rings[w][0], rings[w][1], lane);
+        if (item >= n_pairs) break;
+        const PairTask &T = pairs[item];
+        sweep_pair<+1, TRACE, true>(T, rings[w][0], rings[w][1], lane);
+        __threadfence_block();
+        __syncwarp();
+        sweep_pair<-1, TRACE, TRACE>(T, rings[w][0], rings[w][1], lane);
         __syncwarp();
     }
 }
@@ -198,45 +238,59 @@ void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cud
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int items = 2 * n_pairs;
-    int blocks = (items + SWEEP_WARPS - 1) / SWEEP_WARPS;
+    int blocks = (n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS;
     const int cap = sms * 4;                              // persistent: 4 CTAs x 4 warps per SM
     if (blocks > cap) blocks = cap;
     cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st);
-    age_sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
+    static const bool fast = getenv("AGE_EXPERIMENT_FAST") != nullptr;     // timing experiment only: no traces
+    static const int occ = getenv("AGE_OCC") ? atoi(getenv("AGE_OCC")) : 4;
+    if (blocks > sms * occ) blocks = sms * occ;
+    if (fast) age_sweep_kernel<false><<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
+    else      age_sweep_kernel<true><<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
 }
 
 // ------------------------------------------------------------------------------------------------
 // pass 2: breakpoint enumeration (K5-K9) and traceback (K10-K12) over the materialised matrices
 // ------------------------------------------------------------------------------------------------
 struct View {
-    int len1, len2, P, half, flag;
-    const uint32_t *Mf, *Mr;
+    int len1, len2, nstrips, nsteps, half, flag;
+    const uint32_t *D, *Dtail, *Mr;
     const uint2 *Tf, *Tr;
 
-    __device__ int F2(int r, int c) const {              // 2 * Fmax[r][c], zero on the borders
-        if (r < 1 || c < 1 || r > len2 || c > len1) return 0;
-        return (Mf[(size_t)c * P + (r - 1)] >> (16 * half)) & 0xFFFF;
+    // The planes are diagonal-major: [strip][step][lane][k].  Forward lane l is at column t-l in step t; reverse
+    // lane l (logical lane 31-l) is at column len1+32-t-l.
+    __device__ size_t fslot(int q, int c) const { const int l = (q & 255) >> 3; return ((size_t)(q >> 8) * nsteps + (c + l - 1)) * 32 + l; }
+    __device__ size_t rslot(int q, int c) const { const int l = (q & 255) >> 3; return ((size_t)(q >> 8) * nsteps + (len1 + 31 - c - l)) * 32 + l; }
+    __device__ uint32_t F2w(int r, int c) const {        // packed pair word of 2 * Fmax[r][c]
+        if (r < 1 || c < 1 || r > len2 || c > len1) return 0u;
+        if ((r >> 8) == nstrips) return Dtail[c];
+        return D[fslot(r, c) * 8 + (r & 7)];              // D row index = r (shifted by one row, see the sweep)
     }
-    __device__ int R2(int r, int c) const {              // 2 * Rmax[r][c]
-        if (r < 1 || c < 1 || r > len2 || c > len1) return 0;
-        return (Mr[(size_t)c * P + (r - 1)] >> (16 * half)) & 0xFFFF;
+    __device__ uint32_t R2w(int r, int c) const {
+        if (r < 1 || c < 1 || r > len2 || c > len1) return 0u;
+        return Mr[rslot(r - 1, c) * 8 + ((r - 1) & 7)];
     }
-    __device__ uint32_t nib(const uint2 *T, int r, int c) const {
-        const uint2 w = T[(size_t)c * (P / RPT) + ((r - 1) >> 3)];
+    __device__ int F2(int r, int c) const { return (F2w(r, c) >> (16 * half)) & 0xFFFF; }
+    __device__ int R2(int r, int c) const { return (R2w(r, c) >> (16 * half)) & 0xFFFF; }
+    __device__ uint32_t nibf(int r, int c) const {
+        const uint2 w = Tf[fslot(r - 1, c)];
+        return ((half ? w.y : w.x) >> (4 * ((r - 1) & 7))) & 15u;
+    }
+    __device__ uint32_t nibr(int r, int c) const {
+        const uint2 w = Tr[rslot(r - 1, c)];
         return ((half ? w.y : w.x) >> (4 * ((r - 1) & 7))) & 15u;
     }
     __device__ bool interior(int r, int c) const { return r >= 1 && c >= 1 && r <= len2 && c <= len1; }
-    __device__ uint32_t FS(int r, int c) const { return interior(r, c) ? (nib(Tf, r, c) & 3u) : (uint32_t)T_STOP; }
-    __device__ uint32_t RS(int r, int c) const { return interior(r, c) ? (nib(Tr, r, c) & 3u) : (uint32_t)T_STOP; }
+    __device__ uint32_t FS(int r, int c) const { return interior(r, c) ? (nibf(r, c) & 3u) : (uint32_t)T_STOP; }
+    __device__ uint32_t RS(int r, int c) const { return interior(r, c) ? (nibr(r, c) & 3u) : (uint32_t)T_STOP; }
     __device__ uint32_t FM(int r, int c) const {         // borders: :874-882
-        if (interior(r, c)) return nib(Tf, r, c) >> 2;
+        if (interior(r, c)) return nibf(r, c) >> 2;
         if (r == 0) return c >= 1 ? T_HORI : T_STOP;
         if (c == 0) return r <= len2 ? T_VERT : T_STOP;
         return T_STOP;
     }
     __device__ uint32_t RM(int r, int c) const {         // reverse border keeps RM = 0 (:924-932 sets FM bits there)
-        return interior(r, c) ? (nib(Tr, r, c) >> 2) : (uint32_t)T_STOP;
+        return interior(r, c) ? (nibr(r, c) >> 2) : (uint32_t)T_STOP;
     }
 };
 
@@ -273,19 +327,20 @@ __device__ int add_bp(const View &V, BpList &L, int lg1, int lg2, int rg1, int r
     return -1;
 }
 
-// K6 findIndelBPs, ordered part (:552-610) restricted to the rows flagged by the coalesced pre-scan
-__device__ void indel_enumerate(const View &V, BpList &L, int max2, const uint32_t *rowmask, int lane)
+// K6 findIndelBPs, ordered part (:552-610).  rlo/rhi bound, per row, the columns that can hold a cell with
+// Fmax + Rmax == max (from the hot tiles of the reverse sweep and the border rule); rows with rhi < rlo are skipped.
+__device__ void indel_enumerate(const View &V, BpList &L, int max2, const int *rlo, const int *rhi, int lane)
 {
-    const int len1 = V.len1, len2 = V.len2;
-    const uint32_t fbit = 1u << (2 * V.half), rbit = 2u << (2 * V.half);
+    const int len2 = V.len2;
     int n_add = 0;
     bool stop = false;
     for (int r = 0; r <= len2 && !stop; ++r) {                           // forward scan (:552-573)
-        if (!(rowmask[r] & fbit)) continue;
-        for (int cb = 0; cb <= len1 && !stop; cb += 32) {
+        const int lo = rlo[r], hi = rhi[r];
+        if (hi < lo) continue;
+        for (int cb = lo & ~31; cb <= hi && !stop; cb += 32) {
             const int c = cb + lane;
             bool hit = false;
-            if (c <= len1 && V.F2(r, c) + V.R2(r + 1, c + 1) == max2) hit = V.FM(r, c) == T_STOP;
+            if (c >= lo && c <= hi && V.F2(r, c) + V.R2(r + 1, c + 1) == max2) hit = V.FM(r, c) == T_STOP;
             unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             while (m && !stop) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -299,11 +354,12 @@ __device__ void indel_enumerate(const View &V, BpList &L, int max2, const uint32
     }
     n_add = 0; stop = false;
     for (int r = len2; r >= 0 && !stop; --r) {                            // reverse scan (:586-610)
-        if (!(rowmask[r] & rbit)) continue;
-        for (int cb = (len1 / 32) * 32; cb >= 0 && !stop; cb -= 32) {
+        const int lo = rlo[r], hi = rhi[r];
+        if (hi < lo) continue;
+        for (int cb = hi & ~31; cb >= (lo & ~31) && !stop; cb -= 32) {
             const int c = cb + lane;
             bool hit = false;
-            if (c <= len1 && V.F2(r, c) + V.R2(r + 1, c + 1) == max2) hit = V.RM(r + 1, c + 1) == T_STOP;
+            if (c >= lo && c <= hi && V.F2(r, c) + V.R2(r + 1, c + 1) == max2) hit = V.RM(r + 1, c + 1) == T_STOP;
             unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             while (m && !stop) {
                 const int b = 31 - __clz(m); m &= ~(1u << b);
@@ -315,6 +371,55 @@ __device__ void indel_enumerate(const View &V, BpList &L, int max2, const uint32
             }
         }
     }
+}
+
+// Hot-tile refinement for one half: every reverse-sweep tile whose maximum equals the split maximum is scanned
+// exactly and the K6 cells (r, c) = (r'-1, c'-1) with Fmax + Rmax == max widen the column range of their row.
+__device__ void indel_row_ranges(const PairTask &T, const View &V, int max2, int *rlo, int *rhi, int lane)
+{
+    const int len1 = T.len1, len2 = T.len2, h = V.half, nsteps = len1 + 31;
+    for (int r = lane; r <= len2; r += 32) { rlo[r] = 0x7FFFFFFF; rhi[r] = -1; }
+    __syncwarp();
+    const int ntiles = T.nstrips * T.nwin * 32;
+    for (int tb = 0; tb < ntiles; tb += 32) {
+        const int ti = tb + lane;
+        const bool hot = ti < ntiles && (int)((T.tilemax[ti] >> (16 * h)) & 0xFFFF) == max2;
+        unsigned m = __ballot_sync(0xFFFFFFFFu, hot);
+        while (m) {
+            const int tile = tb + __ffs(m) - 1; m &= m - 1;
+            const int l = tile & 31, w = (tile >> 5) % T.nwin, s = (tile >> 5) / T.nwin;
+            const int q0 = s * STRIP + l * RPT, p = 31 - l;
+            for (int i = lane; i < 128; i += 32) {
+                const int t = 128 * w + 1 + i;                        // reverse step
+                const int u = t - p;                                  // its logical column for lane l
+                if (u < 1 || u > len1) continue;
+                const int c = len1 + 1 - u;                           // reverse cell column c' (1..len1)
+                const uint32_t *mr = T.Mr + (((size_t)s * nsteps + (t - 1)) * 32 + l) * 8;
+                const uint32_t *df = T.D + (((size_t)s * nsteps + (c - 2 + l)) * 32 + l) * 8;
+                for (int k = 0; k < RPT; ++k) {
+                    const int q = q0 + k;                             // reverse cell row r' = q+1
+                    if (q >= len2) break;
+                    const int rv = (mr[k] >> (16 * h)) & 0xFFFF;
+                    const int fv = c >= 2 ? (int)((df[k] >> (16 * h)) & 0xFFFF) : 0;
+                    if (rv + fv == max2) { atomicMin(&rlo[q], c - 1); atomicMax(&rhi[q], c - 1); }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // border cells of K6 (r = len2 or c = len1): Rmax is zero there, so they tie only when Fmax itself == max
+    if (V.F2(len2, len1) == max2) {
+        // row len2: Fmax[len2][c] is non-decreasing in c -> first column that reaches max
+        int lo = 1, hi = len1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.F2(len2, mid) >= max2) hi = mid; else lo = mid + 1; }
+        if (lane == 0) { rlo[len2] = min(rlo[len2], lo); rhi[len2] = len1; }
+        for (int r = 1 + lane; r < len2; r += 32)
+            if (V.F2(r, len1) == max2) { rlo[r] = min(rlo[r], len1); rhi[r] = len1; }
+    }
+    if (max2 == 0) {                                                  // everything ties at zero: scan it all
+        for (int r = lane; r <= len2; r += 32) { rlo[r] = 0; rhi[r] = len1; }
+    }
+    __syncwarp();
 }
 
 // K7 findInversionTDuplicationBPs (:472-538).  The reference walks every (j1, j2) pair; here the monotone
@@ -433,63 +538,49 @@ age_pass2_kernel(Pass2Params prm)
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= prm.n_pairs) break;
         const PairTask &T = prm.pairs[item];
-        const int len1 = T.len1, len2 = T.len2, P = T.P;
+        const int len1 = T.len1, len2 = T.len2;
 
-        // ---- coalesced pre-scan: split maxima of both halves (:545-550 / :476-481) -----------------
+        // ---- split maxima of both halves (:545-550 / :476-481) ------------------------------------------
         uint32_t mx_indel = 0;                                   // packed u16x2: max of 2*(Fmax + Rmax)
-        for (int rb = 0; rb <= len2; rb += 32) {
-            const int r = rb + lane;
-            if (r > len2) continue;
-            for (int c = 0; c <= len1; ++c) {
-                const uint32_t f = (r >= 1 && c >= 1) ? T.Mf[(size_t)c * P + (r - 1)] : 0u;
-                const uint32_t q = (r + 1 <= len2 && c + 1 <= len1) ? T.Mr[(size_t)(c + 1) * P + r] : 0u;
-                mx_indel = __vmaxu2(mx_indel, __vadd2(f, q));
-            }
-        }
+        const int ntiles = T.nstrips * T.nwin * 32;
+        for (int i = lane; i < ntiles; i += 32) mx_indel = __vmaxu2(mx_indel, T.tilemax[i]);
+        const View V0{len1, len2, T.nstrips, len1 + 31, 0, 0, T.D, T.Dtail, T.Mr, T.Tf, T.Tr};
         uint32_t mx_col = 0;
-        for (int r = lane; r <= len2; r += 32) {
-            const uint32_t f = r >= 1 ? T.Mf[(size_t)len1 * P + (r - 1)] : 0u;
-            const uint32_t q = r + 1 <= len2 ? T.Mr[(size_t)1 * P + r] : 0u;
-            mx_col = __vmaxu2(mx_col, __vadd2(f, q));
-        }
+        if (T.flag[0] != F_INDEL || T.flag[1] != F_INDEL)
+            for (int r = lane; r <= len2; r += 32) mx_col = __vmaxu2(mx_col, __vadd2(V0.F2w(r, len1), V0.R2w(r + 1, 1)));
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             mx_indel = __vmaxu2(mx_indel, __shfl_xor_sync(0xFFFFFFFFu, mx_indel, o));
             mx_col   = __vmaxu2(mx_col,   __shfl_xor_sync(0xFFFFFFFFu, mx_col, o));
         }
+        mx_indel = __vmaxu2(mx_indel, V0.F2w(len2, len1));                          // Fmax[len2][len1] + 0 (border cells)
         int max2[2];
         for (int h = 0; h < 2; ++h) {
             const uint32_t v = (T.flag[h] == F_INDEL) ? mx_indel : mx_col;
             max2[h] = (v >> (16 * h)) & 0xFFFF;
         }
-        // ---- coalesced pre-scan 2: rows that hold a cell with Fmax + Rmax == max (indel halves) -------
-        const bool indelA = T.flag[0] == F_INDEL && T.out[0] >= 0, indelB = T.flag[1] == F_INDEL && T.out[1] >= 0;
-        if (indelA || indelB) {
-            const uint32_t want = (uint32_t)max2[0] | ((uint32_t)max2[1] << 16);
-            for (int rb = 0; rb <= len2; rb += 32) {
-                const int r = rb + lane;
-                if (r > len2) continue;
-                uint32_t bits = 0;
-                for (int c = 0; c <= len1; ++c) {
-                    const uint32_t f = (r >= 1 && c >= 1) ? T.Mf[(size_t)c * P + (r - 1)] : 0u;
-                    const uint32_t q = (r + 1 <= len2 && c + 1 <= len1) ? T.Mr[(size_t)(c + 1) * P + r] : 0u;
-                    const uint32_t e = __vadd2(f, q) ^ want;
-                    if ((e & 0xFFFFu) == 0) bits |= 3u;
-                    if ((e >> 16) == 0) bits |= 12u;
-                }
-                T.rowmask[r] = bits;
+        bool need[2] = {T.out[0] >= 0 && T.flag[0] != 0, T.out[1] >= 0 && T.flag[1] != 0};
+        if (T.select && need[0] && need[1]) {                    // age_align.cpp:273 / AGEaligner.cpp:151: ties keep half 0
+            const int win = max2[1] > max2[0] ? 1 : 0;
+            if (lane == 0) {
+                AlignerOut &Lo = prm.outs[T.out[1 - win]];
+                Lo.status = 0; Lo.score = max2[1 - win] >> 1; Lo.n_bp = -1; Lo.alt_index = -1;
+                for (int q = 0; q < 4; ++q) { Lo.n_blk[q] = 0; Lo.blk_off[q] = 0; }
             }
-            __syncwarp();
+            need[1 - win] = false;
         }
 
         for (int h = 0; h < 2; ++h) {
-            if (T.out[h] < 0 || T.flag[h] == 0) continue;
-            View V{len1, len2, P, h, T.flag[h], T.Mf, T.Mr, T.Tf, T.Tr};
+            if (!need[h]) continue;
+            View V{len1, len2, T.nstrips, len1 + 31, h, T.flag[h], T.D, T.Dtail, T.Mr, T.Tf, T.Tr};
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
             __syncwarp();
-            if (T.flag[h] == F_INDEL) indel_enumerate(V, L, max2[h], T.rowmask, lane);
-            else                      invtdup_enumerate(V, L, max2[h], lane);
+            if (T.flag[h] == F_INDEL) {
+                int *rlo = T.rowrange, *rhi = T.rowrange + (len2 + 2);
+                indel_row_ranges(T, V, max2[h], rlo, rhi, lane);
+                indel_enumerate(V, L, max2[h], rlo, rhi, lane);
+            } else invtdup_enumerate(V, L, max2[h], lane);
             __syncwarp();
             // ---- K10: blocks of bpoint 0 and of the alternative shown by printAlignment (:287-306) ----
             if (lane == 0) {
@@ -535,6 +626,7 @@ age_pass2_kernel(Pass2Params prm)
 void launch_pass2(const Pass2Params &p, cudaStream_t st)
 {
     if (p.n_pairs <= 0) return;
+    if (getenv("AGE_EXPERIMENT_FAST")) return;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

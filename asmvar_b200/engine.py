@@ -48,15 +48,17 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     @staticmethod
     def make_jobs(jobs: Iterable[tuple]):
-        """jobs: (seq1: bytes, seq2: bytes, flag, match, mismatch, gap_open, gap_extend) -> (ctypes array, keepalive)"""
+        """jobs: (seq1: bytes, seq2: bytes, flag, match, mismatch, gap_open, gap_extend[, partner]) -> (ctypes array, keepalive, n)"""
         jobs = list(jobs)
         arr = (capi.AgeJob * max(1, len(jobs)))()
         keep = []
-        for i, (s1, s2, flag, m, mm, go, ge) in enumerate(jobs):
+        for i, job in enumerate(jobs):
+            s1, s2, flag, m, mm, go, ge = job[:7]
             keep.append((s1, s2))
             j = arr[i]
             j.seq1, j.len1, j.seq2, j.len2 = s1, len(s1), s2, len(s2)
             j.flag, j.match, j.mismatch, j.gap_open, j.gap_extend = flag, m, mm, go, ge
+            j.partner = job[7] if len(job) > 7 else -1
         return arr, keep, len(jobs)
 
     def _check(self, rc: int, what: str):

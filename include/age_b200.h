@@ -46,6 +46,10 @@ typedef struct {
     const char *seq2; int32_t len2;     /* second sequence = query / assembly contig    */
     int32_t flag;                       /* exactly one AGE_*_FLAG                       */
     int16_t match, mismatch, gap_open, gap_extend;
+    int32_t partner;                    /* -both (age_align.cpp:264-278): index in the same batch of the job that aligns the
+                                         * reverse-complemented contig against the same seq1, or -1.  When two jobs name each other,
+                                         * only the one age_align would print (the lower index if score >= the other's) gets
+                                         * breakpoints and blocks; the other returns its score with detail = 0. */
 } age_job;
 
 /* A gap-free diagonal run; 1-based positions in seq1 / seq2 (class Block, AGEaligner.hh:128-177). */
@@ -54,6 +58,7 @@ typedef struct { int32_t start1, start2, length; } age_block;
 /* Everything AGEaligner::score() / printAlignment() need (AGEaligner.cpp:149-154,179-380). */
 typedef struct {
     int32_t status;
+    int32_t detail;         /* 1: breakpoints and blocks are filled in; 0: score only (lost the -both selection) */
     int32_t score;          /* AGEaligner::score(): the aux (INVR) score only if strictly greater */
     int32_t flag;           /* single mode of the aligner whose record is printed (INVL/INVR for -inv) */
     int32_t used_aux;       /* 1 if the auxiliary INVR aligner is the printed one (AGEaligner.cpp:181-184) */

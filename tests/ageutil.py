@@ -94,6 +94,7 @@ def summary_to_result(d: dict):
     r = capi.AgeResult()
     keep = []
     r.status, r.score, r.flag, r.used_aux = d["status"], d["score"], d["flag"], d["used_aux"]
+    r.detail = 1
     r.main_score, r.aux_score = d["main_score"], d["aux_score"]
     r.n_bp = len(d["bp"])
     for i, b in enumerate(d["bp"]):
@@ -114,6 +115,7 @@ def make_job(seq1: bytes, seq2: bytes, flag, match, mismatch, go, ge):
     j = capi.AgeJob()
     j.seq1, j.len1, j.seq2, j.len2 = seq1, len(seq1), seq2, len(seq2)
     j.flag, j.match, j.mismatch, j.gap_open, j.gap_extend = flag, match, mismatch, go, ge
+    j.partner = -1
     return j
 
 

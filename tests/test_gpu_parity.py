@@ -19,27 +19,36 @@ def eng():
         yield e
 
 
-def case_jobs(case):
+def case_jobs(case, base=0, partners=True):
+    """jobs of one candidate; with `partners` the two -both jobs name each other (age_job.partner)"""
     s1, s2 = case["s1"]["seq"].encode(), case["s2"]["seq"].encode()
     sc = (case["match"], case["mismatch"], case["go"], case["ge"])
-    jobs = [(s1, s2, case["flag"], *sc)]
-    if case["both"]:
-        jobs.append((s1, U.revcom_str(case["s2"]["seq"]).encode(), case["flag"], *sc))
-    return jobs
+    if not case["both"]:
+        return [(s1, s2, case["flag"], *sc, -1)]
+    p = (base + 1, base) if partners else (-1, -1)
+    return [(s1, s2, case["flag"], *sc, p[0]), (s1, U.revcom_str(case["s2"]["seq"]).encode(), case["flag"], *sc, p[1])]
 
 
 def diff_summary(got, want):
     return [k for k in KEYS if k in want and got.get(k) != want.get(k)]
 
 
-def test_golden_records_one_batch(eng):
+@pytest.mark.parametrize("partners", [True, False])
+def test_golden_records_one_batch(eng, partners):
     """All 247 golden records (the reference's 15 known-answer cases, Test1, Test2, 220 reference-generated
-    random cases) in ONE batch: exercises pairing, mixed shapes and modes."""
+    random cases) in ONE batch: exercises pairing, mixed shapes and modes, with and without the -both
+    partner selection done inside the library."""
     jobs, owner = [], []
     for ci, c in enumerate(CASES):
-        for j in case_jobs(c):
+        for j in case_jobs(c, len(jobs), partners):
             jobs.append(j); owner.append(ci)
     res = eng.align(jobs)
+    if partners:
+        for k, j in enumerate(jobs):
+            if j[7] > k and j[2] != capi.INVERSION_FLAG:      # exactly one job of a -both couple carries breakpoints, the one age_align prints
+                a, b = res[k], res[j[7]]
+                assert a["detail"] + b["detail"] == 1
+                assert a["detail"] == (1 if a["score"] >= b["score"] else 0)
     by_case = {}
     for r, ci in zip(res, owner):
         by_case.setdefault(ci, []).append(r)
