@@ -72,7 +72,8 @@ struct Aligner {                 // one single-mode AGEaligner run
 struct HostPair {
     int a[2];                    // aligner indices (second may be -1)
     int select;                  // 1: only the better half needs breakpoints (see PairTask::select)
-    int len1, len2, nstrips, P, nwin;
+    int len1, len2, nstrips, P, nb, nsteps, nwin;
+    int k7;                      // holds a TDUP / INVL / INVR aligner (pass 2 then needs the reverse maxima plane)
     size_t in_bytes, scratch_bytes;
     double cells;
 };
@@ -80,7 +81,8 @@ struct HostPair {
 struct Device {
     int id = 0;
     cudaStream_t st = nullptr;
-    Arena in, scratch, outbuf;
+    Arena in, scratch, outbuf, p2;
+    int p2_warps = 0; size_t p2_stride = 0, max_slots = 0, max_rows = 0; int need_mp = 0;
     PinnedBuf hin, hout;
     cudaEvent_t ev[6] = {};
     // the sub-batch currently resident on this device
@@ -181,13 +183,15 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
         const age_job &j = jobs[ctx->aligners[a0].job];
         hp.len1 = j.len1; hp.len2 = j.len2;
         hp.nstrips = (j.len2 + STRIP - 1) / STRIP; hp.P = hp.nstrips * STRIP;
-        hp.nwin = (j.len1 + 31 + 127) / 128;
-        const size_t cols = (size_t)j.len1 + 2;
-        hp.in_bytes = align_up(cols * 4, 16) * 2 + align_up((size_t)hp.P * 8, 16) + align_up((size_t)hp.P, 16);
-        const size_t slots = (size_t)hp.nstrips * (j.len1 + 31);           // (strip, step) slots of the diagonal-major planes
-        hp.scratch_bytes = 2 * align_up(slots * 1024, 256) + 2 * align_up(slots * 256, 256) + align_up(cols * 4, 256) +
-                           2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256) +
-                           align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256) + align_up(((size_t)j.len2 + 2) * 8, 256);
+        hp.nb = (j.len1 + W - 1) / W; hp.nsteps = hp.nb + 31; hp.nwin = (hp.nsteps + CKS - 1) / CKS;
+        hp.k7 = (ctx->aligners[a0].flag != F_INDEL) || (a1 >= 0 && ctx->aligners[a1].flag != F_INDEL);
+        const size_t slots = (size_t)hp.nstrips * hp.nsteps;                 // (strip, step) slots of the diagonal-major planes
+        hp.in_bytes = 2 * align_up(((size_t)hp.nb + 2) * 16, 16) + align_up((size_t)hp.P * 8, 16) + align_up((size_t)hp.P, 16);
+        hp.scratch_bytes = align_up(slots * W * 2 * 32 * 16, 256) +
+                           2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16, 256) +
+                           2 * align_up(((size_t)hp.P + 2) * 4, 256) + align_up(((size_t)W * hp.nb + 4) * 4, 256) +
+                           align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256) +
+                           2 * align_up((size_t)hp.nstrips * hp.nwin * CKW * 32 * 4, 256);
         hp.cells = (double)j.len1 * j.len2;
         ctx->pairs.push_back(hp);
     };
@@ -216,16 +220,22 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
     ctx->blocks.assign(ctx->aligners.size(), {});
 }
 
-// per-column PRMT selector of a pair (see age_device.cuh) for the strings xa / xb (either may be null)
-void fill_xsel(uint32_t *dst, int len1, const char *xa, const char *xb)
+// per-block column descriptors of a pair (see PairTask::xblk) for the strings xa / xb (either may be null).
+// dir > 0: logical block b holds columns W(b-1)+1 .. Wb ascending; dir < 0: columns W(nb-b+1) .. W(nb-b)+1 descending.
+// Columns beyond len1 are padding: special, scoring 0 against everything.
+void fill_xblk(uint4 *dst, int len1, int nb, int dir, const char *xa, const char *xb)
 {
-    dst[0] = 0; dst[len1 + 1] = 0;
-    for (int c = 1; c <= len1; ++c) {
-        const int a = xa ? nuc_code(xa[c - 1]) : 5, b = xb ? nuc_code(xb[c - 1]) : 5;
-        uint32_t w;
-        if (a < 4 && b < 4) w = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + b) << 8) | ((uint32_t)((4 + b) | 8) << 12);
-        else w = XSEL_SPECIAL | ((uint32_t)a << 20) | ((uint32_t)b << 24);
-        dst[c] = w;
+    dst[0] = make_uint4(0, 0, 0x3B3B3B3Bu, 0); dst[nb + 1] = dst[0];
+    for (int b = 1; b <= nb; ++b) {
+        uint32_t sel[W], info = 0;
+        for (int w = 0; w < W; ++w) {
+            const int c = dir > 0 ? W * (b - 1) + 1 + w : W * (nb - b + 1) - w;
+            int a = 5, e = 5;
+            if (c <= len1) { a = xa ? nuc_code(xa[c - 1]) : 5; e = xb ? nuc_code(xb[c - 1]) : 5; }
+            if (a < 4 && e < 4) sel[w] = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + e) << 8) | ((uint32_t)((4 + e) | 8) << 12);
+            else { sel[w] = 0; info |= (1u | ((uint32_t)a << 1) | ((uint32_t)e << 4)) << (8 * w); }
+        }
+        dst[b] = make_uint4(sel[0] | (sel[1] << 16), sel[2] | (sel[3] << 16), info, 0);
     }
 }
 
@@ -235,14 +245,13 @@ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi
 void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
 {
     const HostPair &hp = ctx->pairs[pi];
-    const size_t cols = (size_t)hp.len1 + 2;
-    const size_t xs = align_up(cols * 4, 16);
-    uint32_t *xf = (uint32_t *)h, *xr = (uint32_t *)(h + xs);
+    const size_t xs = align_up(((size_t)hp.nb + 2) * 16, 16);
+    uint4 *xf = (uint4 *)h, *xr = (uint4 *)(h + xs);
     uint2 *ytab = (uint2 *)(h + 2 * xs);
     uint8_t *ycode = (uint8_t *)(h + 2 * xs + align_up((size_t)hp.P * 8, 16));
     memset(&T, 0, sizeof(T));
     T.len1 = hp.len1; T.len2 = hp.len2; T.nstrips = hp.nstrips; T.P = hp.P;
-    T.select = hp.select; T.nwin = hp.nwin;
+    T.select = hp.select; T.nb = hp.nb; T.nsteps = hp.nsteps; T.nwin = hp.nwin;
     const char *xfwd[2] = {nullptr, nullptr}, *xrev[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr};
     int sc[2][4] = {{1, -1, -1, -1}, {1, -1, -1, -1}};
     for (int k = 0; k < 2; ++k) {
@@ -258,9 +267,8 @@ void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
         sc[k][0] = j.match; sc[k][1] = j.mismatch; sc[k][2] = j.gap_open; sc[k][3] = j.gap_extend;
     }
     if (hp.a[1] < 0) { for (int q = 0; q < 4; ++q) sc[1][q] = sc[0][q]; }
-    fill_xsel(xf, hp.len1, xfwd[0], xfwd[1]);
-    const bool same = xfwd[0] == xrev[0] && xfwd[1] == xrev[1];
-    if (!same) fill_xsel(xr, hp.len1, xrev[0], xrev[1]);
+    fill_xblk(xf, hp.len1, hp.nb, +1, xfwd[0], xfwd[1]);
+    fill_xblk(xr, hp.len1, hp.nb, -1, xrev[0], xrev[1]);
     for (int q = 0; q < hp.P; ++q) {
         uint32_t tab[2] = {0, 0}; int code[2] = {5, 5};
         for (int k = 0; k < 2; ++k) {
@@ -288,27 +296,26 @@ void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
     // identical scoring
     T.c0x = pack2(c0x[0], c0x[1]); T.kabs = (uint32_t)kabs[0]; T.flip = pack2(flip[0], flip[1]); T.gborder = pack2(gb[0], gb[1]);
     T.m2 = pack2(2 * sc[0][0], 2 * sc[1][0]); T.mm2 = pack2(2 * sc[0][1], 2 * sc[1][1]);
-    T.xsel_f = (const uint32_t *)d;
-    T.xsel_r = same ? T.xsel_f : (const uint32_t *)(d + xs);
+    T.xblk_f = (const uint4 *)d;
+    T.xblk_r = (const uint4 *)(d + xs);
     T.ytab = (const uint2 *)(d + 2 * xs);
     T.ycode = (const uint8_t *)(d + 2 * xs + align_up((size_t)hp.P * 8, 16));
 }
 
 void assign_scratch(const HostPair &hp, char *s, PairTask &T)
 {
-    const size_t cols = (size_t)hp.len1 + 2;
-    const size_t slots = (size_t)hp.nstrips * (hp.len1 + 31);
-    const size_t msz = align_up(slots * 1024, 256), tsz = align_up(slots * 256, 256);
-    const size_t bsz = align_up((size_t)std::max(hp.nstrips - 1, 0) * cols * 16, 256);
-    T.D = (uint32_t *)s; s += msz;
-    T.Mr = (uint32_t *)s; s += msz;
-    T.Tf = (uint2 *)s; s += tsz;
-    T.Tr = (uint2 *)s; s += tsz;
-    T.Dtail = (uint32_t *)s; s += align_up(cols * 4, 256);
+    const size_t slots = (size_t)hp.nstrips * hp.nsteps;
+    const size_t bsz = align_up((size_t)std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16, 256);
+    const size_t csz = align_up((size_t)hp.nstrips * hp.nwin * CKW * 32 * 4, 256);
+    T.D = (uint32_t *)s; s += align_up(slots * W * 2 * 32 * 16, 256);
     T.bnd_f = (uint4 *)s; s += bsz;
     T.bnd_r = (uint4 *)s; s += bsz;
+    T.Dlast = (uint32_t *)s; s += align_up(((size_t)hp.P + 2) * 4, 256);
+    T.Rfirst = (uint32_t *)s; s += align_up(((size_t)hp.P + 2) * 4, 256);
+    T.Dtail = (uint32_t *)s; s += align_up(((size_t)W * hp.nb + 4) * 4, 256);
     T.tilemax = (uint32_t *)s; s += align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256);
-    T.rowrange = (int32_t *)s;
+    T.ckpt_f = (uint32_t *)s; s += csz;
+    T.ckpt_r = (uint32_t *)s;
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
@@ -329,6 +336,23 @@ bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids
         for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) ctx->aligners[hp.a[k]].out = n_outs++;
     }
     dev.n_outs = n_outs;
+    dev.max_slots = 0; dev.max_rows = 0; dev.need_mp = 0;
+    for (size_t i = 0; i < np; ++i) {
+        const HostPair &hp = ctx->pairs[pair_ids[i]];
+        dev.max_slots = std::max(dev.max_slots, (size_t)hp.nstrips * hp.nsteps);
+        dev.max_rows = std::max(dev.max_rows, (size_t)hp.len2);
+        dev.need_mp |= hp.k7;
+    }
+    dev.p2_stride = align_up(pass2_scratch_bytes(dev.max_slots, dev.max_rows, dev.need_mp), 256);
+    {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        const size_t budget = std::max((size_t)(0.10 * (double)tot), dev.p2.cap);   // pass-2 trace scratch: at most ~10 % of HBM
+        int nw = pass2_warps((int)np);
+        while (nw > 4 && (size_t)nw * dev.p2_stride > budget) nw -= 4;
+        dev.p2_warps = nw;
+    }
+    if (!dev.p2.ensure((size_t)dev.p2_warps * dev.p2_stride)) { dev.err = "device allocation failed (pass-2 scratch)"; return false; }
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
     dev.in_bytes = task_bytes + in_off[np];
     if (!dev.hin.ensure(dev.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
@@ -371,7 +395,8 @@ bool run_on_device(age_ctx *, Device &dev)
     Pass2Params p{};
     p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = np; p.outs = L.outs;
     p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 1;
-    launch_pass2(p, dev.st);
+    p.scratch = dev.p2.ptr; p.scratch_stride = dev.p2_stride; p.max_slots = dev.max_slots; p.max_rows = dev.max_rows; p.need_mp = dev.need_mp;
+    launch_pass2(p, dev.p2_warps, dev.st);
     CK(cudaEventRecord(dev.ev[4], dev.st));
     CK(cudaGetLastError());
     return true;
@@ -415,7 +440,8 @@ bool fetch_from_device(age_ctx *ctx, Device &dev)
         Pass2Params p{};
         p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = (int)dev.tasks.size(); p.outs = L.outs;
         p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 1;
-        launch_pass2(p, dev.st);
+        p.scratch = dev.p2.ptr; p.scratch_stride = dev.p2_stride; p.max_slots = dev.max_slots; p.max_rows = dev.max_rows; p.need_mp = dev.need_mp;
+        launch_pass2(p, dev.p2_warps, dev.st);
     }
     dev.err = "block pool overflow";
     return false;
@@ -440,8 +466,8 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
         cudaSetDevice(ctx->devs[d].id);
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
-        fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap;
-        budget[d] = (size_t)(0.80 * (double)fr);
+        fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap + ctx->devs[d].p2.cap;
+        budget[d] = (size_t)(0.70 * (double)fr);
     }
     // longest-processing-time-first deal across devices
     std::vector<int> order(ctx->pairs.size());
@@ -548,7 +574,7 @@ extern "C" void age_destroy(age_ctx *ctx)
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
         if (d.st) cudaStreamSynchronize(d.st);
-        d.in.release(); d.scratch.release(); d.outbuf.release(); d.hin.release(); d.hout.release();
+        d.in.release(); d.scratch.release(); d.outbuf.release(); d.p2.release(); d.hin.release(); d.hout.release();
         for (auto &e : d.ev) if (e) cudaEventDestroy(e);
         if (d.st) cudaStreamDestroy(d.st);
     }

@@ -7,216 +7,24 @@
 //   K8     traceBackMaxima :615-642 K9 addBpoints :644-668
 //   K11/12 findLeftBlocks / findRightBlocks :752-860
 //
-// Layout: one warp owns one *pair* of aligners (two independent DP problems of identical shape in the two
-// int16 halves of every register).  A lane holds 8 contig rows in registers, the 32 lanes of the warp form a
-// 256-row strip, and the strip is swept along the reference window as an anti-diagonal wavefront: lane p is at
-// column t-p in step t and hands its bottom row to lane p+1 with warp shuffles.  Strip boundaries travel
-// through a small shared-memory ring that is refilled / flushed with coalesced 512-byte transactions.
-#include "age_device.cuh"
+// age_sweep_kernel   the hot kernel: per pair, the forward sweep streams the shifted running maxima D to HBM,
+//                    the reverse sweep folds D back in and leaves one split maximum per (lane, window) tile.
+//                    Neither sweep keeps a trace; both leave a 5 KB lane-state checkpoint per window.
+// age_pass2_kernel   per pair, one warp: split maximum, -both / -inv winner selection, then for the winner only
+//                    breakpoint enumeration and traceback.  Every trace bit it looks at comes from re-running
+//                    the sweep over the one window that holds it (MODE_TRACE), from that window's checkpoint.
+#include "age_sweep.cuh"
 #include <cuda_runtime.h>
 #include <cstdlib>
 
 namespace age {
 
-// ------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
-{
-    uint32_t d;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
-    return d;
-}
-__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
-__device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
-
-template <int DIR> __device__ __forceinline__ uint32_t shfl_prev(uint32_t v)
-{
-    return DIR > 0 ? __shfl_up_sync(0xFFFFFFFFu, v, 1) : __shfl_down_sync(0xFFFFFFFFu, v, 1);
-}
-
-// substitution score (x2) of one half for a special column (Scorer.hh:24-39): codes >= 5 score 0
-__device__ __forceinline__ int subst2(int xc, int yc, int m2, int mm2)
-{
-    if (xc >= 5 || yc >= 5) return 0;
-    return xc == yc ? m2 : mm2;
-}
-
-// FS code of one cell from its three (2x+tag) candidates -- the tie order of :1015-1017
-__device__ __forceinline__ uint32_t fs_code(int d, int h, int v)
-{
-    int s = d; uint32_t t = T_DIAG;
-    if (h >= s) { s = h; t = T_HORI; }
-    if (v >= s) { s = v; t = T_VERT; }
-    if (s < 0) t = T_STOP;
-    return t;
-}
-// FM code (:899-915 / :952-968): VERTICAL is tested first, HORIZONTAL overrides when strictly greater
-__device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
-{
-    int cur = own; uint32_t t = T_STOP;
-    if (up > cur)   { cur = up; t = T_VERT; }
-    if (left > cur) { t = T_HORI; }
-    return t;
-}
-
-// ------------------------------------------------------------------------------------------------
-// the sweep: K1+K3 (DIR = +1) or K2+K4 (DIR = -1) of one pair, all strips
-// ------------------------------------------------------------------------------------------------
-template <int DIR, bool TRACE, bool STOREM>
-__device__ void sweep_pair(const PairTask &T, uint4 *ring_in, uint4 *ring_out, const int lane)
-{
-    constexpr bool FWD = DIR > 0;
-    constexpr bool SUM = !FWD;                            // the reverse sweep folds in D = shifted Fmax (K6 :545-550)
-    const int p = FWD ? lane : 31 - lane;                 // logical lane: 0 leads the wavefront
-    const int len1 = T.len1, len2 = T.len2;
-    const uint32_t c0x = T.c0x, kabs = T.kabs, flip = T.flip, gborder = T.gborder;
-    const uint32_t *__restrict__ xsel = FWD ? T.xsel_f : T.xsel_r;
-    uint2 *__restrict__ Tmat = FWD ? T.Tf : T.Tr;
-    uint4 *bnd = FWD ? T.bnd_f : T.bnd_r;
-    const int nsteps = len1 + 31;
-
-    for (int si = 0; si < T.nstrips; ++si) {
-        const int s = FWD ? si : T.nstrips - 1 - si;
-        const int q0 = s * STRIP + lane * RPT;            // 0-based first row of this lane
-        const int nvalid = min(max(len2 - q0, 0), RPT);   // rows of this lane that exist
-        const size_t sbase = (size_t)s * nsteps;          // first (strip, step) slot of the diagonal-major planes
-        uint32_t Ta[RPT], Tb[RPT], Hl[RPT], Gl[RPT], Ml[RPT];
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const uint2 y = T.ytab[q0 + k];
-            Ta[k] = y.x; Tb[k] = y.y;
-            Hl[k] = 0; Gl[k] = gborder; Ml[k] = 0;
-        }
-        uint32_t outH = 0, outG = gborder, outM = 0, outS = 0, prevH = 0;
-        const uint4 *bin = si == 0 ? nullptr : bnd + (size_t)(si - 1) * (len1 + 2);
-        uint4 *bout = (si + 1 < T.nstrips) ? bnd + (size_t)si * (len1 + 2) : nullptr;
-        const bool tail_row = FWD && p == 31 && si + 1 == T.nstrips;   // also stores row q0+8 of D
-
-        auto fetch = [&](int u) -> uint4 {
-            if (u > len1) return make_uint4(0, gborder, 0, 0);
-            const int c = FWD ? u : len1 + 1 - u;
-            if (bin) return __ldcg(bin + c);
-            return make_uint4(0, gborder, 0, xsel[c]);
-        };
-        uint4 pre = fetch(1 + lane);
-
-        // D of the next column, loaded one step ahead (reverse sweep only)
-        uint4 Dn0 = make_uint4(0, 0, 0, 0), Dn1 = make_uint4(0, 0, 0, 0);
-        auto prefetchD = [&](int un) {
-            if (!SUM) return;
-            if (un >= 1 && un <= len1) {
-                const int c = len1 + 1 - un;
-                if (c >= 2) {                              // slot written by forward lane `lane` in step c-1+lane
-                    const uint4 *src = reinterpret_cast<const uint4 *>(T.D + (sbase + (size_t)(c - 2 + lane)) * 256 + lane * 8);
-                    Dn0 = __ldcg(src); Dn1 = __ldcg(src + 1);
-                } else { Dn0 = make_uint4(0, 0, 0, 0); Dn1 = Dn0; }
-            }
-        };
-        prefetchD(1 - p);
-        uint32_t best = 0;
-
-        for (int t = 1; t <= nsteps; ++t) {
-            if (((t - 1) & 31) == 0) {
-                __syncwarp();
-                ring_in[lane] = pre;
-                __syncwarp();
-                pre = fetch(t + 32 + lane);
-            }
-            uint32_t rH = shfl_prev<DIR>(outH), rG = shfl_prev<DIR>(outG);
-            uint32_t rM = shfl_prev<DIR>(outM), rS = shfl_prev<DIR>(outS);
-            if (p == 0) { const uint4 e = ring_in[(t - 1) & 31]; rH = e.x; rG = e.y; rM = e.z; rS = e.w; }
-            const int u = t - p;
-            if (u >= 1 && u <= len1) {
-                const int c = FWD ? u : len1 + 1 - u;
-                uint32_t Dc[RPT];
-                if (SUM) {
-                    Dc[0] = Dn0.x; Dc[1] = Dn0.y; Dc[2] = Dn0.z; Dc[3] = Dn0.w;
-                    Dc[4] = Dn1.x; Dc[5] = Dn1.y; Dc[6] = Dn1.z; Dc[7] = Dn1.w;
-                    prefetchD(u + 1);
-                }
-                uint32_t S2[RPT];
-                if (rS & XSEL_SPECIAL) {
-                    const int xa = (rS >> 20) & 7, xb = (rS >> 24) & 7;
-                    const int m2a = lo16(T.m2), m2b = hi16(T.m2), mm2a = lo16(T.mm2), mm2b = hi16(T.mm2);
-#pragma unroll
-                    for (int k = 0; k < RPT; ++k) {
-                        const int yc = T.ycode[q0 + k];
-                        const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xb, yc >> 4, m2b, mm2b);
-                        S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
-                    }
-                } else {
-                    const uint32_t sel = rS & 0xFFFFu;
-#pragma unroll
-                    for (int k = 0; k < RPT; ++k) S2[k] = prmt(Ta[k], Tb[k], sel);
-                }
-                uint32_t vG = rG, vM = rM, dg = prevH;
-                uint32_t accA = 0, accB = 0;
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) {
-                    const int k = FWD ? j : RPT - 1 - j;
-                    const uint32_t g  = __vmaxs2(Gl[k], vG);
-                    const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);      // max(2d, 2h+1, 2v+1, 0)
-                    const uint32_t tg = (s2 ^ flip) & 0x00010001u;
-                    const uint32_t G2 = __vadd2(tg * kabs + s2, c0x);             // 2*(s + (gap ? ge : go)) + 1
-                    const uint32_t Hc = s2 & 0xFFFEFFFEu;
-                    const uint32_t Mn = __vimax3_s16x2(Hc, Ml[k], vM);
-                    if (TRACE) {
-                        const uint32_t d2 = __vadd2(dg, S2[k]);
-                        const uint32_t na = fs_code(lo16(d2), lo16(Gl[k]), lo16(vG)) |
-                                            (fm_code(lo16(Hc), lo16(Ml[k]), lo16(vM)) << 2);
-                        const uint32_t nb = fs_code(hi16(d2), hi16(Gl[k]), hi16(vG)) |
-                                            (fm_code(hi16(Hc), hi16(Ml[k]), hi16(vM)) << 2);
-                        accA |= na << (4 * k);
-                        accB |= nb << (4 * k);
-                    }
-                    if (SUM) { if (k < nvalid) best = __vmaxu2(best, __vadd2(Mn, Dc[k])); }
-                    dg = Hl[k];
-                    Hl[k] = Hc; Gl[k] = G2; Ml[k] = Mn;
-                    vG = G2; vM = Mn;
-                }
-                constexpr int last = FWD ? RPT - 1 : 0;
-                outH = Hl[last]; outG = Gl[last]; outM = Ml[last]; outS = rS;
-                if (STOREM) {
-                    if (FWD) {                             // rows q0 .. q0+7 of Fmax (row q0 came from the lane above)
-                        uint4 *dst = reinterpret_cast<uint4 *>(T.D + (sbase + (t - 1)) * 256 + lane * 8);
-                        dst[0] = make_uint4(rM, Ml[0], Ml[1], Ml[2]);
-                        dst[1] = make_uint4(Ml[3], Ml[4], Ml[5], Ml[6]);
-                        if (tail_row) T.Dtail[c] = Ml[7];
-                    } else {
-                        uint4 *dst = reinterpret_cast<uint4 *>(T.Mr + (sbase + (t - 1)) * 256 + lane * 8);
-                        dst[0] = make_uint4(Ml[0], Ml[1], Ml[2], Ml[3]);
-                        dst[1] = make_uint4(Ml[4], Ml[5], Ml[6], Ml[7]);
-                    }
-                }
-                if (TRACE) Tmat[(sbase + (t - 1)) * 32 + lane] = make_uint2(accA, accB);
-                if (p == 31 && bout) ring_out[(u - 1) & 31] = make_uint4(outH, outG, outM, rS);
-            }
-            prevH = rH;
-            if (SUM && ((t & 127) == 0 || t == nsteps)) {
-                T.tilemax[((size_t)s * T.nwin + ((t - 1) >> 7)) * 32 + lane] = best;
-                best = 0;
-            }
-            if (bout) {
-                const int u31 = t - 31;                   // column just finished by the last logical lane
-                if (u31 >= 1 && ((u31 & 31) == 0 || u31 == len1)) {
-                    __syncwarp();
-                    const int ub = ((u31 - 1) & ~31) + 1 + lane;
-                    if (ub <= u31) bout[FWD ? ub : len1 + 1 - ub] = ring_out[lane];
-                    __syncwarp();
-                }
-            }
-        }
-    }
-}
-
 constexpr int SWEEP_WARPS = 4;
 
-template <bool TRACE>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
 {
-    __shared__ uint4 rings[SWEEP_WARPS][2][32];
+    __shared__ WarpRings rings[SWEEP_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (;;) {
         int item = 0;
@@ -224,10 +32,10 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= n_pairs) break;
         const PairTask &T = pairs[item];
-        sweep_pair<+1, TRACE, true>(T, rings[w][0], rings[w][1], lane);
+        sweep_pair_fast<+1>(T, rings[w], lane);
         __threadfence_block();
         __syncwarp();
-        sweep_pair<-1, TRACE, TRACE>(T, rings[w][0], rings[w][1], lane);
+        sweep_pair_fast<-1>(T, rings[w], lane);
         __syncwarp();
     }
 }
@@ -239,58 +47,134 @@ void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cud
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int blocks = (n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS;
-    const int cap = sms * 4;                              // persistent: 4 CTAs x 4 warps per SM
-    if (blocks > cap) blocks = cap;
+    static const int occ = getenv("AGE_OCC") ? atoi(getenv("AGE_OCC")) : 8;
+    if (blocks > sms * occ) blocks = sms * occ;              // persistent: the work counter feeds the warps
     cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st);
-    static const bool fast = getenv("AGE_EXPERIMENT_FAST") != nullptr;     // timing experiment only: no traces
-    static const int occ = getenv("AGE_OCC") ? atoi(getenv("AGE_OCC")) : 4;
-    if (blocks > sms * occ) blocks = sms * occ;
-    if (fast) age_sweep_kernel<false><<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
-    else      age_sweep_kernel<true><<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
+    age_sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
 }
 
 // ------------------------------------------------------------------------------------------------
-// pass 2: breakpoint enumeration (K5-K9) and traceback (K10-K12) over the materialised matrices
+// pass 2
 // ------------------------------------------------------------------------------------------------
 struct View {
-    int len1, len2, nstrips, nsteps, half, flag;
-    const uint32_t *D, *Dtail, *Mr;
-    const uint2 *Tf, *Tr;
+    const PairTask *T;
+    P2Scratch sc;
+    WarpRings *R;
+    int len1, len2, nb, nsteps, nwin, nstrips, half, lane, max2, vwords;
 
-    // The planes are diagonal-major: [strip][step][lane][k].  Forward lane l is at column t-l in step t; reverse
-    // lane l (logical lane 31-l) is at column len1+32-t-l.
-    __device__ size_t fslot(int q, int c) const { const int l = (q & 255) >> 3; return ((size_t)(q >> 8) * nsteps + (c + l - 1)) * 32 + l; }
-    __device__ size_t rslot(int q, int c) const { const int l = (q & 255) >> 3; return ((size_t)(q >> 8) * nsteps + (len1 + 31 - c - l)) * 32 + l; }
+    // ---- geometry --------------------------------------------------------------------------------
+    __device__ int fstep(int q, int c) const { return (c - 1) / W + 1 + ((q & 255) >> 3); }          // forward step of cell (q+1, c)
+    __device__ int rstep(int q, int c) const { return nb - (c - 1) / W + 31 - ((q & 255) >> 3); }    // reverse step
+    __device__ size_t slot(int q, int t) const { return ((size_t)(q >> 8) * nsteps + (t - 1)) * 32 + ((q & 255) >> 3); }
+
+    // ---- on-demand trace windows ---------------------------------------------------------------------
+    __device__ bool valid(int plane, int s, int win) const {
+        const int i = s * nwin + win;
+        return (sc.valid[plane * vwords + (i >> 5)] >> (i & 31)) & 1u;
+    }
+    __device__ void set_valid(int plane, int s, int win) const {
+        const int i = s * nwin + win;
+        __syncwarp();
+        if (lane == 0) sc.valid[plane * vwords + (i >> 5)] |= 1u << (i & 31);
+        __syncwarp();
+    }
+    __device__ void ensure_f(int s, int win) const {
+        if (valid(0, s, win)) return;
+        const TraceOut TO{sc.Tf, nullptr, nullptr, 16 * half, 0};
+        sweep_window_trace<+1>(*T, *R, lane, s, win, TO);
+        set_valid(0, s, win);
+    }
+    __device__ void ensure_r(int s, int win) const {
+        if (valid(1, s, win)) return;
+        const TraceOut TO{sc.Tr, sc.hot, nullptr, 16 * half, max2};
+        sweep_window_trace<-1>(*T, *R, lane, s, win, TO);
+        set_valid(1, s, win);
+    }
+    __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)
+        for (int win = 0; win < nwin; ++win) {
+            if (valid(2, s, win)) continue;
+            const TraceOut TO{sc.Tr, sc.hot, sc.Mp, 16 * half, max2};
+            sweep_window_trace<-1>(*T, *R, lane, s, win, TO);
+            set_valid(1, s, win); set_valid(2, s, win);
+        }
+    }
+    __device__ void reset_valid() const {
+        __syncwarp();
+        for (int i = lane; i < 3 * vwords; i += 32) sc.valid[i] = 0;
+        __syncwarp();
+    }
+    // make the trace of row r, columns c0..c1 (clamped to the interior) resident; warp-uniform
+    __device__ void ensure_f_row(int r, int c0, int c1) const {
+        if (r < 1 || r > len2) return;
+        c0 = max(c0, 1); c1 = min(c1, len1);
+        if (c0 > c1) return;
+        const int q = r - 1, w0 = (fstep(q, c0) - 1) / CKS, w1 = (fstep(q, c1) - 1) / CKS;
+        for (int w = w0; w <= w1; ++w) ensure_f(q >> 8, w);
+    }
+    __device__ void ensure_r_row(int r, int c0, int c1) const {
+        if (r < 1 || r > len2) return;
+        c0 = max(c0, 1); c1 = min(c1, len1);
+        if (c0 > c1) return;
+        const int q = r - 1, w0 = (rstep(q, c1) - 1) / CKS, w1 = (rstep(q, c0) - 1) / CKS;
+        for (int w = w0; w <= w1; ++w) ensure_r(q >> 8, w);
+    }
+
+    // ---- maxima ------------------------------------------------------------------------------------------
     __device__ uint32_t F2w(int r, int c) const {        // packed pair word of 2 * Fmax[r][c]
         if (r < 1 || c < 1 || r > len2 || c > len1) return 0u;
-        if ((r >> 8) == nstrips) return Dtail[c];
-        return D[fslot(r, c) * 8 + (r & 7)];              // D row index = r (shifted by one row, see the sweep)
-    }
-    __device__ uint32_t R2w(int r, int c) const {
-        if (r < 1 || c < 1 || r > len2 || c > len1) return 0u;
-        return Mr[rslot(r - 1, c) * 8 + ((r - 1) & 7)];
+        if (c == len1) return T->Dlast[r];
+        if ((r >> 8) == nstrips) return T->Dtail[c - 1];
+        const int l = (r & 255) >> 3, k = r & 7, t = c / W + 1 + l, w = c % W;   // D is shifted by one row and column
+        return T->D[(((((size_t)(r >> 8) * nsteps + (t - 1)) * W + w) * 2 + (k >> 2)) * 32 + l) * 4 + (k & 3)];
     }
     __device__ int F2(int r, int c) const { return (F2w(r, c) >> (16 * half)) & 0xFFFF; }
-    __device__ int R2(int r, int c) const { return (R2w(r, c) >> (16 * half)) & 0xFFFF; }
-    __device__ uint32_t nibf(int r, int c) const {
-        const uint2 w = Tf[fslot(r - 1, c)];
-        return ((half ? w.y : w.x) >> (4 * ((r - 1) & 7))) & 15u;
+    __device__ int R2(int r, int c) const {              // 2 * Rmax[r][c]; needs ensure_rm(strip of r)
+        if (r < 1 || c < 1 || r > len2 || c > len1) return 0;
+        if (c == 1) return (T->Rfirst[r] >> (16 * half)) & 0xFFFF;
+        const int q = r - 1, l = (q & 255) >> 3, k = q & 7, t = rstep(q, c), w = W * ((c - 1) / W + 1) - c;
+        return (sc.Mp[(((((size_t)(q >> 8) * nsteps + (t - 1)) * W + w) * 2 + (k >> 2)) * 32 + l) * 4 + (k & 3)] >> (16 * half)) & 0xFFFF;
     }
-    __device__ uint32_t nibr(int r, int c) const {
-        const uint2 w = Tr[rslot(r - 1, c)];
-        return ((half ? w.y : w.x) >> (4 * ((r - 1) & 7))) & 15u;
-    }
+
+    // ---- trace (no residency check: callers ensure first) -----------------------------------------------------
     __device__ bool interior(int r, int c) const { return r >= 1 && c >= 1 && r <= len2 && c <= len1; }
+    __device__ uint32_t nibf_nc(int r, int c) const {
+        const int q = r - 1;
+        const uint4 v = sc.Tf[slot(q, fstep(q, c))];
+        const int w = (c - 1) % W;
+        const uint32_t x = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+        return (x >> (4 * (q & 7))) & 15u;
+    }
+    __device__ uint32_t nibr_nc(int r, int c) const {
+        const int q = r - 1;
+        const uint4 v = sc.Tr[slot(q, rstep(q, c))];
+        const int w = W * ((c - 1) / W + 1) - c;
+        const uint32_t x = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
+        return (x >> (4 * (q & 7))) & 15u;
+    }
+    __device__ bool hot_nc(int r, int c) const {          // reverse cell (r, c): Fmax[r-1][c-1] + Rmax[r][c] == max
+        const int q = r - 1;
+        const int w = W * ((c - 1) / W + 1) - c;
+        return (sc.hot[slot(q, rstep(q, c))] >> (8 * w + (q & 7))) & 1u;
+    }
+    // ---- trace with residency check (warp-uniform arguments only) -------------------------------------------
+    __device__ uint32_t nibf(int r, int c) const { const int q = r - 1; ensure_f(q >> 8, (fstep(q, c) - 1) / CKS); return nibf_nc(r, c); }
+    __device__ uint32_t nibr(int r, int c) const { const int q = r - 1; ensure_r(q >> 8, (rstep(q, c) - 1) / CKS); return nibr_nc(r, c); }
     __device__ uint32_t FS(int r, int c) const { return interior(r, c) ? (nibf(r, c) & 3u) : (uint32_t)T_STOP; }
     __device__ uint32_t RS(int r, int c) const { return interior(r, c) ? (nibr(r, c) & 3u) : (uint32_t)T_STOP; }
-    __device__ uint32_t FM(int r, int c) const {         // borders: :874-882
-        if (interior(r, c)) return nibf(r, c) >> 2;
+    __device__ uint32_t FM_border(int r, int c) const {  // :874-882
         if (r == 0) return c >= 1 ? T_HORI : T_STOP;
         if (c == 0) return r <= len2 ? T_VERT : T_STOP;
         return T_STOP;
     }
-    __device__ uint32_t RM(int r, int c) const {         // reverse border keeps RM = 0 (:924-932 sets FM bits there)
-        return interior(r, c) ? (nibr(r, c) >> 2) : (uint32_t)T_STOP;
+    __device__ uint32_t FM(int r, int c) const { return interior(r, c) ? (nibf(r, c) >> 2) : FM_border(r, c); }
+    __device__ uint32_t FM_nc(int r, int c) const { return interior(r, c) ? (nibf_nc(r, c) >> 2) : FM_border(r, c); }
+    // the reverse border keeps RM = 0 (:924-932 sets FM bits there)
+    __device__ uint32_t RM(int r, int c) const { return interior(r, c) ? (nibr(r, c) >> 2) : (uint32_t)T_STOP; }
+    __device__ uint32_t RM_nc(int r, int c) const { return interior(r, c) ? (nibr_nc(r, c) >> 2) : (uint32_t)T_STOP; }
+    // K6 cell (r, c), 0 <= r <= len2, 0 <= c <= len1: does Fmax[r][c] + Rmax[r+1][c+1] equal the maximum?
+    __device__ bool tie_nc(int r, int c) const {
+        if (r < len2 && c < len1) return hot_nc(r + 1, c + 1);
+        return F2(r, c) == max2;                          // Rmax is zero on the border
     }
 };
 
@@ -328,8 +212,8 @@ __device__ int add_bp(const View &V, BpList &L, int lg1, int lg2, int rg1, int r
 }
 
 // K6 findIndelBPs, ordered part (:552-610).  rlo/rhi bound, per row, the columns that can hold a cell with
-// Fmax + Rmax == max (from the hot tiles of the reverse sweep and the border rule); rows with rhi < rlo are skipped.
-__device__ void indel_enumerate(const View &V, BpList &L, int max2, const int *rlo, const int *rhi, int lane)
+// Fmax + Rmax == max (from the hot windows of the reverse sweep and the border rule); rows with rhi < rlo are skipped.
+__device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const int *rhi, int lane)
 {
     const int len2 = V.len2;
     int n_add = 0;
@@ -338,9 +222,11 @@ __device__ void indel_enumerate(const View &V, BpList &L, int max2, const int *r
         const int lo = rlo[r], hi = rhi[r];
         if (hi < lo) continue;
         for (int cb = lo & ~31; cb <= hi && !stop; cb += 32) {
+            V.ensure_r_row(r + 1, cb + 1, cb + 32);
+            V.ensure_f_row(r, cb, cb + 31);
             const int c = cb + lane;
             bool hit = false;
-            if (c >= lo && c <= hi && V.F2(r, c) + V.R2(r + 1, c + 1) == max2) hit = V.FM(r, c) == T_STOP;
+            if (c >= lo && c <= hi && V.tie_nc(r, c)) hit = V.FM_nc(r, c) == T_STOP;
             unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             while (m && !stop) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -357,9 +243,10 @@ __device__ void indel_enumerate(const View &V, BpList &L, int max2, const int *r
         const int lo = rlo[r], hi = rhi[r];
         if (hi < lo) continue;
         for (int cb = hi & ~31; cb >= (lo & ~31) && !stop; cb -= 32) {
+            V.ensure_r_row(r + 1, cb + 1, cb + 32);
             const int c = cb + lane;
             bool hit = false;
-            if (c >= lo && c <= hi && V.F2(r, c) + V.R2(r + 1, c + 1) == max2) hit = V.RM(r + 1, c + 1) == T_STOP;
+            if (c >= lo && c <= hi && V.tie_nc(r, c)) hit = V.RM_nc(r + 1, c + 1) == T_STOP;
             unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             while (m && !stop) {
                 const int b = 31 - __clz(m); m &= ~(1u << b);
@@ -373,51 +260,48 @@ __device__ void indel_enumerate(const View &V, BpList &L, int max2, const int *r
     }
 }
 
-// Hot-tile refinement for one half: every reverse-sweep tile whose maximum equals the split maximum is scanned
-// exactly and the K6 cells (r, c) = (r'-1, c'-1) with Fmax + Rmax == max widen the column range of their row.
-__device__ void indel_row_ranges(const PairTask &T, const View &V, int max2, int *rlo, int *rhi, int lane)
+// Hot-window refinement: every reverse window that holds a (lane, window) tile whose maximum equals the split
+// maximum is re-swept with the trace on; its hot bits widen the column range of the K6 rows they belong to.
+__device__ void indel_row_ranges(const View &V, int *rlo, int *rhi, int lane)
 {
-    const int len1 = T.len1, len2 = T.len2, h = V.half, nsteps = len1 + 31;
+    const PairTask &T = *V.T;
+    const int len1 = V.len1, len2 = V.len2, nb = V.nb, max2 = V.max2;
     for (int r = lane; r <= len2; r += 32) { rlo[r] = 0x7FFFFFFF; rhi[r] = -1; }
     __syncwarp();
-    const int ntiles = T.nstrips * T.nwin * 32;
-    for (int tb = 0; tb < ntiles; tb += 32) {
-        const int ti = tb + lane;
-        const bool hot = ti < ntiles && (int)((T.tilemax[ti] >> (16 * h)) & 0xFFFF) == max2;
-        unsigned m = __ballot_sync(0xFFFFFFFFu, hot);
-        while (m) {
-            const int tile = tb + __ffs(m) - 1; m &= m - 1;
-            const int l = tile & 31, w = (tile >> 5) % T.nwin, s = (tile >> 5) / T.nwin;
-            const int q0 = s * STRIP + l * RPT, p = 31 - l;
-            for (int i = lane; i < 128; i += 32) {
-                const int t = 128 * w + 1 + i;                        // reverse step
-                const int u = t - p;                                  // its logical column for lane l
-                if (u < 1 || u > len1) continue;
-                const int c = len1 + 1 - u;                           // reverse cell column c' (1..len1)
-                const uint32_t *mr = T.Mr + (((size_t)s * nsteps + (t - 1)) * 32 + l) * 8;
-                const uint32_t *df = T.D + (((size_t)s * nsteps + (c - 2 + l)) * 32 + l) * 8;
-                for (int k = 0; k < RPT; ++k) {
-                    const int q = q0 + k;                             // reverse cell row r' = q+1
-                    if (q >= len2) break;
-                    const int rv = (mr[k] >> (16 * h)) & 0xFFFF;
-                    const int fv = c >= 2 ? (int)((df[k] >> (16 * h)) & 0xFFFF) : 0;
-                    if (rv + fv == max2) { atomicMin(&rlo[q], c - 1); atomicMax(&rhi[q], c - 1); }
-                }
+    if (max2 == 0) {                                                  // everything ties at zero: scan it all
+        for (int r = lane; r <= len2; r += 32) { rlo[r] = 0; rhi[r] = len1; }
+        __syncwarp();
+        return;
+    }
+    const int nwt = T.nstrips * T.nwin;
+    for (int wi = 0; wi < nwt; ++wi) {
+        const bool hot = (int)((T.tilemax[(size_t)wi * 32 + lane] >> (16 * V.half)) & 0xFFFF) == max2;
+        if (!__any_sync(0xFFFFFFFFu, hot)) continue;
+        const int s = wi / T.nwin, win = wi % T.nwin;
+        V.ensure_r(s, win);
+        const int t1 = min(CKS * win + CKS, T.nsteps);
+        for (int t = CKS * win + 1; t <= t1; ++t) {
+            const int bq = t - 31 + lane;                             // logical reverse block of this lane
+            if (bq < 1 || bq > nb) continue;
+            uint32_t hw = V.sc.hot[((size_t)s * T.nsteps + (t - 1)) * 32 + lane];
+            while (hw) {
+                const int bit = __ffs(hw) - 1; hw &= hw - 1;
+                const int w = bit >> 3, k = bit & 7;
+                const int r = s * STRIP + lane * RPT + k + 1;         // reverse cell (r, c)
+                const int c = W * (nb + 1 - bq) - w;
+                if (r > len2 || c > len1) continue;                   // padding
+                atomicMin(&rlo[r - 1], c - 1); atomicMax(&rhi[r - 1], c - 1);
             }
         }
     }
     __syncwarp();
     // border cells of K6 (r = len2 or c = len1): Rmax is zero there, so they tie only when Fmax itself == max
     if (V.F2(len2, len1) == max2) {
-        // row len2: Fmax[len2][c] is non-decreasing in c -> first column that reaches max
-        int lo = 1, hi = len1;
+        int lo = 1, hi = len1;                                        // Fmax[len2][c] is non-decreasing in c
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.F2(len2, mid) >= max2) hi = mid; else lo = mid + 1; }
         if (lane == 0) { rlo[len2] = min(rlo[len2], lo); rhi[len2] = len1; }
         for (int r = 1 + lane; r < len2; r += 32)
             if (V.F2(r, len1) == max2) { rlo[r] = min(rlo[r], len1); rhi[r] = len1; }
-    }
-    if (max2 == 0) {                                                  // everything ties at zero: scan it all
-        for (int r = lane; r <= len2; r += 32) { rlo[r] = 0; rhi[r] = len1; }
     }
     __syncwarp();
 }
@@ -426,16 +310,22 @@ __device__ void indel_row_ranges(const PairTask &T, const View &V, int max2, int
 // rows are binary-searched for the run of matching values and every H-chain of the maxima trace (whose
 // members share one traceBackMaxima endpoint, hence one addBpoints key) is tried once -- the later members
 // of a chain are guaranteed duplicates (:652-655) and change nothing.
-__device__ void invtdup_enumerate(const View &V, BpList &L, int max2, int lane)
+__device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
 {
-    const int len1 = V.len1, len2 = V.len2;
+    const int len1 = V.len1, len2 = V.len2, max2 = V.max2;
+    const uint32_t *colF = V.T->Dlast, *colR = V.T->Rfirst;
+    const int sh = 16 * V.half;
+    auto A = [&](int r) { return r >= 1 ? (int)((colF[r] >> sh) & 0xFFFF) : 0; };                 // 2*Fmax[r][len1]
+    auto B = [&](int r) { return (r >= 1 && r <= len2) ? (int)((colR[r] >> sh) & 0xFFFF) : 0; };  // 2*Rmax[r][1]
     int n_add = 0;
     bool stop = false;
     for (int r = 0; r <= len2 && !stop; ++r) {                            // forward (:485-504)
-        if (V.F2(r, len1) + V.R2(r + 1, 1) != max2) continue;
+        if (A(r) + B(r + 1) != max2) continue;
+        if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
         for (int jb = 0; jb <= len1 && !stop; jb += 32) {
+            V.ensure_f_row(r, jb, jb + 31);
             const int j = jb + lane;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, j <= len1 && V.FM(r, j) == T_STOP);
+            unsigned m = __ballot_sync(0xFFFFFFFFu, j <= len1 && V.FM_nc(r, j) == T_STOP);
             while (m && !stop) {
                 const int j1 = jb + __ffs(m) - 1; m &= m - 1;
                 const int tv = max2 - V.F2(r, j1);
@@ -459,10 +349,12 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int max2, int lane)
     }
     n_add = 0; stop = false;
     for (int i2 = len2 + 1; i2 >= 1 && !stop; --i2) {                     // reverse (:515-534)
-        if (V.F2(i2 - 1, len1) + V.R2(i2, 1) != max2) continue;
+        if (A(i2 - 1) + B(i2) != max2) continue;
+        if (i2 <= len2) V.ensure_rm((i2 - 1) >> 8);
         for (int jb = ((len1 + 1) / 32) * 32; jb >= 0 && !stop; jb -= 32) {
+            V.ensure_r_row(i2, jb, jb + 31);
             const int j = jb + lane;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, j >= 1 && j <= len1 + 1 && V.RM(i2, j) == T_STOP);
+            unsigned m = __ballot_sync(0xFFFFFFFFu, j >= 1 && j <= len1 + 1 && V.RM_nc(i2, j) == T_STOP);
             while (m && !stop) {
                 const int b = 31 - __clz(m); m &= ~(1u << b);
                 const int j2 = jb + b;
@@ -488,7 +380,7 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int max2, int lane)
 }
 
 // K11 findLeftBlocks (:752-808).  dst == nullptr: count only.  Blocks are produced last-first.
-__device__ int left_blocks(const View &V, int c, int r, Block *dst, int n_total)
+__device__ int left_blocks(const View &V, int c, int r, Block *dst, int n_total, int lane)
 {
     int n = 0, run = 0, last_c = 0, last_r = 0;
     uint32_t t;
@@ -496,19 +388,19 @@ __device__ int left_blocks(const View &V, int c, int r, Block *dst, int n_total)
         if (t == T_DIAG) {
             if (run > 0 && last_c - c == 1 && last_r - r == 1) ++run;
             else {
-                if (run > 0) { if (dst) dst[n_total - 1 - n] = Block{last_c, last_r, run}; ++n; }
+                if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{last_c, last_r, run}; ++n; }
                 run = 1;
             }
             last_c = c; last_r = r; --c; --r;
         } else if (t == T_HORI) --c;
         else --r;
     }
-    if (run > 0) { if (dst) dst[n_total - 1 - n] = Block{last_c, last_r, run}; ++n; }
+    if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{last_c, last_r, run}; ++n; }
     return n;
 }
 
 // K12 findRightBlocks (:810-860)
-__device__ int right_blocks(const View &V, int c, int r, Block *dst)
+__device__ int right_blocks(const View &V, int c, int r, Block *dst, int lane)
 {
     int n = 0, run = 0, s1 = 0, s2 = 0;
     uint32_t t;
@@ -518,20 +410,46 @@ __device__ int right_blocks(const View &V, int c, int r, Block *dst)
             ++c; ++r;
         } else {
             if (t == T_HORI) ++c; else ++r;
-            if (run > 0) { if (dst) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
+            if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
         }
     }
-    if (run > 0) { if (dst) dst[n] = Block{s1, s2, run}; ++n; }
+    if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; }
     return n;
 }
 
 constexpr int P2_WARPS = 4;
 
+__host__ __device__ inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+__host__ __device__ inline size_t p2_vwords(size_t max_slots) { return max_slots / 32 + 2; }   // one bit per window, windows <= slots
+
+__device__ P2Scratch carve_scratch(char *base, size_t max_slots, size_t max_rows, int need_mp, int &vwords)
+{
+    P2Scratch sc;
+    sc.Tf = (uint4 *)base; base += up256(max_slots * 32 * 16);
+    sc.Tr = (uint4 *)base; base += up256(max_slots * 32 * 16);
+    sc.hot = (uint32_t *)base; base += up256(max_slots * 32 * 4);
+    sc.Mp = need_mp ? (uint32_t *)base : nullptr; base += need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0;
+    vwords = (int)p2_vwords(max_slots);
+    sc.valid = (uint32_t *)base; base += up256((size_t)3 * vwords * 4);
+    sc.rowrange = (int32_t *)base;
+    return sc;
+}
+
+size_t pass2_scratch_bytes(size_t max_slots, size_t max_rows, int need_mp)
+{
+    return 2 * up256(max_slots * 32 * 16) + up256(max_slots * 32 * 4) + (need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0) +
+           up256(3 * p2_vwords(max_slots) * 4) + up256(2 * (max_rows + 2) * 4);
+}
+
 __global__ void __launch_bounds__(P2_WARPS * 32)
 age_pass2_kernel(Pass2Params prm)
 {
     __shared__ int bp_s[P2_WARPS][MAX_BP][4];
+    __shared__ WarpRings rings[P2_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int gw = blockIdx.x * P2_WARPS + w;
+    int vwords = 0;
+    const P2Scratch sc = carve_scratch(prm.scratch + (size_t)gw * prm.scratch_stride, prm.max_slots, prm.max_rows, prm.need_mp, vwords);
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(prm.next, 1);
@@ -541,19 +459,19 @@ age_pass2_kernel(Pass2Params prm)
         const int len1 = T.len1, len2 = T.len2;
 
         // ---- split maxima of both halves (:545-550 / :476-481) ------------------------------------------
-        uint32_t mx_indel = 0;                                   // packed u16x2: max of 2*(Fmax + Rmax)
+        uint32_t mx_indel = 0, mx_col = 0;                       // packed u16x2: max of 2*(Fmax + Rmax)
         const int ntiles = T.nstrips * T.nwin * 32;
         for (int i = lane; i < ntiles; i += 32) mx_indel = __vmaxu2(mx_indel, T.tilemax[i]);
-        const View V0{len1, len2, T.nstrips, len1 + 31, 0, 0, T.D, T.Dtail, T.Mr, T.Tf, T.Tr};
-        uint32_t mx_col = 0;
-        if (T.flag[0] != F_INDEL || T.flag[1] != F_INDEL)
-            for (int r = lane; r <= len2; r += 32) mx_col = __vmaxu2(mx_col, __vadd2(V0.F2w(r, len1), V0.R2w(r + 1, 1)));
+        for (int r = lane; r <= len2; r += 32) {
+            const uint32_t f = r >= 1 ? T.Dlast[r] : 0u, q = r + 1 <= len2 ? T.Rfirst[r + 1] : 0u;
+            mx_col = __vmaxu2(mx_col, __vadd2(f, q));
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             mx_indel = __vmaxu2(mx_indel, __shfl_xor_sync(0xFFFFFFFFu, mx_indel, o));
             mx_col   = __vmaxu2(mx_col,   __shfl_xor_sync(0xFFFFFFFFu, mx_col, o));
         }
-        mx_indel = __vmaxu2(mx_indel, V0.F2w(len2, len1));                          // Fmax[len2][len1] + 0 (border cells)
+        mx_indel = __vmaxu2(mx_indel, T.Dlast[len2]);            // Fmax[len2][len1] + 0 (border cells)
         int max2[2];
         for (int h = 0; h < 2; ++h) {
             const uint32_t v = (T.flag[h] == F_INDEL) ? mx_indel : mx_col;
@@ -572,69 +490,76 @@ age_pass2_kernel(Pass2Params prm)
 
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
-            View V{len1, len2, T.nstrips, len1 + 31, h, T.flag[h], T.D, T.Dtail, T.Mr, T.Tf, T.Tr};
+            const View V{&T, sc, &rings[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], vwords};
+            V.reset_valid();
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
             __syncwarp();
             if (T.flag[h] == F_INDEL) {
-                int *rlo = T.rowrange, *rhi = T.rowrange + (len2 + 2);
-                indel_row_ranges(T, V, max2[h], rlo, rhi, lane);
-                indel_enumerate(V, L, max2[h], rlo, rhi, lane);
-            } else invtdup_enumerate(V, L, max2[h], lane);
+                int *rlo = sc.rowrange, *rhi = sc.rowrange + (len2 + 2);
+                indel_row_ranges(V, rlo, rhi, lane);
+                indel_enumerate(V, L, rlo, rhi, lane);
+            } else invtdup_enumerate(V, L, lane);
             __syncwarp();
             // ---- K10: blocks of bpoint 0 and of the alternative shown by printAlignment (:287-306) ----
+            // (the walks are executed by the whole warp: a trace window that is not resident is re-swept by all lanes)
             if (lane == 0) {
                 O.status = 0;
                 O.score = max2[h] >> 1;
                 O.n_bp = L.n;
                 for (int i = 0; i < L.n; ++i)
                     for (int k = 0; k < 4; ++k) O.bp[i][k] = L.bp[i][k];
-                int alt = -1;
-                for (int which = 0; which < 2; ++which) {
-                    int idx = 0;
-                    int nl = 0, nr = 0;
-                    if (which == 0) {
-                        nl = left_blocks(V, L.bp[0][0], L.bp[0][1], nullptr, 0);
-                        nr = right_blocks(V, L.bp[0][2], L.bp[0][3], nullptr);
-                    } else {
-                        for (idx = L.n - 1; idx >= 1; --idx) {
-                            nl = left_blocks(V, L.bp[idx][0], L.bp[idx][1], nullptr, 0);
-                            nr = right_blocks(V, L.bp[idx][2], L.bp[idx][3], nullptr);
-                            if (nl + nr > 0) break;
-                        }
-                        if (idx < 1) { nl = nr = 0; idx = -1; }
-                        alt = idx;
+            }
+            int alt = -1;
+            for (int which = 0; which < 2; ++which) {
+                int idx = 0, nl = 0, nr = 0;
+                if (which == 0) {
+                    nl = left_blocks(V, L.bp[0][0], L.bp[0][1], nullptr, 0, lane);
+                    nr = right_blocks(V, L.bp[0][2], L.bp[0][3], nullptr, lane);
+                } else {
+                    for (idx = L.n - 1; idx >= 1; --idx) {
+                        nl = left_blocks(V, L.bp[idx][0], L.bp[idx][1], nullptr, 0, lane);
+                        nr = right_blocks(V, L.bp[idx][2], L.bp[idx][3], nullptr, lane);
+                        if (nl + nr > 0) break;
                     }
-                    int off = 0;
-                    if (nl + nr > 0) {
-                        off = atomicAdd(prm.pool_used, nl + nr);
-                        if (off + nl + nr <= prm.pool_cap) {
-                            left_blocks(V, L.bp[idx][0], L.bp[idx][1], prm.pool + off, nl);
-                            right_blocks(V, L.bp[idx][2], L.bp[idx][3], prm.pool + off + nl);
-                        } else O.status = -4;                   // pool overflow: host retries with a larger pool
-                    }
+                    if (idx < 1) { nl = nr = 0; idx = -1; }
+                    alt = idx;
+                }
+                int off = 0;
+                if (nl + nr > 0) {
+                    if (lane == 0) off = atomicAdd(prm.pool_used, nl + nr);
+                    off = __shfl_sync(0xFFFFFFFFu, off, 0);
+                    if (off + nl + nr <= prm.pool_cap) {
+                        left_blocks(V, L.bp[idx][0], L.bp[idx][1], prm.pool + off, nl, lane);
+                        right_blocks(V, L.bp[idx][2], L.bp[idx][3], prm.pool + off + nl, lane);
+                    } else if (lane == 0) O.status = -4;          // pool overflow: host retries with a larger pool
+                }
+                if (lane == 0) {
                     O.n_blk[2 * which] = nl; O.n_blk[2 * which + 1] = nr;
                     O.blk_off[2 * which] = off; O.blk_off[2 * which + 1] = off + nl;
                 }
-                O.alt_index = alt;
             }
+            if (lane == 0) O.alt_index = alt;
             __syncwarp();
         }
     }
 }
 
-void launch_pass2(const Pass2Params &p, cudaStream_t st)
+int pass2_warps(int n_pairs)
 {
-    if (p.n_pairs <= 0) return;
-    if (getenv("AGE_EXPERIMENT_FAST")) return;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int blocks = (p.n_pairs + P2_WARPS - 1) / P2_WARPS;
-    const int cap = sms * 4;
-    if (blocks > cap) blocks = cap;
+    int blocks = (n_pairs + P2_WARPS - 1) / P2_WARPS;
+    if (blocks > sms * 2) blocks = sms * 2;
+    return blocks * P2_WARPS;
+}
+
+void launch_pass2(const Pass2Params &p, int n_warps, cudaStream_t st)
+{
+    if (p.n_pairs <= 0) return;
     cudaMemsetAsync(p.next, 0, sizeof(int32_t), st);
-    age_pass2_kernel<<<blocks, P2_WARPS * 32, 0, st>>>(p);
+    age_pass2_kernel<<<n_warps / P2_WARPS, P2_WARPS * 32, 0, st>>>(p);
 }
 
 } // namespace age

@@ -1,0 +1,384 @@
+// age_sweep.cuh -- the wavefront sweep shared by the main sweep kernel (MODE_FAST) and by the on-demand trace
+// recomputation of pass 2 (MODE_TRACE).
+//
+// Reference semantics (src/AsmvarAGE/src/AGEaligner.cpp): K1/K2 calcScores :978-1083 and K3/K4 calcMaxima :862-976.
+// One warp sweeps one strip (32 lanes x 8 rows) of one pair along the reference window; lane p works on block
+// t-p (4 columns) in step t and hands the H/G/M values of its bottom row to lane p+1 with warp shuffles.
+#pragma once
+#include "age_device.cuh"
+
+namespace age {
+
+enum { MODE_FAST = 0, MODE_TRACE = 1 };
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
+__device__ __forceinline__ int half16(uint32_t v, int sh) { return (int)(short)((v >> sh) & 0xFFFFu); }
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// substitution score (x2) of one half for a special column (Scorer.hh:24-39): codes >= 5 score 0
+__device__ __forceinline__ int subst2(int xc, int yc, int m2, int mm2)
+{
+    if (xc >= 5 || yc >= 5) return 0;
+    return xc == yc ? m2 : mm2;
+}
+// FS code of one cell from its three (2x+tag) candidates -- the tie order of :1015-1017
+__device__ __forceinline__ uint32_t fs_code(int d, int h, int v)
+{
+    int s = d; uint32_t t = T_DIAG;
+    if (h >= s) { s = h; t = T_HORI; }
+    if (v >= s) { s = v; t = T_VERT; }
+    if (s < 0) t = T_STOP;
+    return t;
+}
+// FM code (:899-915 / :952-968): VERTICAL is tested first, HORIZONTAL overrides when strictly greater
+__device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
+{
+    int cur = own; uint32_t t = T_STOP;
+    if (up > cur)   { cur = up; t = T_VERT; }
+    if (left > cur) { t = T_HORI; }
+    return t;
+}
+
+struct LaneState {
+    uint32_t Hl[RPT], Gl[RPT], Ml[RPT];    // row state at the last finished column
+    uint32_t oH[W], oG[W], oM[W];          // bottom-row outputs of the last finished block (shuffled to lane p+1)
+    uint32_t pH, pM;                       // H / M of the row above at the last finished column (diagonal / D row shift)
+};
+
+struct WarpRings {                          // shared memory of one warp
+    uint4 in[2][3][32];                     // double-buffered boundary feed of lane p = 0: planes H, G, M
+    uint4 out[3][32];                       // boundary rows produced by lane p = 31
+};
+
+struct TraceOut {                           // MODE_TRACE outputs (one half of the pair)
+    uint4 *T; uint32_t *hot; uint32_t *Mp;
+    int sh;                                 // 0 / 16: the half whose trace is wanted
+    int max2;                               // hot bit = (2*Fmax + 2*Rmax == max2)
+};
+
+template <int DIR> __device__ __forceinline__ uint32_t shfl_prev(uint32_t v)
+{
+    return DIR > 0 ? __shfl_up_sync(0xFFFFFFFFu, v, 1) : __shfl_down_sync(0xFFFFFFFFu, v, 1);
+}
+
+// Everything one (pair, direction, strip) sweep needs, hoisted out of the PairTask once.
+template <int DIR> struct StripCtx {
+    int len1, nb, nsteps, nwin, s, q0, lane, p;
+    size_t sbase;                           // s * nsteps
+    uint32_t c0x, kabs, flip, gborder, m2, mm2;
+    uint32_t Ta[RPT], Tb[RPT];
+    const uint4 *xblk;
+    const uint8_t *ycode;
+    const uint4 *bin; uint4 *bout;          // boundary planes in / out (nullptr at the first / last strip)
+    uint4 *D4;                              // D as uint4
+    uint4 *Dtail4;                          // forward, last lane of the last strip only (else nullptr)
+    uint32_t *tilemax;
+    uint32_t *ckpt;
+    bool first;                             // no boundary input: the strip starts at the matrix border
+
+    __device__ __forceinline__ void init(const PairTask &T, int s_, int si, int lane_)
+    {
+        constexpr bool FWD = DIR > 0;
+        len1 = T.len1; nb = T.nb; nsteps = T.nsteps; nwin = T.nwin; s = s_; lane = lane_;
+        p = FWD ? lane : 31 - lane;
+        q0 = s * STRIP + lane * RPT;
+        sbase = (size_t)s * nsteps;
+        c0x = T.c0x; kabs = T.kabs; flip = T.flip; gborder = T.gborder; m2 = T.m2; mm2 = T.mm2;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) { const uint2 y = __ldg(T.ytab + q0 + k); Ta[k] = y.x; Tb[k] = y.y; }
+        xblk = FWD ? T.xblk_f : T.xblk_r;
+        ycode = T.ycode;
+        uint4 *bnd = FWD ? T.bnd_f : T.bnd_r;
+        first = si == 0;
+        bin = first ? nullptr : bnd + (size_t)(si - 1) * 3 * (nb + 1);
+        bout = (si + 1 < T.nstrips) ? bnd + (size_t)si * 3 * (nb + 1) : nullptr;
+        D4 = reinterpret_cast<uint4 *>(T.D);
+        Dtail4 = (FWD && p == 31 && si + 1 == T.nstrips) ? reinterpret_cast<uint4 *>(T.Dtail) : nullptr;
+        tilemax = T.tilemax;
+        ckpt = FWD ? T.ckpt_f : T.ckpt_r;
+    }
+};
+
+__device__ __forceinline__ void state_init(LaneState &S, uint32_t gborder)
+{
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { S.Hl[k] = 0; S.Gl[k] = gborder; S.Ml[k] = 0; }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { S.oH[w] = 0; S.oG[w] = gborder; S.oM[w] = 0; }
+    S.pH = 0; S.pM = 0;
+}
+
+__device__ __forceinline__ void state_save(const LaneState &S, uint32_t *dst /* + lane */)
+{
+    int i = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { dst[32 * i++] = S.Hl[k]; }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { dst[32 * i++] = S.Gl[k]; }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { dst[32 * i++] = S.Ml[k]; }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { dst[32 * i++] = S.oH[w]; }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { dst[32 * i++] = S.oG[w]; }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { dst[32 * i++] = S.oM[w]; }
+    dst[32 * i++] = S.pH; dst[32 * i++] = S.pM;
+}
+
+__device__ __forceinline__ void state_load(LaneState &S, const uint32_t *src /* + lane */)
+{
+    int i = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { S.Hl[k] = __ldcg(src + 32 * i++); }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { S.Gl[k] = __ldcg(src + 32 * i++); }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { S.Ml[k] = __ldcg(src + 32 * i++); }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { S.oH[w] = __ldcg(src + 32 * i++); }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { S.oG[w] = __ldcg(src + 32 * i++); }
+#pragma unroll
+    for (int w = 0; w < W; ++w) { S.oM[w] = __ldcg(src + 32 * i++); }
+    S.pH = __ldcg(src + 32 * i++); S.pM = __ldcg(src + 32 * i++);
+}
+
+// asynchronous copy of the boundary blocks that lane p = 0 consumes in window `win` into ring buffer `buf`
+template <int DIR>
+__device__ __forceinline__ void ring_prefetch(const StripCtx<DIR> &C, WarpRings &R, int win, int buf)
+{
+    const int b = CKS * win + 1 + C.lane;
+    if (C.bin && b <= C.nb) {
+#pragma unroll
+        for (int pl = 0; pl < 3; ++pl) cp_async16(&R.in[buf][pl][C.lane], C.bin + (size_t)pl * (C.nb + 1) + b);
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void ring_fill_border(WarpRings &R, int lane, uint32_t gborder)
+{
+#pragma unroll
+    for (int buf = 0; buf < 2; ++buf) {
+        R.in[buf][0][lane] = make_uint4(0, 0, 0, 0);
+        R.in[buf][1][lane] = make_uint4(gborder, gborder, gborder, gborder);
+        R.in[buf][2][lane] = make_uint4(0, 0, 0, 0);
+    }
+    __syncwarp();
+}
+
+// One window (steps t0 .. t1) of one strip.  GUARD = false is the steady state in which every lane is active in
+// every step of the window.
+template <int DIR, int MODE, bool GUARD>
+__device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, const int win,
+                                             const int t0, const int t1, uint32_t &best, const TraceOut &TO)
+{
+    constexpr bool FWD = DIR > 0;
+    constexpr bool TRACE = MODE == MODE_TRACE;
+    const int lane = C.lane, p = C.p, nb = C.nb;
+    const int buf = win & 1;
+    auto xload = [&](int b) { return __ldg(C.xblk + min(max(b, 0), nb + 1)); };
+    uint4 xnext = xload(t0 - p);
+
+    for (int t = t0; t <= t1; ++t) {
+        const uint4 xb = xnext;
+        xnext = xload(t + 1 - p);
+        // ---- values of the row above for the 4 columns of this block -------------------------------------
+        uint32_t uH[W], uG[W], uM[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
+        if (p == 0) {
+            const int e = (t - 1) & 31;
+            const uint4 h = R.in[buf][0][e], g = R.in[buf][1][e], m = R.in[buf][2][e];
+            uH[0] = h.x; uH[1] = h.y; uH[2] = h.z; uH[3] = h.w;
+            uG[0] = g.x; uG[1] = g.y; uG[2] = g.z; uG[3] = g.w;
+            uM[0] = m.x; uM[1] = m.y; uM[2] = m.z; uM[3] = m.w;
+        }
+        const int b = t - p;
+        if (!GUARD || (b >= 1 && b <= nb)) {
+            const size_t slot = C.sbase + (size_t)(t - 1);
+            // reverse sweep: the shifted forward maxima of this block, written by the forward lane in step nb+32-t
+            uint4 dq[W][2];
+            if (!FWD) {
+                const uint4 *src = C.D4 + ((C.sbase + (size_t)(nb + 31 - t)) * W) * 64 + lane;
+#pragma unroll
+                for (int w = 0; w < W; ++w) { dq[w][0] = __ldcg(src + (w * 2 + 0) * 32); dq[w][1] = __ldcg(src + (w * 2 + 1) * 32); }
+            }
+            const bool special = (xb.z & 0x01010101u) != 0;
+            uint32_t tw[W];
+            uint32_t hotw = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                // ---- forward: D[w] = maxima at the previous column, rows shifted by one (entry 0 = row above) ----
+                const uint32_t upMprev = w == 0 ? S.pM : uM[w - 1];
+                if (FWD && !TRACE) {
+                    uint4 *dst = C.D4 + (slot * W + w) * 64 + lane;
+                    dst[0]  = make_uint4(upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
+                    dst[32] = make_uint4(S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
+                }
+                // ---- substitution scores of this column ---------------------------------------------------------
+                uint32_t S2[RPT];
+                if (special) {
+                    const uint32_t info = (xb.z >> (8 * w)) & 0xFFu;
+                    if (info & 1u) {
+                        const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
+                        const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) {
+                            const int yc = C.ycode[C.q0 + k];
+                            const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
+                            S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
+                        }
+                    } else {
+                        const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
+#pragma unroll
+                        for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
+                    }
+                } else {
+                    const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
+                }
+                // ---- the column ---------------------------------------------------------------------------------
+                uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
+                uint32_t nibw = 0;
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const int k = FWD ? j : RPT - 1 - j;
+                    const uint32_t g  = __vmaxs2(S.Gl[k], vG);
+                    const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);      // max(2d, 2h+1, 2v+1, 0)
+                    const uint32_t tg = (s2 ^ C.flip) & 0x00010001u;
+                    const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);         // 2*(s + (gap ? ge : go)) + 1
+                    const uint32_t Hc = s2 & 0xFFFEFFFEu;
+                    const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
+                    if (TRACE) {
+                        const uint32_t d2 = __vadd2(dg, S2[k]);
+                        const uint32_t nb4 = fs_code(half16(d2, TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) |
+                                             (fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << 2);
+                        nibw |= nb4 << (4 * k);
+                    }
+                    if (!FWD) {
+                        const uint4 dv = dq[W - 1 - w][k >> 2];
+                        const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
+                        const uint32_t sum = __vadd2(Mn, dk);
+                        if (!TRACE) best = __vmaxu2(best, sum);
+                        else if ((int)((sum >> TO.sh) & 0xFFFFu) == TO.max2) hotw |= 1u << (8 * w + k);
+                    }
+                    dg = S.Hl[k];
+                    S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
+                    vG = G2; vM = Mn;
+                }
+                constexpr int last = FWD ? RPT - 1 : 0;
+                S.oH[w] = S.Hl[last]; S.oG[w] = S.Gl[last]; S.oM[w] = S.Ml[last];
+                tw[w] = nibw;
+                if (TRACE && TO.Mp) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(TO.Mp) + (slot * W + w) * 64 + lane;
+                    dst[0]  = make_uint4(S.Ml[0], S.Ml[1], S.Ml[2], S.Ml[3]);
+                    dst[32] = make_uint4(S.Ml[4], S.Ml[5], S.Ml[6], S.Ml[7]);
+                }
+            }
+            S.pH = uH[W - 1]; S.pM = uM[W - 1];
+            if (TRACE) {
+                TO.T[slot * 32 + lane] = make_uint4(tw[0], tw[1], tw[2], tw[3]);
+                if (!FWD && TO.hot) TO.hot[slot * 32 + lane] = hotw;
+            }
+            if (!TRACE) {
+                if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
+                if (p == 31 && C.bout) {
+                    const int e = (b - 1) & 31;
+                    R.out[0][e] = make_uint4(S.oH[0], S.oH[1], S.oH[2], S.oH[3]);
+                    R.out[1][e] = make_uint4(S.oG[0], S.oG[1], S.oG[2], S.oG[3]);
+                    R.out[2][e] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
+                }
+            }
+        }
+        if (!TRACE && C.bout) {
+            const int b31 = t - 31;                      // block just finished by the last logical lane
+            if (b31 >= 1 && ((b31 & 31) == 0 || b31 == nb)) {
+                __syncwarp();
+                const int bb = ((b31 - 1) & ~31) + 1 + lane;
+                if (bb <= b31) {
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) C.bout[(size_t)pl * (nb + 1) + bb] = R.out[pl][lane];
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// dispatch on whether the window is steady (all lanes active in all of its steps)
+template <int DIR, int MODE>
+__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, int win,
+                                                 uint32_t &best, const TraceOut &TO)
+{
+    const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
+    if (t0 >= 32 && t1 <= C.nb) sweep_window<DIR, MODE, false>(C, S, R, win, t0, t1, best, TO);
+    else                        sweep_window<DIR, MODE, true>(C, S, R, win, t0, t1, best, TO);
+}
+
+// The main sweep of one pair in one direction: all strips, all windows, checkpoints and tile maxima.
+template <int DIR>
+__device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, const int lane)
+{
+    constexpr bool FWD = DIR > 0;
+    const TraceOut none{nullptr, nullptr, nullptr, 0, 0};
+    for (int si = 0; si < T.nstrips; ++si) {
+        const int s = FWD ? si : T.nstrips - 1 - si;
+        StripCtx<DIR> C;
+        C.init(T, s, si, lane);
+        LaneState S;
+        state_init(S, C.gborder);
+        if (C.first) ring_fill_border(R, lane, C.gborder);
+        else ring_prefetch(C, R, 0, 0);
+        uint32_t best = 0;
+        for (int win = 0; win < C.nwin; ++win) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (!C.first && win + 1 < C.nwin) ring_prefetch(C, R, win + 1, (win + 1) & 1);
+            state_save(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
+            sweep_window_any<DIR, MODE_FAST>(C, S, R, win, best, none);
+            if (!FWD) { C.tilemax[(size_t)(s * C.nwin + win) * 32 + lane] = best; best = 0; }
+        }
+        // the maxima at the last processed column: Fmax[.][len1] (forward) / Rmax[.][1] (reverse)
+        uint32_t *col = FWD ? T.Dlast : T.Rfirst;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) col[C.q0 + k + 1] = S.Ml[k];
+        if (s == 0 && lane == 0) col[0] = 0;
+        __syncwarp();
+    }
+}
+
+// Recompute one window of one strip from its checkpoint, emitting the trace (pass 2).
+template <int DIR>
+__device__ void sweep_window_trace(const PairTask &T, WarpRings &R, const int lane, int s, int win, const TraceOut &TO)
+{
+    constexpr bool FWD = DIR > 0;
+    const int si = FWD ? s : T.nstrips - 1 - s;
+    StripCtx<DIR> C;
+    C.init(T, s, si, lane);
+    LaneState S;
+    state_load(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
+    __syncwarp();
+    if (C.first) ring_fill_border(R, lane, C.gborder);
+    else { ring_prefetch(C, R, win, win & 1); cp_async_wait_all(); __syncwarp(); }
+    uint32_t best = 0;
+    sweep_window_any<DIR, MODE_TRACE>(C, S, R, win, best, TO);
+    __syncwarp();
+}
+
+} // namespace age
