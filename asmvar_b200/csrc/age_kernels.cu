@@ -16,10 +16,16 @@
 #include "age_sweep.cuh"
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace age {
 
 constexpr int SWEEP_WARPS = 4;
+
+// optional cycle accounting of pass 2 (AGE_P2_PROF=1): 0 maxima, 1 row ranges, 2 enumerate, 3 blocks, 4 forward re-sweeps,
+// 5 reverse re-sweeps, 6 number of forward windows, 7 number of reverse windows
+__device__ unsigned long long g_prof[8];
+#define PROF_ADD(i, v) atomicAdd(&g_prof[i], (unsigned long long)(v))
 
 __global__ void __launch_bounds__(SWEEP_WARPS * 32)
 age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
@@ -81,14 +87,18 @@ struct View {
     __device__ void ensure_f(int s, int win) const {
         if (valid(0, s, win)) return;
         const TraceOut TO{sc.Tf, nullptr, nullptr, 16 * half, 0};
+        const long long c0 = clock64();
         sweep_window_trace<+1>(*T, *R, lane, s, win, TO);
         set_valid(0, s, win);
+        if (lane == 0) { PROF_ADD(4, clock64() - c0); PROF_ADD(6, 1); }
     }
     __device__ void ensure_r(int s, int win) const {
         if (valid(1, s, win)) return;
         const TraceOut TO{sc.Tr, sc.hot, nullptr, 16 * half, max2};
+        const long long c0 = clock64();
         sweep_window_trace<-1>(*T, *R, lane, s, win, TO);
         set_valid(1, s, win);
+        if (lane == 0) { PROF_ADD(5, clock64() - c0); PROF_ADD(7, 1); }
     }
     __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)
         for (int win = 0; win < nwin; ++win) {
@@ -171,6 +181,45 @@ struct View {
     // the reverse border keeps RM = 0 (:924-932 sets FM bits there)
     __device__ uint32_t RM(int r, int c) const { return interior(r, c) ? (nibr(r, c) >> 2) : (uint32_t)T_STOP; }
     __device__ uint32_t RM_nc(int r, int c) const { return interior(r, c) ? (nibr_nc(r, c) >> 2) : (uint32_t)T_STOP; }
+    // ---- lane-parallel chains ------------------------------------------------------------------------------------
+    // Every lane names one cell of plane pair `rev` (0: forward trace, 1: reverse trace); windows that are not
+    // resident are re-swept one after the other until every lane's cell can be read.
+    __device__ void ensure_lanes(int rev, int r, int c) const {
+        const bool in = interior(r, c);
+        const int q = r - 1;
+        const int s = in ? (q >> 8) : 0;
+        const int win = in ? ((rev ? rstep(q, c) : fstep(q, c)) - 1) / CKS : 0;
+        bool ok = !in || valid(rev, s, win);
+        unsigned m;
+        while ((m = __ballot_sync(0xFFFFFFFFu, !ok)) != 0) {
+            const int src = __ffs(m) - 1;
+            const int ss = __shfl_sync(0xFFFFFFFFu, s, src), ww = __shfl_sync(0xFFFFFFFFu, win, src);
+            if (rev) ensure_r(ss, ww); else ensure_f(ss, ww);
+            ok = ok || (s == ss && win == ww);
+        }
+    }
+    // code of a chain plane at any cell: 0 = FS, 1 = FM, 2 = RS, 3 = RM (cells outside the matrix stop the chain)
+    __device__ uint32_t code_nc(int plane, int r, int c) const {
+        if (r < 0 || c < 0 || r > len2 + 1 || c > len1 + 1) return T_STOP;
+        if (!interior(r, c)) return plane == 1 ? FM_border(r, c) : (uint32_t)T_STOP;
+        const uint32_t nb4 = plane < 2 ? nibf_nc(r, c) : nibr_nc(r, c);
+        return (plane & 1) ? (nb4 >> 2) : (nb4 & 3u);
+    }
+    // Starting at (r, c) and stepping by (dr, dc): how many consecutive cells (at most 32) carry code t, and the
+    // code of the first cell that does not (T_STOP-coded as 0..3; meaningful when the result is < 32).
+    __device__ int run_len(int plane, int r, int c, int dr, int dc, uint32_t t, uint32_t &tnext) const {
+        const int rr = r + lane * dr, cc = c + lane * dc;
+        ensure_lanes(plane >> 1, rr, cc);
+        const uint32_t code = code_nc(plane, rr, cc);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, code != t);
+        const int n = m ? __ffs(m) - 1 : 32;
+        tnext = __shfl_sync(0xFFFFFFFFu, code, n & 31);
+        return n;
+    }
+    __device__ uint32_t code_at(int plane, int r, int c) const {      // warp-uniform single read
+        if (interior(r, c)) { const int q = r - 1; if (plane >> 1) ensure_r(q >> 8, (rstep(q, c) - 1) / CKS); else ensure_f(q >> 8, (fstep(q, c) - 1) / CKS); }
+        return code_nc(plane, r, c);
+    }
     // K6 cell (r, c), 0 <= r <= len2, 0 <= c <= len1: does Fmax[r][c] + Rmax[r+1][c+1] equal the maximum?
     __device__ bool tie_nc(int r, int c) const {
         if (r < len2 && c < len1) return hot_nc(r + 1, c + 1);
@@ -183,17 +232,21 @@ struct BpList {
     int (*bp)[4];
 };
 
-// K8 traceBackMaxima (:615-642)
-__device__ void walk_left(const View &V, int &lg1, int &lg2)
+// K8 traceBackMaxima (:615-642).  The chains are followed run by run: the 32 lanes read the next 32 cells along the
+// current direction and the warp jumps to the first cell whose code differs.
+__device__ void walk_chain(const View &V, int plane, int sign, int &c, int &r)
 {
-    uint32_t t;
-    while ((t = V.FM(lg2, lg1)) != T_STOP) { if (t == T_VERT) --lg2; else --lg1; }
+    uint32_t t = V.code_at(plane, r, c);
+    while (t != T_STOP) {
+        const int dr = t == T_VERT ? sign : 0, dc = t == T_VERT ? 0 : sign;
+        uint32_t tn;
+        const int n = V.run_len(plane, r, c, dr, dc, t, tn);
+        r += n * dr; c += n * dc;
+        t = n < 32 ? tn : V.code_at(plane, r, c);
+    }
 }
-__device__ void walk_right(const View &V, int &rg1, int &rg2)
-{
-    uint32_t t;
-    while ((t = V.RM(rg2, rg1)) != T_STOP) { if (t == T_VERT) ++rg2; else ++rg1; }
-}
+__device__ void walk_left(const View &V, int &lg1, int &lg2) { walk_chain(V, 1, -1, lg1, lg2); }
+__device__ void walk_right(const View &V, int &rg1, int &rg2) { walk_chain(V, 3, +1, rg1, rg2); }
 
 // K9 addBpoints (:644-668); executed redundantly by every lane on the shared list, lane 0 writes
 __device__ int add_bp(const View &V, BpList &L, int lg1, int lg2, int rg1, int rg2, int lane)
@@ -335,8 +388,8 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.R2(r + 1, mid) <= tv) hi = mid; else lo = mid + 1; }
                 int x = lo;
                 while (x <= len1 + 1 && V.R2(r + 1, x) == tv && !stop) {
-                    int xe = x;
-                    while (V.RM(r + 1, xe) == T_HORI) ++xe;                // chain shares the endpoint
+                    int xe = x;                                            // H-chain: its members share the endpoint
+                    for (;;) { uint32_t tn; const int len = V.run_len(3, r + 1, xe, 0, 1, T_HORI, tn); xe += len; if (len < 32) break; }
                     int rg1 = xe, rg2 = r + 1, lg1 = j1, lg2 = r;
                     walk_right(V, rg1, rg2);
                     const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
@@ -366,7 +419,7 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
                 int x = lo;
                 while (x >= 0 && V.F2(i2 - 1, x) == tv && !stop) {
                     int xe = x;
-                    while (V.FM(i2 - 1, xe) == T_HORI) --xe;
+                    for (;;) { uint32_t tn; const int len = V.run_len(1, i2 - 1, xe, 0, -1, T_HORI, tn); xe -= len; if (len < 32) break; }
                     int lg1 = xe, lg2 = i2 - 1, rg1 = j2, rg2 = i2;
                     walk_left(V, lg1, lg2);
                     const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
@@ -379,23 +432,22 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
     }
 }
 
-// K11 findLeftBlocks (:752-808).  dst == nullptr: count only.  Blocks are produced last-first.
+// K11 findLeftBlocks (:752-808).  dst == nullptr: count only.  Blocks are produced last-first; a block is a maximal
+// run of DIAGONAL codes (any H / V step in between starts a new block, :774-790).
 __device__ int left_blocks(const View &V, int c, int r, Block *dst, int n_total, int lane)
 {
-    int n = 0, run = 0, last_c = 0, last_r = 0;
-    uint32_t t;
-    while ((t = V.FS(r, c)) != T_STOP) {
-        if (t == T_DIAG) {
-            if (run > 0 && last_c - c == 1 && last_r - r == 1) ++run;
-            else {
-                if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{last_c, last_r, run}; ++n; }
-                run = 1;
-            }
-            last_c = c; last_r = r; --c; --r;
-        } else if (t == T_HORI) --c;
-        else --r;
+    int n = 0, run = 0;
+    uint32_t t = V.code_at(0, r, c);
+    while (t != T_STOP) {
+        const int dr = t == T_HORI ? 0 : -1, dc = t == T_VERT ? 0 : -1;
+        uint32_t tn;
+        const int len = V.run_len(0, r, c, dr, dc, t, tn);
+        r += len * dr; c += len * dc;
+        if (t == T_DIAG) run += len;
+        else if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{c - len * dc + 1, r - len * dr + 1, run}; ++n; run = 0; }
+        t = len < 32 ? tn : V.code_at(0, r, c);
     }
-    if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{last_c, last_r, run}; ++n; }
+    if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{c + 1, r + 1, run}; ++n; }
     return n;
 }
 
@@ -403,21 +455,24 @@ __device__ int left_blocks(const View &V, int c, int r, Block *dst, int n_total,
 __device__ int right_blocks(const View &V, int c, int r, Block *dst, int lane)
 {
     int n = 0, run = 0, s1 = 0, s2 = 0;
-    uint32_t t;
-    while ((t = V.RS(r, c)) != T_STOP) {
-        if (t == T_DIAG) {
-            if (c <= V.len1 && r <= V.len2) { if (run == 0) { s1 = c; s2 = r; run = 1; } else ++run; }
-            ++c; ++r;
-        } else {
-            if (t == T_HORI) ++c; else ++r;
-            if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
-        }
+    uint32_t t = V.code_at(2, r, c);
+    while (t != T_STOP) {
+        const int dr = t == T_HORI ? 0 : 1, dc = t == T_VERT ? 0 : 1;
+        uint32_t tn;
+        const int len = V.run_len(2, r, c, dr, dc, t, tn);
+        if (t == T_DIAG) { if (run == 0) { s1 = c; s2 = r; } run += len; }     // interior cells only (:820 always holds)
+        else if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
+        r += len * dr; c += len * dc;
+        t = len < 32 ? tn : V.code_at(2, r, c);
     }
     if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; }
     return n;
 }
 
 constexpr int P2_WARPS = 4;
+#ifndef P2_OCC
+#define P2_OCC 4
+#endif
 
 __host__ __device__ inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 __host__ __device__ inline size_t p2_vwords(size_t max_slots) { return max_slots / 32 + 2; }   // one bit per window, windows <= slots
@@ -441,7 +496,7 @@ size_t pass2_scratch_bytes(size_t max_slots, size_t max_rows, int need_mp)
            up256(3 * p2_vwords(max_slots) * 4) + up256(2 * (max_rows + 2) * 4);
 }
 
-__global__ void __launch_bounds__(P2_WARPS * 32)
+__global__ void __launch_bounds__(P2_WARPS * 32, P2_OCC)
 age_pass2_kernel(Pass2Params prm)
 {
     __shared__ int bp_s[P2_WARPS][MAX_BP][4];
@@ -459,6 +514,7 @@ age_pass2_kernel(Pass2Params prm)
         const int len1 = T.len1, len2 = T.len2;
 
         // ---- split maxima of both halves (:545-550 / :476-481) ------------------------------------------
+        long long pc = clock64();
         uint32_t mx_indel = 0, mx_col = 0;                       // packed u16x2: max of 2*(Fmax + Rmax)
         const int ntiles = T.nstrips * T.nwin * 32;
         for (int i = lane; i < ntiles; i += 32) mx_indel = __vmaxu2(mx_indel, T.tilemax[i]);
@@ -488,6 +544,7 @@ age_pass2_kernel(Pass2Params prm)
             need[1 - win] = false;
         }
 
+        const long long pair_c0 = pc;
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
             const View V{&T, sc, &rings[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], vwords};
@@ -497,8 +554,12 @@ age_pass2_kernel(Pass2Params prm)
             __syncwarp();
             if (T.flag[h] == F_INDEL) {
                 int *rlo = sc.rowrange, *rhi = sc.rowrange + (len2 + 2);
+                pc = clock64();
                 indel_row_ranges(V, rlo, rhi, lane);
+                if (lane == 0) PROF_ADD(1, clock64() - pc);
+                pc = clock64();
                 indel_enumerate(V, L, rlo, rhi, lane);
+                if (lane == 0) PROF_ADD(2, clock64() - pc);
             } else invtdup_enumerate(V, L, lane);
             __syncwarp();
             // ---- K10: blocks of bpoint 0 and of the alternative shown by printAlignment (:287-306) ----
@@ -511,6 +572,7 @@ age_pass2_kernel(Pass2Params prm)
                     for (int k = 0; k < 4; ++k) O.bp[i][k] = L.bp[i][k];
             }
             int alt = -1;
+            pc = clock64();
             for (int which = 0; which < 2; ++which) {
                 int idx = 0, nl = 0, nr = 0;
                 if (which == 0) {
@@ -539,9 +601,10 @@ age_pass2_kernel(Pass2Params prm)
                     O.blk_off[2 * which] = off; O.blk_off[2 * which + 1] = off + nl;
                 }
             }
-            if (lane == 0) O.alt_index = alt;
+            if (lane == 0) { O.alt_index = alt; PROF_ADD(3, clock64() - pc); }
             __syncwarp();
         }
+        if (lane == 0) atomicMax(&g_prof[0], (unsigned long long)(clock64() - pair_c0));
     }
 }
 
@@ -551,7 +614,7 @@ int pass2_warps(int n_pairs)
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     int blocks = (n_pairs + P2_WARPS - 1) / P2_WARPS;
-    if (blocks > sms * 2) blocks = sms * 2;
+    if (blocks > sms * P2_OCC) blocks = sms * P2_OCC;
     return blocks * P2_WARPS;
 }
 
@@ -559,7 +622,16 @@ void launch_pass2(const Pass2Params &p, int n_warps, cudaStream_t st)
 {
     if (p.n_pairs <= 0) return;
     cudaMemsetAsync(p.next, 0, sizeof(int32_t), st);
+    static const bool prof = getenv("AGE_P2_PROF") != nullptr;
+    if (prof) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
     age_pass2_kernel<<<n_warps / P2_WARPS, P2_WARPS * 32, 0, st>>>(p);
+    if (prof) {
+        unsigned long long z[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(z, g_prof, sizeof(z));
+        fprintf(stderr, "[p2 prof] pairs %d warps %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
+                p.n_pairs, n_warps, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[6], z[5] / 1e6, z[7]);
+    }
 }
 
 } // namespace age

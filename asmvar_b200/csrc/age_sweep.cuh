@@ -53,6 +53,15 @@ __device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
     return t;
 }
 
+// Trace nibble (FS | FM << 2) of one cell of one half.  Deliberately not inlined: the re-sweep of pass 2 is
+// latency-bound and its 32-cell step body must stay small enough for the instruction cache.
+//   d2, gl, vg : the three candidates 2d, 2h+1, 2v+1 (diagonal, from the previous column, from the previous row)
+//   hc, ml, vm : the cell's own score and the running maxima of the previous column / previous row
+__device__ __noinline__ uint32_t trace_nibble(uint32_t d2, uint32_t gl, uint32_t vg, uint32_t hc, uint32_t ml, uint32_t vm, int sh)
+{
+    return fs_code(half16(d2, sh), half16(gl, sh), half16(vg, sh)) | (fm_code(half16(hc, sh), half16(ml, sh), half16(vm, sh)) << 2);
+}
+
 struct LaneState {
     uint32_t Hl[RPT], Gl[RPT], Ml[RPT];    // row state at the last finished column
     uint32_t oH[W], oG[W], oM[W];          // bottom-row outputs of the last finished block (shuffled to lane p+1)
@@ -266,10 +275,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                     const uint32_t Hc = s2 & 0xFFFEFFFEu;
                     const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
                     if (TRACE) {
-                        const uint32_t d2 = __vadd2(dg, S2[k]);
-                        const uint32_t nb4 = fs_code(half16(d2, TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) |
-                                             (fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << 2);
-                        nibw |= nb4 << (4 * k);
+                        nibw |= trace_nibble(__vadd2(dg, S2[k]), S.Gl[k], vG, Hc, S.Ml[k], vM, TO.sh) << (4 * k);
                     }
                     if (!FWD) {
                         const uint4 dv = dq[W - 1 - w][k >> 2];
@@ -327,7 +333,7 @@ __device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneSta
                                                  uint32_t &best, const TraceOut &TO)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
-    if (t0 >= 32 && t1 <= C.nb) sweep_window<DIR, MODE, false>(C, S, R, win, t0, t1, best, TO);
+    if (MODE == MODE_FAST && t0 >= 32 && t1 <= C.nb) sweep_window<DIR, MODE, false>(C, S, R, win, t0, t1, best, TO);
     else                        sweep_window<DIR, MODE, true>(C, S, R, win, t0, t1, best, TO);
 }
 
