@@ -76,10 +76,10 @@ struct Block { int32_t start1, start2, length; };
 // Per-warp scratch of pass 2: trace planes of the aligner being enumerated, filled window by window on demand
 // by re-running the sweep from its checkpoints.
 struct P2Scratch {
-    uint4 *Tf, *Tr;                      // [slots][32]: trace nibbles (FS | FM << 2) of 8 rows, one word per block column
-    uint32_t *hot;                       // [slots][32]: bit 8w+k = reverse cell holds Fmax + Rmax == max
+    uint2 *P[4];                         // 2-bit code planes FS, FM, RS, RM: [slots][32], 16 bits per block column
+    uint32_t *hot;                       // [slots][32]: bit 8w+k = reverse cell holds Fmax + Rmax == max (with RM)
     uint32_t *Mp;                        // reverse maxima, same layout as D but unshifted (K7 only)
-    uint32_t *valid;                     // [3][valid_words] window-valid bits: Tf, Tr(+hot), Mp
+    uint32_t *valid;                     // [5][valid_words] window-valid bits: the four planes, Mp
     int32_t *rowrange;                   // [2][len2 + 2]
 };
 

@@ -66,14 +66,17 @@ struct View {
     const PairTask *T;
     P2Scratch sc;
     WarpRings *R;
+    TraceSmem *X;
     int len1, len2, nb, nsteps, nwin, nstrips, half, lane, max2, vwords;
 
     // ---- geometry --------------------------------------------------------------------------------
     __device__ int fstep(int q, int c) const { return (c - 1) / W + 1 + ((q & 255) >> 3); }          // forward step of cell (q+1, c)
     __device__ int rstep(int q, int c) const { return nb - (c - 1) / W + 31 - ((q & 255) >> 3); }    // reverse step
     __device__ size_t slot(int q, int t) const { return ((size_t)(q >> 8) * nsteps + (t - 1)) * 32 + ((q & 255) >> 3); }
+    __device__ bool interior(int r, int c) const { return r >= 1 && c >= 1 && r <= len2 && c <= len1; }
 
     // ---- on-demand trace windows ---------------------------------------------------------------------
+    // planes: 0 = FS, 1 = FM, 2 = RS, 3 = RM (+ hot bits), 4 = reverse maxima (K7)
     __device__ bool valid(int plane, int s, int win) const {
         const int i = s * nwin + win;
         return (sc.valid[plane * vwords + (i >> 5)] >> (i & 31)) & 1u;
@@ -84,49 +87,42 @@ struct View {
         if (lane == 0) sc.valid[plane * vwords + (i >> 5)] |= 1u << (i & 31);
         __syncwarp();
     }
-    __device__ void ensure_f(int s, int win) const {
-        if (valid(0, s, win)) return;
-        const TraceOut TO{sc.Tf, nullptr, nullptr, 16 * half, 0};
+    __device__ void ensure(int plane, int s, int win, bool with_mp = false) const {
+        if (valid(with_mp ? 4 : plane, s, win)) return;
         const long long c0 = clock64();
-        sweep_window_trace<+1>(*T, *R, lane, s, win, TO);
-        set_valid(0, s, win);
-        if (lane == 0) { PROF_ADD(4, clock64() - c0); PROF_ADD(6, 1); }
-    }
-    __device__ void ensure_r(int s, int win) const {
-        if (valid(1, s, win)) return;
-        const TraceOut TO{sc.Tr, sc.hot, nullptr, 16 * half, max2};
-        const long long c0 = clock64();
-        sweep_window_trace<-1>(*T, *R, lane, s, win, TO);
-        set_valid(1, s, win);
-        if (lane == 0) { PROF_ADD(5, clock64() - c0); PROF_ADD(7, 1); }
+        const TraceOut TO{sc.P[plane], sc.hot, with_mp ? sc.Mp : nullptr, 16 * half, max2};
+        switch (plane) {
+        case 0:  sweep_window_trace<+1, MODE_TRACE_S>(*T, *R, *X, lane, s, win, TO); break;
+        case 1:  sweep_window_trace<+1, MODE_TRACE_M>(*T, *R, *X, lane, s, win, TO); break;
+        case 2:  sweep_window_trace<-1, MODE_TRACE_S>(*T, *R, *X, lane, s, win, TO); break;
+        default: sweep_window_trace<-1, MODE_TRACE_M>(*T, *R, *X, lane, s, win, TO); break;
+        }
+        set_valid(plane, s, win);
+        if (with_mp) set_valid(4, s, win);
+        if (lane == 0) { PROF_ADD(4 + (plane >> 1), clock64() - c0); PROF_ADD(6 + (plane >> 1), 1); }
     }
     __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)
-        for (int win = 0; win < nwin; ++win) {
-            if (valid(2, s, win)) continue;
-            const TraceOut TO{sc.Tr, sc.hot, sc.Mp, 16 * half, max2};
-            sweep_window_trace<-1>(*T, *R, lane, s, win, TO);
-            set_valid(1, s, win); set_valid(2, s, win);
-        }
+        for (int win = 0; win < nwin; ++win) ensure(3, s, win, true);
     }
     __device__ void reset_valid() const {
         __syncwarp();
-        for (int i = lane; i < 3 * vwords; i += 32) sc.valid[i] = 0;
+        for (int i = lane; i < 5 * vwords; i += 32) sc.valid[i] = 0;
         __syncwarp();
     }
-    // make the trace of row r, columns c0..c1 (clamped to the interior) resident; warp-uniform
-    __device__ void ensure_f_row(int r, int c0, int c1) const {
-        if (r < 1 || r > len2) return;
-        c0 = max(c0, 1); c1 = min(c1, len1);
-        if (c0 > c1) return;
-        const int q = r - 1, w0 = (fstep(q, c0) - 1) / CKS, w1 = (fstep(q, c1) - 1) / CKS;
-        for (int w = w0; w <= w1; ++w) ensure_f(q >> 8, w);
-    }
-    __device__ void ensure_r_row(int r, int c0, int c1) const {
-        if (r < 1 || r > len2) return;
-        c0 = max(c0, 1); c1 = min(c1, len1);
-        if (c0 > c1) return;
-        const int q = r - 1, w0 = (rstep(q, c1) - 1) / CKS, w1 = (rstep(q, c0) - 1) / CKS;
-        for (int w = w0; w <= w1; ++w) ensure_r(q >> 8, w);
+    __device__ int win_of(int plane, int r, int c) const { return (((plane >> 1) ? rstep(r - 1, c) : fstep(r - 1, c)) - 1) / CKS; }
+    // Every lane names one cell of `plane`; windows that are not resident are re-swept one after the other until
+    // every lane's cell can be read (warp-collective).
+    __device__ void ensure_lanes(int plane, int r, int c) const {
+        const bool in = interior(r, c);
+        const int s = in ? ((r - 1) >> 8) : 0, win = in ? win_of(plane, r, c) : 0;
+        bool ok = !in || valid(plane, s, win);
+        unsigned m;
+        while ((m = __ballot_sync(0xFFFFFFFFu, !ok)) != 0) {
+            const int src = __ffs(m) - 1;
+            const int ss = __shfl_sync(0xFFFFFFFFu, s, src), ww = __shfl_sync(0xFFFFFFFFu, win, src);
+            ensure(plane, ss, ww);
+            ok = ok || (s == ss && win == ww);
+        }
     }
 
     // ---- maxima ------------------------------------------------------------------------------------------
@@ -145,71 +141,32 @@ struct View {
         return (sc.Mp[(((((size_t)(q >> 8) * nsteps + (t - 1)) * W + w) * 2 + (k >> 2)) * 32 + l) * 4 + (k & 3)] >> (16 * half)) & 0xFFFF;
     }
 
-    // ---- trace (no residency check: callers ensure first) -----------------------------------------------------
-    __device__ bool interior(int r, int c) const { return r >= 1 && c >= 1 && r <= len2 && c <= len1; }
-    __device__ uint32_t nibf_nc(int r, int c) const {
-        const int q = r - 1;
-        const uint4 v = sc.Tf[slot(q, fstep(q, c))];
-        const int w = (c - 1) % W;
-        const uint32_t x = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
-        return (x >> (4 * (q & 7))) & 15u;
+    // ---- trace codes (no residency check: callers ensure first) ---------------------------------------------------
+    __device__ uint32_t FM_border(int r, int c) const {  // :874-882
+        if (r == 0) return c >= 1 ? T_HORI : T_STOP;
+        if (c == 0) return r <= len2 ? T_VERT : T_STOP;
+        return T_STOP;
     }
-    __device__ uint32_t nibr_nc(int r, int c) const {
-        const int q = r - 1;
-        const uint4 v = sc.Tr[slot(q, rstep(q, c))];
-        const int w = W * ((c - 1) / W + 1) - c;
-        const uint32_t x = w == 0 ? v.x : w == 1 ? v.y : w == 2 ? v.z : v.w;
-        return (x >> (4 * (q & 7))) & 15u;
+    // code of plane 0 = FS, 1 = FM, 2 = RS, 3 = RM at any cell (cells outside the matrix stop a chain; the reverse
+    // border keeps RM = 0, :924-932)
+    __device__ uint32_t code_nc(int plane, int r, int c) const {
+        if (r < 0 || c < 0 || r > len2 + 1 || c > len1 + 1) return T_STOP;
+        if (!interior(r, c)) return plane == 1 ? FM_border(r, c) : (uint32_t)T_STOP;
+        const int q = r - 1, rev = plane >> 1;
+        const uint2 v = sc.P[plane][slot(q, rev ? rstep(q, c) : fstep(q, c))];
+        const int w = rev ? W * ((c - 1) / W + 1) - c : (c - 1) % W;
+        return (((w < 2 ? v.x : v.y) >> (16 * (w & 1))) >> (2 * (q & 7))) & 3u;
     }
     __device__ bool hot_nc(int r, int c) const {          // reverse cell (r, c): Fmax[r-1][c-1] + Rmax[r][c] == max
         const int q = r - 1;
         const int w = W * ((c - 1) / W + 1) - c;
         return (sc.hot[slot(q, rstep(q, c))] >> (8 * w + (q & 7))) & 1u;
     }
-    // ---- trace with residency check (warp-uniform arguments only) -------------------------------------------
-    __device__ uint32_t nibf(int r, int c) const { const int q = r - 1; ensure_f(q >> 8, (fstep(q, c) - 1) / CKS); return nibf_nc(r, c); }
-    __device__ uint32_t nibr(int r, int c) const { const int q = r - 1; ensure_r(q >> 8, (rstep(q, c) - 1) / CKS); return nibr_nc(r, c); }
-    __device__ uint32_t FS(int r, int c) const { return interior(r, c) ? (nibf(r, c) & 3u) : (uint32_t)T_STOP; }
-    __device__ uint32_t RS(int r, int c) const { return interior(r, c) ? (nibr(r, c) & 3u) : (uint32_t)T_STOP; }
-    __device__ uint32_t FM_border(int r, int c) const {  // :874-882
-        if (r == 0) return c >= 1 ? T_HORI : T_STOP;
-        if (c == 0) return r <= len2 ? T_VERT : T_STOP;
-        return T_STOP;
-    }
-    __device__ uint32_t FM(int r, int c) const { return interior(r, c) ? (nibf(r, c) >> 2) : FM_border(r, c); }
-    __device__ uint32_t FM_nc(int r, int c) const { return interior(r, c) ? (nibf_nc(r, c) >> 2) : FM_border(r, c); }
-    // the reverse border keeps RM = 0 (:924-932 sets FM bits there)
-    __device__ uint32_t RM(int r, int c) const { return interior(r, c) ? (nibr(r, c) >> 2) : (uint32_t)T_STOP; }
-    __device__ uint32_t RM_nc(int r, int c) const { return interior(r, c) ? (nibr_nc(r, c) >> 2) : (uint32_t)T_STOP; }
-    // ---- lane-parallel chains ------------------------------------------------------------------------------------
-    // Every lane names one cell of plane pair `rev` (0: forward trace, 1: reverse trace); windows that are not
-    // resident are re-swept one after the other until every lane's cell can be read.
-    __device__ void ensure_lanes(int rev, int r, int c) const {
-        const bool in = interior(r, c);
-        const int q = r - 1;
-        const int s = in ? (q >> 8) : 0;
-        const int win = in ? ((rev ? rstep(q, c) : fstep(q, c)) - 1) / CKS : 0;
-        bool ok = !in || valid(rev, s, win);
-        unsigned m;
-        while ((m = __ballot_sync(0xFFFFFFFFu, !ok)) != 0) {
-            const int src = __ffs(m) - 1;
-            const int ss = __shfl_sync(0xFFFFFFFFu, s, src), ww = __shfl_sync(0xFFFFFFFFu, win, src);
-            if (rev) ensure_r(ss, ww); else ensure_f(ss, ww);
-            ok = ok || (s == ss && win == ww);
-        }
-    }
-    // code of a chain plane at any cell: 0 = FS, 1 = FM, 2 = RS, 3 = RM (cells outside the matrix stop the chain)
-    __device__ uint32_t code_nc(int plane, int r, int c) const {
-        if (r < 0 || c < 0 || r > len2 + 1 || c > len1 + 1) return T_STOP;
-        if (!interior(r, c)) return plane == 1 ? FM_border(r, c) : (uint32_t)T_STOP;
-        const uint32_t nb4 = plane < 2 ? nibf_nc(r, c) : nibr_nc(r, c);
-        return (plane & 1) ? (nb4 >> 2) : (nb4 & 3u);
-    }
     // Starting at (r, c) and stepping by (dr, dc): how many consecutive cells (at most 32) carry code t, and the
-    // code of the first cell that does not (T_STOP-coded as 0..3; meaningful when the result is < 32).
+    // code of the first cell that does not (meaningful when the result is < 32).
     __device__ int run_len(int plane, int r, int c, int dr, int dc, uint32_t t, uint32_t &tnext) const {
         const int rr = r + lane * dr, cc = c + lane * dc;
-        ensure_lanes(plane >> 1, rr, cc);
+        ensure_lanes(plane, rr, cc);
         const uint32_t code = code_nc(plane, rr, cc);
         const unsigned m = __ballot_sync(0xFFFFFFFFu, code != t);
         const int n = m ? __ffs(m) - 1 : 32;
@@ -217,10 +174,11 @@ struct View {
         return n;
     }
     __device__ uint32_t code_at(int plane, int r, int c) const {      // warp-uniform single read
-        if (interior(r, c)) { const int q = r - 1; if (plane >> 1) ensure_r(q >> 8, (rstep(q, c) - 1) / CKS); else ensure_f(q >> 8, (fstep(q, c) - 1) / CKS); }
+        if (interior(r, c)) ensure(plane, (r - 1) >> 8, win_of(plane, r, c));
         return code_nc(plane, r, c);
     }
     // K6 cell (r, c), 0 <= r <= len2, 0 <= c <= len1: does Fmax[r][c] + Rmax[r+1][c+1] equal the maximum?
+    // (interior cells need the RM window of (r+1, c+1) resident)
     __device__ bool tie_nc(int r, int c) const {
         if (r < len2 && c < len1) return hot_nc(r + 1, c + 1);
         return F2(r, c) == max2;                          // Rmax is zero on the border
@@ -275,11 +233,12 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
         const int lo = rlo[r], hi = rhi[r];
         if (hi < lo) continue;
         for (int cb = lo & ~31; cb <= hi && !stop; cb += 32) {
-            V.ensure_r_row(r + 1, cb + 1, cb + 32);
-            V.ensure_f_row(r, cb, cb + 31);
             const int c = cb + lane;
-            bool hit = false;
-            if (c >= lo && c <= hi && V.tie_nc(r, c)) hit = V.FM_nc(r, c) == T_STOP;
+            const bool in = c >= lo && c <= hi;
+            V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
+            const bool tie = in && V.tie_nc(r, c);
+            V.ensure_lanes(1, tie ? r : -1, c);
+            const bool hit = tie && V.code_nc(1, r, c) == T_STOP;
             unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             while (m && !stop) {
                 const int b = __ffs(m) - 1; m &= m - 1;
@@ -296,10 +255,10 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
         const int lo = rlo[r], hi = rhi[r];
         if (hi < lo) continue;
         for (int cb = hi & ~31; cb >= (lo & ~31) && !stop; cb -= 32) {
-            V.ensure_r_row(r + 1, cb + 1, cb + 32);
             const int c = cb + lane;
-            bool hit = false;
-            if (c >= lo && c <= hi && V.tie_nc(r, c)) hit = V.RM_nc(r + 1, c + 1) == T_STOP;
+            const bool in = c >= lo && c <= hi;
+            V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
+            const bool hit = in && V.tie_nc(r, c) && V.code_nc(3, r + 1, c + 1) == T_STOP;
             unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
             while (m && !stop) {
                 const int b = 31 - __clz(m); m &= ~(1u << b);
@@ -331,7 +290,7 @@ __device__ void indel_row_ranges(const View &V, int *rlo, int *rhi, int lane)
         const bool hot = (int)((T.tilemax[(size_t)wi * 32 + lane] >> (16 * V.half)) & 0xFFFF) == max2;
         if (!__any_sync(0xFFFFFFFFu, hot)) continue;
         const int s = wi / T.nwin, win = wi % T.nwin;
-        V.ensure_r(s, win);
+        V.ensure(3, s, win);
         const int t1 = min(CKS * win + CKS, T.nsteps);
         for (int t = CKS * win + 1; t <= t1; ++t) {
             const int bq = t - 31 + lane;                             // logical reverse block of this lane
@@ -376,9 +335,9 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
         if (A(r) + B(r + 1) != max2) continue;
         if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
         for (int jb = 0; jb <= len1 && !stop; jb += 32) {
-            V.ensure_f_row(r, jb, jb + 31);
             const int j = jb + lane;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, j <= len1 && V.FM_nc(r, j) == T_STOP);
+            V.ensure_lanes(1, j <= len1 ? r : -1, j);
+            unsigned m = __ballot_sync(0xFFFFFFFFu, j <= len1 && V.code_nc(1, r, j) == T_STOP);
             while (m && !stop) {
                 const int j1 = jb + __ffs(m) - 1; m &= m - 1;
                 const int tv = max2 - V.F2(r, j1);
@@ -405,9 +364,9 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
         if (A(i2 - 1) + B(i2) != max2) continue;
         if (i2 <= len2) V.ensure_rm((i2 - 1) >> 8);
         for (int jb = ((len1 + 1) / 32) * 32; jb >= 0 && !stop; jb -= 32) {
-            V.ensure_r_row(i2, jb, jb + 31);
             const int j = jb + lane;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, j >= 1 && j <= len1 + 1 && V.RM_nc(i2, j) == T_STOP);
+            V.ensure_lanes(3, (j >= 1 && j <= len1 + 1) ? i2 : -1, j);
+            unsigned m = __ballot_sync(0xFFFFFFFFu, j >= 1 && j <= len1 + 1 && V.code_nc(3, i2, j) == T_STOP);
             while (m && !stop) {
                 const int b = 31 - __clz(m); m &= ~(1u << b);
                 const int j2 = jb + b;
@@ -480,20 +439,19 @@ __host__ __device__ inline size_t p2_vwords(size_t max_slots) { return max_slots
 __device__ P2Scratch carve_scratch(char *base, size_t max_slots, size_t max_rows, int need_mp, int &vwords)
 {
     P2Scratch sc;
-    sc.Tf = (uint4 *)base; base += up256(max_slots * 32 * 16);
-    sc.Tr = (uint4 *)base; base += up256(max_slots * 32 * 16);
+    for (int i = 0; i < 4; ++i) { sc.P[i] = (uint2 *)base; base += up256(max_slots * 32 * 8); }
     sc.hot = (uint32_t *)base; base += up256(max_slots * 32 * 4);
     sc.Mp = need_mp ? (uint32_t *)base : nullptr; base += need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0;
     vwords = (int)p2_vwords(max_slots);
-    sc.valid = (uint32_t *)base; base += up256((size_t)3 * vwords * 4);
+    sc.valid = (uint32_t *)base; base += up256((size_t)5 * vwords * 4);
     sc.rowrange = (int32_t *)base;
     return sc;
 }
 
 size_t pass2_scratch_bytes(size_t max_slots, size_t max_rows, int need_mp)
 {
-    return 2 * up256(max_slots * 32 * 16) + up256(max_slots * 32 * 4) + (need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0) +
-           up256(3 * p2_vwords(max_slots) * 4) + up256(2 * (max_rows + 2) * 4);
+    return 4 * up256(max_slots * 32 * 8) + up256(max_slots * 32 * 4) + (need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0) +
+           up256(5 * p2_vwords(max_slots) * 4) + up256(2 * (max_rows + 2) * 4);
 }
 
 __global__ void __launch_bounds__(P2_WARPS * 32, P2_OCC)
@@ -501,6 +459,7 @@ age_pass2_kernel(Pass2Params prm)
 {
     __shared__ int bp_s[P2_WARPS][MAX_BP][4];
     __shared__ WarpRings rings[P2_WARPS];
+    __shared__ TraceSmem tsm[P2_WARPS];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int gw = blockIdx.x * P2_WARPS + w;
     int vwords = 0;
@@ -547,7 +506,7 @@ age_pass2_kernel(Pass2Params prm)
         const long long pair_c0 = pc;
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
-            const View V{&T, sc, &rings[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], vwords};
+            const View V{&T, sc, &rings[w], &tsm[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], vwords};
             V.reset_valid();
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
@@ -604,7 +563,7 @@ age_pass2_kernel(Pass2Params prm)
             if (lane == 0) { O.alt_index = alt; PROF_ADD(3, clock64() - pc); }
             __syncwarp();
         }
-        if (lane == 0) atomicMax(&g_prof[0], (unsigned long long)(clock64() - pair_c0));
+        if (lane == 0) atomicMax(&g_prof[0], ((unsigned long long)(clock64() - pair_c0) >> 10 << 24) | (unsigned long long)item);
     }
 }
 
@@ -629,6 +588,7 @@ void launch_pass2(const Pass2Params &p, int n_warps, cudaStream_t st)
         unsigned long long z[8];
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(z, g_prof, sizeof(z));
+        fprintf(stderr, "[p2 prof] slowest pair index %llu\n", z[0] & 0xFFFFFF); z[0] = (z[0] >> 24) << 10;
         fprintf(stderr, "[p2 prof] pairs %d warps %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
                 p.n_pairs, n_warps, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[6], z[5] / 1e6, z[7]);
     }

@@ -9,7 +9,7 @@
 
 namespace age {
 
-enum { MODE_FAST = 0, MODE_TRACE = 1 };
+enum { MODE_FAST = 0, MODE_TRACE_S = 1, MODE_TRACE_M = 2 };   // S: FS / RS (scores trace), M: FM / RM (maxima trace) + hot bits
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
@@ -53,15 +53,6 @@ __device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
     return t;
 }
 
-// Trace nibble (FS | FM << 2) of one cell of one half.  Deliberately not inlined: the re-sweep of pass 2 is
-// latency-bound and its 32-cell step body must stay small enough for the instruction cache.
-//   d2, gl, vg : the three candidates 2d, 2h+1, 2v+1 (diagonal, from the previous column, from the previous row)
-//   hc, ml, vm : the cell's own score and the running maxima of the previous column / previous row
-__device__ __noinline__ uint32_t trace_nibble(uint32_t d2, uint32_t gl, uint32_t vg, uint32_t hc, uint32_t ml, uint32_t vm, int sh)
-{
-    return fs_code(half16(d2, sh), half16(gl, sh), half16(vg, sh)) | (fm_code(half16(hc, sh), half16(ml, sh), half16(vm, sh)) << 2);
-}
-
 struct LaneState {
     uint32_t Hl[RPT], Gl[RPT], Ml[RPT];    // row state at the last finished column
     uint32_t oH[W], oG[W], oM[W];          // bottom-row outputs of the last finished block (shuffled to lane p+1)
@@ -73,10 +64,12 @@ struct WarpRings {                          // shared memory of one warp
     uint4 out[3][32];                       // boundary rows produced by lane p = 31
 };
 
-struct TraceOut {                           // MODE_TRACE outputs (one half of the pair)
-    uint4 *T; uint32_t *hot; uint32_t *Mp;
+struct TraceOut {                           // trace re-sweep outputs (one half of the pair, one kind of trace)
+    uint2 *P;                               // 2-bit codes: [slot][lane], 16 bits per block column, 2 bits per row
+    uint32_t *hot;                          // MODE_TRACE_M, reverse: bit 8w+k = the cell holds Fmax + Rmax == max
+    uint32_t *Mp;                           // MODE_TRACE_M, reverse, optional: the running maxima themselves (K7 rows)
     int sh;                                 // 0 / 16: the half whose trace is wanted
-    int max2;                               // hot bit = (2*Fmax + 2*Rmax == max2)
+    int max2;
 };
 
 template <int DIR> __device__ __forceinline__ uint32_t shfl_prev(uint32_t v)
@@ -197,7 +190,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                                              const int t0, const int t1, uint32_t &best, const TraceOut &TO)
 {
     constexpr bool FWD = DIR > 0;
-    constexpr bool TRACE = MODE == MODE_TRACE;
+    constexpr bool TRACE = false, TRACE_S = false, TRACE_M = false;   // the trace re-sweep is sweep_window_compact
     const int lane = C.lane, p = C.p, nb = C.nb;
     const int buf = win & 1;
     auto xload = [&](int b) { return __ldg(C.xblk + min(max(b, 0), nb + 1)); };
@@ -222,7 +215,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
             const size_t slot = C.sbase + (size_t)(t - 1);
             // reverse sweep: the shifted forward maxima of this block, written by the forward lane in step nb+32-t
             uint4 dq[W][2];
-            if (!FWD) {
+            if (!FWD && !TRACE_S) {
                 const uint4 *src = C.D4 + ((C.sbase + (size_t)(nb + 31 - t)) * W) * 64 + lane;
 #pragma unroll
                 for (int w = 0; w < W; ++w) { dq[w][0] = __ldcg(src + (w * 2 + 0) * 32); dq[w][1] = __ldcg(src + (w * 2 + 1) * 32); }
@@ -274,10 +267,9 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                     const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);         // 2*(s + (gap ? ge : go)) + 1
                     const uint32_t Hc = s2 & 0xFFFEFFFEu;
                     const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
-                    if (TRACE) {
-                        nibw |= trace_nibble(__vadd2(dg, S2[k]), S.Gl[k], vG, Hc, S.Ml[k], vM, TO.sh) << (4 * k);
-                    }
-                    if (!FWD) {
+                    if (TRACE_S) nibw |= fs_code(half16(__vadd2(dg, S2[k]), TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) << (2 * k);
+                    if (TRACE_M) nibw |= fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << (2 * k);
+                    if (!FWD && !TRACE_S) {
                         const uint4 dv = dq[W - 1 - w][k >> 2];
                         const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
                         const uint32_t sum = __vadd2(Mn, dk);
@@ -291,7 +283,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                 constexpr int last = FWD ? RPT - 1 : 0;
                 S.oH[w] = S.Hl[last]; S.oG[w] = S.Gl[last]; S.oM[w] = S.Ml[last];
                 tw[w] = nibw;
-                if (TRACE && TO.Mp) {
+                if (TRACE_M && !FWD && TO.Mp) {
                     uint4 *dst = reinterpret_cast<uint4 *>(TO.Mp) + (slot * W + w) * 64 + lane;
                     dst[0]  = make_uint4(S.Ml[0], S.Ml[1], S.Ml[2], S.Ml[3]);
                     dst[32] = make_uint4(S.Ml[4], S.Ml[5], S.Ml[6], S.Ml[7]);
@@ -299,8 +291,8 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
             }
             S.pH = uH[W - 1]; S.pM = uM[W - 1];
             if (TRACE) {
-                TO.T[slot * 32 + lane] = make_uint4(tw[0], tw[1], tw[2], tw[3]);
-                if (!FWD && TO.hot) TO.hot[slot * 32 + lane] = hotw;
+                TO.P[slot * 32 + lane] = make_uint2(tw[0] | (tw[1] << 16), tw[2] | (tw[3] << 16));
+                if (!FWD && TRACE_M) TO.hot[slot * 32 + lane] = hotw;
             }
             if (!TRACE) {
                 if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
@@ -369,9 +361,115 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, const int lane)
     }
 }
 
+// Shared-memory staging of the compact trace re-sweep (one per warp): the per-column values that the fast sweep
+// keeps in statically indexed registers.
+struct TraceSmem {
+    uint32_t uH[W][32], uG[W][32], uM[W][32];   // values of the row above, per block column
+    uint32_t oH[W][32], oG[W][32], oM[W][32];   // bottom-row outputs of the lane's last finished block
+    uint32_t tw[W][32];                         // 2-bit codes of the 8 rows, per block column
+};
+
+// The trace re-sweep of pass 2: the same recurrence as sweep_window, written compactly -- the loop over the four
+// columns of a block is NOT unrolled (its per-column values live in shared memory), so the whole step body is a few
+// hundred instructions.  Pass 2 is latency- and instruction-fetch-bound: a fully unrolled 32-cell body with the
+// trace code inlined overflows the instruction cache and runs several times slower.
+template <int DIR, int MODE>
+__device__ __noinline__ void sweep_window_compact(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, TraceSmem &X,
+                                                  const int win, const TraceOut &TO)
+{
+    constexpr bool FWD = DIR > 0;
+    constexpr bool TRACE_S = MODE == MODE_TRACE_S, TRACE_M = MODE == MODE_TRACE_M;
+    const int lane = C.lane, p = C.p, nb = C.nb, buf = win & 1;
+    const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
+    const int prev_lane = FWD ? (lane + 31) & 31 : (lane + 1) & 31;
+#pragma unroll
+    for (int w = 0; w < W; ++w) { X.oH[w][lane] = S.oH[w]; X.oG[w][lane] = S.oG[w]; X.oM[w][lane] = S.oM[w]; }
+
+    for (int t = t0; t <= t1; ++t) {
+        const int b = t - p;
+        const uint4 xb = __ldg(C.xblk + min(max(b, 0), nb + 1));
+        __syncwarp();
+        uint32_t uH[W], uG[W], uM[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { uH[w] = X.oH[w][prev_lane]; uG[w] = X.oG[w][prev_lane]; uM[w] = X.oM[w][prev_lane]; }
+        if (p == 0) {
+            const int e = (t - 1) & 31;
+            const uint4 h = R.in[buf][0][e], g = R.in[buf][1][e], m = R.in[buf][2][e];
+            uH[0] = h.x; uH[1] = h.y; uH[2] = h.z; uH[3] = h.w;
+            uG[0] = g.x; uG[1] = g.y; uG[2] = g.z; uG[3] = g.w;
+            uM[0] = m.x; uM[1] = m.y; uM[2] = m.z; uM[3] = m.w;
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) { X.uH[w][lane] = uH[w]; X.uG[w][lane] = uG[w]; X.uM[w][lane] = uM[w]; }
+        __syncwarp();
+        if (b < 1 || b > nb) continue;
+        const size_t slot = C.sbase + (size_t)(t - 1);
+        uint32_t hotw = 0;
+        uint32_t dg = S.pH;
+#pragma unroll 1
+        for (int w = 0; w < W; ++w) {
+            const uint32_t upH = X.uH[w][lane], upG = X.uG[w][lane], upM = X.uM[w][lane];
+            uint32_t S2[RPT];
+            const uint32_t info = (xb.z >> (8 * w)) & 0xFFu;
+            if (info & 1u) {
+                const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
+                const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const int yc = C.ycode[C.q0 + k];
+                    const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
+                    S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
+                }
+            } else {
+                const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
+            }
+            uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+            if (!FWD && TRACE_M) {              // shifted forward maxima of this column (for the hot bits)
+                const uint4 *src = C.D4 + ((C.sbase + (size_t)(nb + 31 - t)) * W + (W - 1 - w)) * 64 + lane;
+                d0 = __ldcg(src); d1 = __ldcg(src + 32);
+            }
+            const uint32_t dk[RPT] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+            uint32_t vG = upG, vM = upM, codes = 0;
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int k = FWD ? j : RPT - 1 - j;
+                const uint32_t g  = __vmaxs2(S.Gl[k], vG);
+                const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);
+                const uint32_t tg = (s2 ^ C.flip) & 0x00010001u;
+                const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
+                const uint32_t Hc = s2 & 0xFFFEFFFEu;
+                const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
+                if (TRACE_S) codes |= fs_code(half16(__vadd2(dg, S2[k]), TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) << (2 * k);
+                if (TRACE_M) codes |= fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << (2 * k);
+                if (!FWD && TRACE_M) {
+                    if ((int)((__vadd2(Mn, dk[k]) >> TO.sh) & 0xFFFFu) == TO.max2) hotw |= 1u << (8 * w + k);
+                }
+                dg = S.Hl[k];
+                S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
+                vG = G2; vM = Mn;
+            }
+            constexpr int last = FWD ? RPT - 1 : 0;
+            X.oH[w][lane] = S.Hl[last]; X.oG[w][lane] = S.Gl[last]; X.oM[w][lane] = S.Ml[last];
+            X.tw[w][lane] = codes;
+            if (TRACE_M && !FWD && TO.Mp) {
+                uint4 *dst = reinterpret_cast<uint4 *>(TO.Mp) + (slot * W + w) * 64 + lane;
+                dst[0]  = make_uint4(S.Ml[0], S.Ml[1], S.Ml[2], S.Ml[3]);
+                dst[32] = make_uint4(S.Ml[4], S.Ml[5], S.Ml[6], S.Ml[7]);
+            }
+            dg = upH;                           // diagonal of the next column's first row
+        }
+        S.pH = X.uH[W - 1][lane]; S.pM = X.uM[W - 1][lane];
+        TO.P[slot * 32 + lane] = make_uint2(X.tw[0][lane] | (X.tw[1][lane] << 16), X.tw[2][lane] | (X.tw[3][lane] << 16));
+        if (!FWD && TRACE_M) TO.hot[slot * 32 + lane] = hotw;
+    }
+    __syncwarp();
+}
+
 // Recompute one window of one strip from its checkpoint, emitting the trace (pass 2).
-template <int DIR>
-__device__ void sweep_window_trace(const PairTask &T, WarpRings &R, const int lane, int s, int win, const TraceOut &TO)
+template <int DIR, int MODE>
+__device__ void sweep_window_trace(const PairTask &T, WarpRings &R, TraceSmem &X, const int lane, int s, int win, const TraceOut &TO)
 {
     constexpr bool FWD = DIR > 0;
     const int si = FWD ? s : T.nstrips - 1 - s;
@@ -382,8 +480,7 @@ __device__ void sweep_window_trace(const PairTask &T, WarpRings &R, const int la
     __syncwarp();
     if (C.first) ring_fill_border(R, lane, C.gborder);
     else { ring_prefetch(C, R, win, win & 1); cp_async_wait_all(); __syncwarp(); }
-    uint32_t best = 0;
-    sweep_window_any<DIR, MODE_TRACE>(C, S, R, win, best, TO);
+    sweep_window_compact<DIR, MODE>(C, S, R, X, win, TO);
     __syncwarp();
 }
 
