@@ -62,6 +62,9 @@ struct PairTask {
     uint32_t *Rfirst;                    // [P + 2]  2*Rmax[r][1]
     uint32_t *tilemax;                   // [nstrips][nwin][32] max over (lane's 8 rows x one window) of Fmax + Rmax
     uint32_t *ckpt_f, *ckpt_r;           // [nstrips][nwin][CKW][32] lane state at the start of every window
+    // pass-2 trace planes of the aligner(s) of this pair that get breakpoints (one set when `select`, else one per half)
+    char *p2set; uint32_t p2stride;
+    int32_t k7;                          // a TDUP / inversion aligner is present: sets also hold the reverse maxima plane
 };
 
 struct AlignerOut {
@@ -73,31 +76,40 @@ struct AlignerOut {
 
 struct Block { int32_t start1, start2, length; };
 
-// Per-warp scratch of pass 2: trace planes of the aligner being enumerated, filled window by window on demand
-// by re-running the sweep from its checkpoints.
+// Trace planes of one aligner (pass 2), filled window by window by re-running the sweep from its checkpoints:
+// the windows of the split row / column by the parallel pre-sweep kernel, everything else on demand.
 struct P2Scratch {
     uint2 *P[4];                         // 2-bit code planes FS, FM, RS, RM: [slots][32], 16 bits per block column
     uint32_t *hot;                       // [slots][32]: bit 8w+k = reverse cell holds Fmax + Rmax == max (with RM)
     uint32_t *Mp;                        // reverse maxima, same layout as D but unshifted (K7 only)
-    uint32_t *valid;                     // [5][valid_words] window-valid bits: the four planes, Mp
+    uint32_t *valid;                     // [6][vwords] window bits: the four planes, Mp, "queued for the pre-sweep"
     int32_t *rowrange;                   // [2][len2 + 2]
+    int32_t vwords;
 };
+
+struct PairHdr { int32_t max2[2]; int32_t need[2]; };   // split maxima (x2) and which halves get breakpoints
 
 struct Pass2Params {
     const PairTask *pairs;
     int32_t n_pairs;
     AlignerOut *outs;
+    PairHdr *hdr;
     Block *pool; int32_t pool_cap; int32_t *pool_used;
-    int32_t *next;                       // work counter
-    char *scratch; size_t scratch_stride; // per-warp scratch: warp w uses scratch + w * stride
-    size_t max_slots, max_rows;          // layout of one warp's scratch
-    int32_t need_mp;
+    uint2 *queue; int32_t queue_cap; int32_t *queue_n;   // pre-sweep work items {pair, half | plane << 1 | strip << 4 | window << 16}
+    int32_t *next;                       // work counters: [0] select, [1] pre-sweep, [2] pass 2
 };
+
+// layout of one plane set (shared by host and device)
+__host__ __device__ inline size_t p2_up(size_t v) { return (v + 255) / 256 * 256; }
+__host__ __device__ inline size_t p2_vwords(size_t nwt) { return (nwt + 31) / 32 + 1; }
+__host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t len2, int k7)
+{
+    return 4 * p2_up(slots * 32 * 8) + p2_up(slots * 32 * 4) + (k7 ? p2_up(slots * W * 2 * 32 * 16) : 0) +
+           p2_up(6 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4);
+}
 
 // launchers (age_kernels.cu)
 void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cudaStream_t st);
-int  pass2_warps(int n_pairs);
-size_t pass2_scratch_bytes(size_t max_slots, size_t max_rows, int need_mp);
-void launch_pass2(const Pass2Params &p, int n_warps, cudaStream_t st);
+void launch_pass2(const Pass2Params &p, cudaStream_t st);
 
 } // namespace age

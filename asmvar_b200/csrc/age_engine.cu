@@ -74,6 +74,7 @@ struct HostPair {
     int select;                  // 1: only the better half needs breakpoints (see PairTask::select)
     int len1, len2, nstrips, P, nb, nsteps, nwin;
     int k7;                      // holds a TDUP / INVL / INVR aligner (pass 2 then needs the reverse maxima plane)
+    int nsets; size_t set_bytes;  // pass-2 trace plane sets (one per aligner that gets breakpoints)
     size_t in_bytes, scratch_bytes;
     double cells;
 };
@@ -81,8 +82,8 @@ struct HostPair {
 struct Device {
     int id = 0;
     cudaStream_t st = nullptr;
-    Arena in, scratch, outbuf, p2;
-    int p2_warps = 0; size_t p2_stride = 0, max_slots = 0, max_rows = 0; int need_mp = 0;
+    Arena in, scratch, outbuf, aux;
+    int queue_cap = 0;
     PinnedBuf hin, hout;
     cudaEvent_t ev[6] = {};
     // the sub-batch currently resident on this device
@@ -192,6 +193,9 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
                            2 * align_up(((size_t)hp.P + 2) * 4, 256) + align_up(((size_t)W * hp.nb + 4) * 4, 256) +
                            align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256) +
                            2 * align_up((size_t)hp.nstrips * hp.nwin * CKW * 32 * 4, 256);
+        hp.nsets = (select || a1 < 0) ? 1 : 2;
+        hp.set_bytes = p2_set_bytes(slots, (size_t)hp.nstrips * hp.nwin, (size_t)j.len2, hp.k7);
+        hp.scratch_bytes += hp.nsets * hp.set_bytes;
         hp.cells = (double)j.len1 * j.len2;
         ctx->pairs.push_back(hp);
     };
@@ -315,7 +319,8 @@ void assign_scratch(const HostPair &hp, char *s, PairTask &T)
     T.Dtail = (uint32_t *)s; s += align_up(((size_t)W * hp.nb + 4) * 4, 256);
     T.tilemax = (uint32_t *)s; s += align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256);
     T.ckpt_f = (uint32_t *)s; s += csz;
-    T.ckpt_r = (uint32_t *)s;
+    T.ckpt_r = (uint32_t *)s; s += csz;
+    T.p2set = s; T.p2stride = (uint32_t)hp.set_bytes; T.k7 = hp.k7;
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
@@ -336,23 +341,9 @@ bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids
         for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) ctx->aligners[hp.a[k]].out = n_outs++;
     }
     dev.n_outs = n_outs;
-    dev.max_slots = 0; dev.max_rows = 0; dev.need_mp = 0;
-    for (size_t i = 0; i < np; ++i) {
-        const HostPair &hp = ctx->pairs[pair_ids[i]];
-        dev.max_slots = std::max(dev.max_slots, (size_t)hp.nstrips * hp.nsteps);
-        dev.max_rows = std::max(dev.max_rows, (size_t)hp.len2);
-        dev.need_mp |= hp.k7;
-    }
-    dev.p2_stride = align_up(pass2_scratch_bytes(dev.max_slots, dev.max_rows, dev.need_mp), 256);
-    {
-        size_t fr = 0, tot = 0;
-        cudaMemGetInfo(&fr, &tot);
-        const size_t budget = std::max((size_t)(0.10 * (double)tot), dev.p2.cap);   // pass-2 trace scratch: at most ~10 % of HBM
-        int nw = pass2_warps((int)np);
-        while (nw > 4 && (size_t)nw * dev.p2_stride > budget) nw -= 4;
-        dev.p2_warps = nw;
-    }
-    if (!dev.p2.ensure((size_t)dev.p2_warps * dev.p2_stride)) { dev.err = "device allocation failed (pass-2 scratch)"; return false; }
+    size_t nwt_total = 0;
+    for (size_t i = 0; i < np; ++i) { const HostPair &hp = ctx->pairs[pair_ids[i]]; nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets; }
+    dev.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
     dev.in_bytes = task_bytes + in_off[np];
     if (!dev.hin.ensure(dev.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
@@ -362,6 +353,7 @@ bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids
     const size_t out_bytes = align_up((size_t)n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
     if (!dev.outbuf.ensure(out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
     if (!dev.hout.ensure(out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
+    if (!dev.aux.ensure(align_up(np * sizeof(PairHdr), 256) + (size_t)dev.queue_cap * sizeof(uint2))) { dev.err = "device allocation failed (work list)"; return false; }
     parallel_for(ctx->host_threads, np, [&](size_t i) {
         pack_pair(ctx, pair_ids[i], dev.hin.ptr + task_bytes + in_off[i], dev.in.ptr + task_bytes + in_off[i], dev.tasks[i]);
         assign_scratch(ctx->pairs[pair_ids[i]], dev.scratch.ptr + sc_off[i], dev.tasks[i]);
@@ -383,6 +375,16 @@ OutLayout out_layout(Device &dev, char *base)
     return L;
 }
 
+Pass2Params pass2_params(Device &dev, const OutLayout &L)
+{
+    Pass2Params p{};
+    p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = (int)dev.tasks.size(); p.outs = L.outs;
+    p.hdr = (PairHdr *)dev.aux.ptr;
+    p.queue = (uint2 *)(dev.aux.ptr + align_up(dev.tasks.size() * sizeof(PairHdr), 256)); p.queue_cap = dev.queue_cap; p.queue_n = L.counters + 8;
+    p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 4;
+    return p;
+}
+
 bool run_on_device(age_ctx *, Device &dev)
 {
     CK(cudaSetDevice(dev.id));
@@ -392,11 +394,7 @@ bool run_on_device(age_ctx *, Device &dev)
     CK(cudaEventRecord(dev.ev[2], dev.st));
     launch_sweeps((const PairTask *)dev.in.ptr, np, L.counters + 0, dev.st);
     CK(cudaEventRecord(dev.ev[3], dev.st));
-    Pass2Params p{};
-    p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = np; p.outs = L.outs;
-    p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 1;
-    p.scratch = dev.p2.ptr; p.scratch_stride = dev.p2_stride; p.max_slots = dev.max_slots; p.max_rows = dev.max_rows; p.need_mp = dev.need_mp;
-    launch_pass2(p, dev.p2_warps, dev.st);
+    launch_pass2(pass2_params(dev, L), dev.st);
     CK(cudaEventRecord(dev.ev[4], dev.st));
     CK(cudaGetLastError());
     return true;
@@ -437,11 +435,7 @@ bool fetch_from_device(age_ctx *ctx, Device &dev)
         if (!dev.outbuf.ensure(nb) || !dev.hout.ensure(nb)) { dev.err = "allocation failed (block pool)"; return false; }
         OutLayout L = out_layout(dev, dev.outbuf.ptr);
         CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
-        Pass2Params p{};
-        p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = (int)dev.tasks.size(); p.outs = L.outs;
-        p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 1;
-        p.scratch = dev.p2.ptr; p.scratch_stride = dev.p2_stride; p.max_slots = dev.max_slots; p.max_rows = dev.max_rows; p.need_mp = dev.need_mp;
-        launch_pass2(p, dev.p2_warps, dev.st);
+        launch_pass2(pass2_params(dev, L), dev.st);
     }
     dev.err = "block pool overflow";
     return false;
@@ -466,8 +460,8 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
         cudaSetDevice(ctx->devs[d].id);
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
-        fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap + ctx->devs[d].p2.cap;
-        budget[d] = (size_t)(0.70 * (double)fr);
+        fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap + ctx->devs[d].aux.cap;
+        budget[d] = (size_t)(0.85 * (double)fr);
     }
     // longest-processing-time-first deal across devices
     std::vector<int> order(ctx->pairs.size());
@@ -574,7 +568,7 @@ extern "C" void age_destroy(age_ctx *ctx)
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
         if (d.st) cudaStreamSynchronize(d.st);
-        d.in.release(); d.scratch.release(); d.outbuf.release(); d.p2.release(); d.hin.release(); d.hout.release();
+        d.in.release(); d.scratch.release(); d.outbuf.release(); d.aux.release(); d.hin.release(); d.hout.release();
         for (auto &e : d.ev) if (e) cudaEventDestroy(e);
         if (d.st) cudaStreamDestroy(d.st);
     }

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <cstdlib>
 #include <cstdio>
+#include <algorithm>
 
 namespace age {
 
@@ -433,50 +434,38 @@ constexpr int P2_WARPS = 4;
 #define P2_OCC 4
 #endif
 
-__host__ __device__ inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-__host__ __device__ inline size_t p2_vwords(size_t max_slots) { return max_slots / 32 + 2; }   // one bit per window, windows <= slots
-
-__device__ P2Scratch carve_scratch(char *base, size_t max_slots, size_t max_rows, int need_mp, int &vwords)
+__device__ P2Scratch carve_set(const PairTask &T, int set)
 {
+    const size_t slots = (size_t)T.nstrips * T.nsteps, nwt = (size_t)T.nstrips * T.nwin;
+    char *base = T.p2set + (size_t)set * T.p2stride;
     P2Scratch sc;
-    for (int i = 0; i < 4; ++i) { sc.P[i] = (uint2 *)base; base += up256(max_slots * 32 * 8); }
-    sc.hot = (uint32_t *)base; base += up256(max_slots * 32 * 4);
-    sc.Mp = need_mp ? (uint32_t *)base : nullptr; base += need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0;
-    vwords = (int)p2_vwords(max_slots);
-    sc.valid = (uint32_t *)base; base += up256((size_t)5 * vwords * 4);
+    for (int i = 0; i < 4; ++i) { sc.P[i] = (uint2 *)base; base += p2_up(slots * 32 * 8); }
+    sc.hot = (uint32_t *)base; base += p2_up(slots * 32 * 4);
+    sc.Mp = T.k7 ? (uint32_t *)base : nullptr; base += T.k7 ? p2_up(slots * W * 2 * 32 * 16) : 0;
+    sc.vwords = (int)p2_vwords(nwt);
+    sc.valid = (uint32_t *)base; base += p2_up((size_t)6 * sc.vwords * 4);
     sc.rowrange = (int32_t *)base;
     return sc;
 }
 
-size_t pass2_scratch_bytes(size_t max_slots, size_t max_rows, int need_mp)
-{
-    return 4 * up256(max_slots * 32 * 8) + up256(max_slots * 32 * 4) + (need_mp ? up256(max_slots * W * 2 * 32 * 16) : 0) +
-           up256(5 * p2_vwords(max_slots) * 4) + up256(2 * (max_rows + 2) * 4);
-}
+// ---- select: split maxima, -both / -inv winner, work list of the windows along the split row / column -------------
+constexpr int SEL_WARPS = 4;
 
-__global__ void __launch_bounds__(P2_WARPS * 32, P2_OCC)
-age_pass2_kernel(Pass2Params prm)
+__global__ void __launch_bounds__(SEL_WARPS * 32)
+age_select_kernel(Pass2Params prm)
 {
-    __shared__ int bp_s[P2_WARPS][MAX_BP][4];
-    __shared__ WarpRings rings[P2_WARPS];
-    __shared__ TraceSmem tsm[P2_WARPS];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int gw = blockIdx.x * P2_WARPS + w;
-    int vwords = 0;
-    const P2Scratch sc = carve_scratch(prm.scratch + (size_t)gw * prm.scratch_stride, prm.max_slots, prm.max_rows, prm.need_mp, vwords);
+    const int lane = threadIdx.x & 31;
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(prm.next, 1);
+        if (lane == 0) item = atomicAdd(prm.next + 0, 1);
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= prm.n_pairs) break;
         const PairTask &T = prm.pairs[item];
-        const int len1 = T.len1, len2 = T.len2;
-
-        // ---- split maxima of both halves (:545-550 / :476-481) ------------------------------------------
-        long long pc = clock64();
+        const int len2 = T.len2;
+        // split maxima of both halves (:545-550 / :476-481)
         uint32_t mx_indel = 0, mx_col = 0;                       // packed u16x2: max of 2*(Fmax + Rmax)
-        const int ntiles = T.nstrips * T.nwin * 32;
-        for (int i = lane; i < ntiles; i += 32) mx_indel = __vmaxu2(mx_indel, T.tilemax[i]);
+        const int nwt = T.nstrips * T.nwin;
+        for (int i = lane; i < nwt * 32; i += 32) mx_indel = __vmaxu2(mx_indel, T.tilemax[i]);
         for (int r = lane; r <= len2; r += 32) {
             const uint32_t f = r >= 1 ? T.Dlast[r] : 0u, q = r + 1 <= len2 ? T.Rfirst[r + 1] : 0u;
             mx_col = __vmaxu2(mx_col, __vadd2(f, q));
@@ -502,12 +491,88 @@ age_pass2_kernel(Pass2Params prm)
             }
             need[1 - win] = false;
         }
+        if (lane == 0) prm.hdr[item] = PairHdr{{max2[0], max2[1]}, {need[0] ? 1 : 0, need[1] ? 1 : 0}};
+        for (int h = 0; h < 2; ++h) {
+            if (!need[h]) continue;
+            const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+            for (int i = lane; i < 6 * sc.vwords; i += 32) sc.valid[i] = 0;
+            __syncwarp();
+            if (T.flag[h] != F_INDEL || max2[h] == 0) continue;
+            // every reverse window with a tile at the maximum, and the forward windows over the same cells
+            uint32_t *queued = sc.valid + 5 * sc.vwords;
+            for (int wi = 0; wi < nwt; ++wi) {
+                const bool hot = (int)((T.tilemax[(size_t)wi * 32 + lane] >> (16 * h)) & 0xFFFF) == max2[h];
+                if (!__any_sync(0xFFFFFFFFu, hot)) continue;
+                if (lane >= 3) continue;
+                const int s = wi / T.nwin, win = wi % T.nwin;
+                // reverse steps t' of the window meet the forward steps nb+32-t' (same anti-diagonal)
+                const int t1 = min(CKS * win + CKS, T.nsteps);
+                const int fa = min(max((T.nb + 32 - t1 - 1) / CKS, 0), T.nwin - 1), fb = min(max((T.nb + 31 - CKS * win - 1) / CKS, 0), T.nwin - 1);
+                const int plane = lane == 0 ? 3 : 1, w2 = lane == 0 ? win : (lane == 1 ? fa : fb);
+                if (lane == 2 && fb == fa) continue;
+                if (plane == 1) {                                 // forward windows repeat between neighbours: queue once
+                    const int i = s * T.nwin + w2;
+                    if (atomicOr(&queued[i >> 5], 1u << (i & 31)) & (1u << (i & 31))) continue;
+                }
+                const int at = atomicAdd(prm.queue_n, 1);
+                if (at < prm.queue_cap) prm.queue[at] = make_uint2((uint32_t)item, (uint32_t)(h | (plane << 1) | (s << 4) | (w2 << 16)));
+            }
+        }
+    }
+}
 
+// ---- pre-sweep: one warp per queued window, at full occupancy ------------------------------------------------------
+constexpr int PRE_WARPS = 4;
+
+__global__ void __launch_bounds__(PRE_WARPS * 32)
+age_presweep_kernel(Pass2Params prm)
+{
+    __shared__ WarpRings rings[PRE_WARPS];
+    __shared__ TraceSmem tsm[PRE_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int n = min(*prm.queue_n, prm.queue_cap);
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(prm.next + 1, 1);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n) break;
+        const uint2 q = prm.queue[item];
+        const PairTask &T = prm.pairs[q.x];
+        const int h = q.y & 1, plane = (q.y >> 1) & 7, s = (q.y >> 4) & 0xFFF, win = q.y >> 16;
+        const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+        const TraceOut TO{sc.P[plane], sc.hot, nullptr, 16 * h, prm.hdr[q.x].max2[h]};
+        if (plane == 1) sweep_window_trace<+1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
+        else            sweep_window_trace<-1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
+        __threadfence();
+        __syncwarp();
+        const int i = s * T.nwin + win;
+        if (lane == 0) atomicOr(&sc.valid[plane * sc.vwords + (i >> 5)], 1u << (i & 31));
+    }
+}
+
+__global__ void __launch_bounds__(P2_WARPS * 32, P2_OCC)
+age_pass2_kernel(Pass2Params prm)
+{
+    __shared__ int bp_s[P2_WARPS][MAX_BP][4];
+    __shared__ WarpRings rings[P2_WARPS];
+    __shared__ TraceSmem tsm[P2_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(prm.next + 2, 1);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= prm.n_pairs) break;
+        const PairTask &T = prm.pairs[item];
+        const int len1 = T.len1, len2 = T.len2;
+        const PairHdr hd = prm.hdr[item];
+        const int max2[2] = {hd.max2[0], hd.max2[1]};
+        const bool need[2] = {hd.need[0] != 0, hd.need[1] != 0};
+        long long pc = clock64();
         const long long pair_c0 = pc;
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
-            const View V{&T, sc, &rings[w], &tsm[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], vwords};
-            V.reset_valid();
+            const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+            const View V{&T, sc, &rings[w], &tsm[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], sc.vwords};
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
             __syncwarp();
@@ -567,30 +632,29 @@ age_pass2_kernel(Pass2Params prm)
     }
 }
 
-int pass2_warps(int n_pairs)
+void launch_pass2(const Pass2Params &p, cudaStream_t st)
 {
+    if (p.n_pairs <= 0) return;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int blocks = (n_pairs + P2_WARPS - 1) / P2_WARPS;
-    if (blocks > sms * P2_OCC) blocks = sms * P2_OCC;
-    return blocks * P2_WARPS;
-}
-
-void launch_pass2(const Pass2Params &p, int n_warps, cudaStream_t st)
-{
-    if (p.n_pairs <= 0) return;
-    cudaMemsetAsync(p.next, 0, sizeof(int32_t), st);
     static const bool prof = getenv("AGE_P2_PROF") != nullptr;
     if (prof) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
-    age_pass2_kernel<<<n_warps / P2_WARPS, P2_WARPS * 32, 0, st>>>(p);
+    cudaMemsetAsync(p.next, 0, 4 * sizeof(int32_t), st);
+    cudaMemsetAsync(p.queue_n, 0, sizeof(int32_t), st);
+    const int nb = (p.n_pairs + 3) / 4;
+    age_select_kernel<<<std::min(nb, sms * 8), SEL_WARPS * 32, 0, st>>>(p);
+    age_presweep_kernel<<<sms * 4, PRE_WARPS * 32, 0, st>>>(p);
+    age_pass2_kernel<<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
     if (prof) {
         unsigned long long z[8];
+        int qn = 0;
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(z, g_prof, sizeof(z));
-        fprintf(stderr, "[p2 prof] slowest pair index %llu\n", z[0] & 0xFFFFFF); z[0] = (z[0] >> 24) << 10;
-        fprintf(stderr, "[p2 prof] pairs %d warps %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
-                p.n_pairs, n_warps, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[6], z[5] / 1e6, z[7]);
+        cudaMemcpy(&qn, p.queue_n, sizeof(int), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[p2 prof] pre-swept windows %d, slowest pair index %llu\n", qn, z[0] & 0xFFFFFF); z[0] = (z[0] >> 24) << 10;
+        fprintf(stderr, "[p2 prof] pairs %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | on-demand re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
+                p.n_pairs, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[6], z[5] / 1e6, z[7]);
     }
 }
 
