@@ -22,16 +22,22 @@
 namespace age {
 
 constexpr int SWEEP_WARPS = 4;
+#ifndef SWEEP_OCC
+#define SWEEP_OCC 4
+#endif
 
 // optional cycle accounting of pass 2 (AGE_P2_PROF=1): 0 maxima, 1 row ranges, 2 enumerate, 3 blocks, 4 forward re-sweeps,
 // 5 reverse re-sweeps, 6 number of forward windows, 7 number of reverse windows
 __device__ unsigned long long g_prof[8];
 #define PROF_ADD(i, v) atomicAdd(&g_prof[i], (unsigned long long)(v))
 
-__global__ void __launch_bounds__(SWEEP_WARPS * 32)
+struct SweepSmem { WarpRings rings; DStage dstage; };
+
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, SWEEP_OCC)
 age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
 {
-    __shared__ WarpRings rings[SWEEP_WARPS];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SweepSmem *sm = reinterpret_cast<SweepSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (;;) {
         int item = 0;
@@ -39,10 +45,11 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= n_pairs) break;
         const PairTask &T = pairs[item];
-        sweep_pair_fast<+1>(T, rings[w], lane);
+        sweep_pair_fast<+1>(T, sm[w].rings, sm[w].dstage, lane);
         __threadfence_block();
         __syncwarp();
-        sweep_pair_fast<-1>(T, rings[w], lane);
+        sweep_pair_fast<-1>(T, sm[w].rings, sm[w].dstage, lane);
+        cp_async_wait_all();
         __syncwarp();
     }
 }
@@ -57,7 +64,9 @@ void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cud
     static const int occ = getenv("AGE_OCC") ? atoi(getenv("AGE_OCC")) : 8;
     if (blocks > sms * occ) blocks = sms * occ;              // persistent: the work counter feeds the warps
     cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st);
-    age_sweep_kernel<<<blocks, SWEEP_WARPS * 32, 0, st>>>(d_pairs, n_pairs, d_counter);
+    const int smem = SWEEP_WARPS * (int)sizeof(SweepSmem);
+    cudaFuncSetAttribute(age_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    age_sweep_kernel<<<blocks, SWEEP_WARPS * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -64,6 +64,10 @@ struct WarpRings {                          // shared memory of one warp
     uint4 out[3][32];                       // boundary rows produced by lane p = 31
 };
 
+struct DStage {                             // reverse main sweep: the D slot of the next step, fetched with cp.async
+    uint4 d[2][W * 2][32];                  // [step parity][block column x half of rows][lane]  (8 KB per warp)
+};
+
 struct TraceOut {                           // trace re-sweep outputs (one half of the pair, one kind of trace)
     uint2 *P;                               // 2-bit codes: [slot][lane], 16 bits per block column, 2 bits per row
     uint32_t *hot;                          // MODE_TRACE_M, reverse: bit 8w+k = the cell holds Fmax + Rmax == max
@@ -185,8 +189,20 @@ __device__ __forceinline__ void ring_fill_border(WarpRings &R, int lane, uint32_
 
 // One window (steps t0 .. t1) of one strip.  GUARD = false is the steady state in which every lane is active in
 // every step of the window.
+// D slot of reverse step t (written by the forward sweep in step nb+32-t) -> shared memory, asynchronously
+template <int DIR>
+__device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS, int t)
+{
+    if (t <= C.nsteps) {
+        const uint4 *src = C.D4 + ((C.sbase + (size_t)(C.nb + 31 - t)) * W) * 64 + C.lane;
+#pragma unroll
+        for (int i = 0; i < W * 2; ++i) cp_async16(&DS.d[t & 1][i][C.lane], src + i * 32);
+    }
+    cp_async_commit();
+}
+
 template <int DIR, int MODE, bool GUARD>
-__device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, const int win,
+__device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
                                              const int t0, const int t1, uint32_t &best, const TraceOut &TO)
 {
     constexpr bool FWD = DIR > 0;
@@ -199,6 +215,10 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
     for (int t = t0; t <= t1; ++t) {
         const uint4 xb = xnext;
         xnext = xload(t + 1 - p);
+        if (!FWD) {                             // D of the next step in flight, D of this step landed (each lane reads its own)
+            dstage_fetch(C, DS, t + 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
         // ---- values of the row above for the 4 columns of this block -------------------------------------
         uint32_t uH[W], uG[W], uM[W];
 #pragma unroll
@@ -214,12 +234,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
         if (!GUARD || (b >= 1 && b <= nb)) {
             const size_t slot = C.sbase + (size_t)(t - 1);
             // reverse sweep: the shifted forward maxima of this block, written by the forward lane in step nb+32-t
-            uint4 dq[W][2];
-            if (!FWD && !TRACE_S) {
-                const uint4 *src = C.D4 + ((C.sbase + (size_t)(nb + 31 - t)) * W) * 64 + lane;
-#pragma unroll
-                for (int w = 0; w < W; ++w) { dq[w][0] = __ldcg(src + (w * 2 + 0) * 32); dq[w][1] = __ldcg(src + (w * 2 + 1) * 32); }
-            }
+
             const bool special = (xb.z & 0x01010101u) != 0;
             uint32_t tw[W];
             uint32_t hotw = 0;
@@ -256,6 +271,8 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                     for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
                 }
                 // ---- the column ---------------------------------------------------------------------------------
+                uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
+                if (!FWD) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
                 uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
                 uint32_t nibw = 0;
 #pragma unroll
@@ -270,7 +287,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                     if (TRACE_S) nibw |= fs_code(half16(__vadd2(dg, S2[k]), TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) << (2 * k);
                     if (TRACE_M) nibw |= fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << (2 * k);
                     if (!FWD && !TRACE_S) {
-                        const uint4 dv = dq[W - 1 - w][k >> 2];
+                        const uint4 dv = (k >> 2) ? dc1 : dc0;
                         const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
                         const uint32_t sum = __vadd2(Mn, dk);
                         if (!TRACE) best = __vmaxu2(best, sum);
@@ -321,17 +338,17 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
 
 // dispatch on whether the window is steady (all lanes active in all of its steps)
 template <int DIR, int MODE>
-__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, int win,
+__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win,
                                                  uint32_t &best, const TraceOut &TO)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
-    if (MODE == MODE_FAST && t0 >= 32 && t1 <= C.nb) sweep_window<DIR, MODE, false>(C, S, R, win, t0, t1, best, TO);
-    else                        sweep_window<DIR, MODE, true>(C, S, R, win, t0, t1, best, TO);
+    if (MODE == MODE_FAST && t0 >= 32 && t1 <= C.nb) sweep_window<DIR, MODE, false>(C, S, R, DS, win, t0, t1, best, TO);
+    else                        sweep_window<DIR, MODE, true>(C, S, R, DS, win, t0, t1, best, TO);
 }
 
 // The main sweep of one pair in one direction: all strips, all windows, checkpoints and tile maxima.
 template <int DIR>
-__device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, const int lane)
+__device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, const int lane)
 {
     constexpr bool FWD = DIR > 0;
     const TraceOut none{nullptr, nullptr, nullptr, 0, 0};
@@ -344,12 +361,13 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, const int lane)
         if (C.first) ring_fill_border(R, lane, C.gborder);
         else ring_prefetch(C, R, 0, 0);
         uint32_t best = 0;
+        if (!FWD) dstage_fetch(C, DS, 1);
         for (int win = 0; win < C.nwin; ++win) {
             cp_async_wait_all();
             __syncwarp();
             if (!C.first && win + 1 < C.nwin) ring_prefetch(C, R, win + 1, (win + 1) & 1);
             state_save(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
-            sweep_window_any<DIR, MODE_FAST>(C, S, R, win, best, none);
+            sweep_window_any<DIR, MODE_FAST>(C, S, R, DS, win, best, none);
             if (!FWD) { C.tilemax[(size_t)(s * C.nwin + win) * 32 + lane] = best; best = 0; }
         }
         // the maxima at the last processed column: Fmax[.][len1] (forward) / Rmax[.][1] (reverse)
