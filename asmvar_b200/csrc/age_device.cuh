@@ -47,9 +47,13 @@ struct PairTask {
     uint32_t m2, mm2;                    // 2*match, 2*mismatch packed per half (special-column path)
     // inputs.  xblk[b] describes the 4 columns of logical block b (1..nb) in processing order:
     //   .x / .y = PRMT selectors of columns 0,1 / 2,3 (16 bit each); .z = per column byte: bit0 special, bits1-3 / 4-6 codes
-    const uint4 *xblk_f, *xblk_r;        // [nb + 2]
-    const uint2 *ytab;                   // [P] {Ta, Tb}: bytes = 2*S(x in ACGT, y_row) of aligner A / B
-    const uint8_t *ycode;                // [P] low nibble = code of A's row, high nibble = B's
+    uint4 *xblk_f, *xblk_r;              // [nb + 2]
+    uint2 *ytab;                         // [P] {Ta, Tb}: bytes = 2*S(x in ACGT, y_row) of aligner A / B
+    uint8_t *ycode;                      // [P] low nibble = code of A's row, high nibble = B's
+    // raw inputs of the two aligners (device copies of age_job::seq1 / seq2; null = no aligner in that half): the pack
+    // kernel derives xblk / ytab / ycode from them (Scorer.hh:24-39, Sequence.hh:138-150,190-198)
+    const char *raw1[2], *raw2[2];
+    int16_t match[2], mismatch[2];
     // strip boundary rows, planes H, G, M: [(nstrips-1)][3][nb + 1] uint4 (4 columns of a block each)
     uint4 *bnd_f, *bnd_r;
     // Diagonal-major planes, [strip][step][...][lane]: what the 32 lanes touch in one step is contiguous, for the
@@ -109,6 +113,7 @@ __host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t 
 }
 
 // launchers (age_kernels.cu)
+void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st);
 void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cudaStream_t st);
 void launch_pass2(const Pass2Params &p, cudaStream_t st);
 

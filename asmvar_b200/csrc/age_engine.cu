@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -25,20 +26,6 @@ namespace {
 thread_local std::string g_create_error;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// nucleotide code of the reference's Scorer (Scorer.hh:24-39, Sequence.hh:138-150,182-188):
-// A C G T U score among themselves (U only matches U), everything else scores 0 against everything.
-inline int nuc_code(char ch)
-{
-    switch (ch) {
-    case 'A': case 'a': return 0;
-    case 'C': case 'c': return 1;
-    case 'G': case 'g': return 2;
-    case 'T': case 't': return 3;
-    case 'U': case 'u': return 4;
-    default: return 5;
-    }
-}
 
 struct Arena {
     char *ptr = nullptr; size_t cap = 0;
@@ -107,7 +94,6 @@ struct age_ctx {
     std::vector<HostPair> pairs;
     std::vector<AlignerOut> outs;                 // per aligner (global index)
     std::vector<std::vector<age_block>> blocks;   // per aligner: left | right | alt_left | alt_right
-    std::vector<std::string> rc1;                 // per job: revcom of seq1 when an inversion mode needs it
     bool staged = false;
     int host_threads = 1;
 };
@@ -144,7 +130,6 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
     ctx->jobs = jobs; ctx->n_jobs = n;
     ctx->job_status.assign(n, AGE_OK);
     ctx->aligners.clear(); ctx->pairs.clear();
-    ctx->rc1.assign(n, std::string());
     for (size_t i = 0; i < n; ++i) {
         const age_job &j = jobs[i];
         int st = AGE_OK;
@@ -159,15 +144,6 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
             ctx->aligners.push_back({(int)i, 1, F_INVR, -1});
         } else ctx->aligners.push_back({(int)i, 0, j.flag, -1});
     }
-    // revcom of seq1 for the inversion modes (AGEaligner.cpp:27, :1000, :1050)
-    parallel_for(ctx->host_threads, n, [&](size_t i) {
-        if (ctx->job_status[i] != AGE_OK) return;
-        const age_job &j = jobs[i];
-        if (j.flag & (F_INV | F_INVL | F_INVR)) {
-            ctx->rc1[i].resize(j.len1);
-            age_revcom(j.seq1, j.len1, &ctx->rc1[i][0]);
-        }
-    });
     // pair aligners of identical shape and scoring.  Selection pairs first: INVL+INVR of one -inv job
     // (AGEaligner.cpp:136-154) and mutual -both partners (age_align.cpp:264-278) share a warp, and only the
     // half that the reference would print is enumerated and traced back.
@@ -187,12 +163,13 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
         hp.nb = (j.len1 + W - 1) / W; hp.nsteps = hp.nb + 31; hp.nwin = (hp.nsteps + CKS - 1) / CKS;
         hp.k7 = (ctx->aligners[a0].flag != F_INDEL) || (a1 >= 0 && ctx->aligners[a1].flag != F_INDEL);
         const size_t slots = (size_t)hp.nstrips * hp.nsteps;                 // (strip, step) slots of the diagonal-major planes
-        hp.in_bytes = 2 * align_up(((size_t)hp.nb + 2) * 16, 16) + align_up((size_t)hp.P * 8, 16) + align_up((size_t)hp.P, 16);
+        hp.in_bytes = 2 * (align_up((size_t)j.len1, 16) + align_up((size_t)j.len2, 16));   // raw sequences of both halves
         hp.scratch_bytes = align_up(slots * W * 2 * 32 * 16, 256) +
                            2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16, 256) +
                            2 * align_up(((size_t)hp.P + 2) * 4, 256) + align_up(((size_t)W * hp.nb + 4) * 4, 256) +
                            align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256) +
                            2 * align_up((size_t)hp.nstrips * hp.nwin * CKW * 32 * 4, 256);
+        hp.scratch_bytes += 2 * align_up(((size_t)hp.nb + 2) * 16, 256) + align_up((size_t)hp.P * 8, 256) + align_up((size_t)hp.P, 256);
         hp.nsets = (select || a1 < 0) ? 1 : 2;
         hp.set_bytes = p2_set_bytes(slots, (size_t)hp.nstrips * hp.nwin, (size_t)j.len2, hp.k7);
         hp.scratch_bytes += hp.nsets * hp.set_bytes;
@@ -224,70 +201,32 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
     ctx->blocks.assign(ctx->aligners.size(), {});
 }
 
-// per-block column descriptors of a pair (see PairTask::xblk) for the strings xa / xb (either may be null).
-// dir > 0: logical block b holds columns W(b-1)+1 .. Wb ascending; dir < 0: columns W(nb-b+1) .. W(nb-b)+1 descending.
-// Columns beyond len1 are padding: special, scoring 0 against everything.
-void fill_xblk(uint4 *dst, int len1, int nb, int dir, const char *xa, const char *xb)
-{
-    dst[0] = make_uint4(0, 0, 0x3B3B3B3Bu, 0); dst[nb + 1] = dst[0];
-    for (int b = 1; b <= nb; ++b) {
-        uint32_t sel[W], info = 0;
-        for (int w = 0; w < W; ++w) {
-            const int c = dir > 0 ? W * (b - 1) + 1 + w : W * (nb - b + 1) - w;
-            int a = 5, e = 5;
-            if (c <= len1) { a = xa ? nuc_code(xa[c - 1]) : 5; e = xb ? nuc_code(xb[c - 1]) : 5; }
-            if (a < 4 && e < 4) sel[w] = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + e) << 8) | ((uint32_t)((4 + e) | 8) << 12);
-            else { sel[w] = 0; info |= (1u | ((uint32_t)a << 1) | ((uint32_t)e << 4)) << (8 * w); }
-        }
-        dst[b] = make_uint4(sel[0] | (sel[1] << 16), sel[2] | (sel[3] << 16), info, 0);
-    }
-}
-
 uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
-// pack the inputs of pair `pi` into host memory at `h`, device addresses based at `d`
+// Copy the raw sequences of pair `pi` into the pinned host blob at `h` (device address `d`) and fill its task record.
+// The column descriptors and row tables are derived from the raw strings on the device (age_pack_kernel).
 void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
 {
     const HostPair &hp = ctx->pairs[pi];
-    const size_t xs = align_up(((size_t)hp.nb + 2) * 16, 16);
-    uint4 *xf = (uint4 *)h, *xr = (uint4 *)(h + xs);
-    uint2 *ytab = (uint2 *)(h + 2 * xs);
-    uint8_t *ycode = (uint8_t *)(h + 2 * xs + align_up((size_t)hp.P * 8, 16));
     memset(&T, 0, sizeof(T));
     T.len1 = hp.len1; T.len2 = hp.len2; T.nstrips = hp.nstrips; T.P = hp.P;
     T.select = hp.select; T.nb = hp.nb; T.nsteps = hp.nsteps; T.nwin = hp.nwin;
-    const char *xfwd[2] = {nullptr, nullptr}, *xrev[2] = {nullptr, nullptr}, *y[2] = {nullptr, nullptr};
     int sc[2][4] = {{1, -1, -1, -1}, {1, -1, -1, -1}};
+    size_t off = 0;
+    const char *first_seq1 = nullptr;
     for (int k = 0; k < 2; ++k) {
         T.flag[k] = 0; T.out[k] = -1;
         if (hp.a[k] < 0) continue;
         const Aligner &al = ctx->aligners[hp.a[k]];
         const age_job &j = ctx->jobs[al.job];
         T.flag[k] = al.flag; T.out[k] = al.out;
-        const char *rc = ctx->rc1[al.job].empty() ? nullptr : ctx->rc1[al.job].data();
-        xfwd[k] = (al.flag & F_INVR) ? rc : j.seq1;           // AGEaligner.cpp:1000
-        xrev[k] = (al.flag & F_INVL) ? rc : j.seq1;           // AGEaligner.cpp:1050
-        y[k] = j.seq2;
+        if (k == 1 && first_seq1 == j.seq1) T.raw1[1] = T.raw1[0];          // -both / -inv halves share the window
+        else { memcpy(h + off, j.seq1, hp.len1); T.raw1[k] = d + off; off += align_up(hp.len1, 16); first_seq1 = j.seq1; }
+        memcpy(h + off, j.seq2, hp.len2); T.raw2[k] = d + off; off += align_up(hp.len2, 16);
         sc[k][0] = j.match; sc[k][1] = j.mismatch; sc[k][2] = j.gap_open; sc[k][3] = j.gap_extend;
+        T.match[k] = j.match; T.mismatch[k] = j.mismatch;
     }
     if (hp.a[1] < 0) { for (int q = 0; q < 4; ++q) sc[1][q] = sc[0][q]; }
-    fill_xblk(xf, hp.len1, hp.nb, +1, xfwd[0], xfwd[1]);
-    fill_xblk(xr, hp.len1, hp.nb, -1, xrev[0], xrev[1]);
-    for (int q = 0; q < hp.P; ++q) {
-        uint32_t tab[2] = {0, 0}; int code[2] = {5, 5};
-        for (int k = 0; k < 2; ++k) {
-            if (!y[k] || q >= hp.len2) continue;
-            const int yc = nuc_code(y[k][q]);
-            code[k] = yc;
-            if (yc >= 5) continue;
-            for (int x = 0; x < 4; ++x) {
-                const int s2 = 2 * (x == yc ? sc[k][0] : sc[k][1]);
-                tab[k] |= ((uint32_t)s2 & 0xFFu) << (8 * x);
-            }
-        }
-        ytab[q] = make_uint2(tab[0], tab[1]);
-        ycode[q] = (uint8_t)(code[0] | (code[1] << 4));
-    }
     int c0x[2], kabs[2], flip[2], gb[2];
     for (int k = 0; k < 2; ++k) {
         const int go = sc[k][2], ge = sc[k][3];
@@ -300,10 +239,6 @@ void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
     // identical scoring
     T.c0x = pack2(c0x[0], c0x[1]); T.kabs = (uint32_t)kabs[0]; T.flip = pack2(flip[0], flip[1]); T.gborder = pack2(gb[0], gb[1]);
     T.m2 = pack2(2 * sc[0][0], 2 * sc[1][0]); T.mm2 = pack2(2 * sc[0][1], 2 * sc[1][1]);
-    T.xblk_f = (const uint4 *)d;
-    T.xblk_r = (const uint4 *)(d + xs);
-    T.ytab = (const uint2 *)(d + 2 * xs);
-    T.ycode = (const uint8_t *)(d + 2 * xs + align_up((size_t)hp.P * 8, 16));
 }
 
 void assign_scratch(const HostPair &hp, char *s, PairTask &T)
@@ -320,16 +255,24 @@ void assign_scratch(const HostPair &hp, char *s, PairTask &T)
     T.tilemax = (uint32_t *)s; s += align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256);
     T.ckpt_f = (uint32_t *)s; s += csz;
     T.ckpt_r = (uint32_t *)s; s += csz;
+    const size_t xs = align_up(((size_t)hp.nb + 2) * 16, 256);
+    T.xblk_f = (uint4 *)s; s += xs;
+    T.xblk_r = (uint4 *)s; s += xs;
+    T.ytab = (uint2 *)s; s += align_up((size_t)hp.P * 8, 256);
+    T.ycode = (uint8_t *)s; s += align_up((size_t)hp.P, 256);
     T.p2set = s; T.p2stride = (uint32_t)hp.set_bytes; T.k7 = hp.k7;
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 // stage one sub-batch (pair ids) on a device: pack, copy inputs, lay out scratch
-bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids)
+bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids_in)
 {
     CK(cudaSetDevice(dev.id));
-    dev.pair_ids = pair_ids;
+    // longest pairs first: the persistent sweep kernel hands out pairs in this order, so its tail is made of short ones
+    dev.pair_ids = pair_ids_in;
+    std::stable_sort(dev.pair_ids.begin(), dev.pair_ids.end(), [&](int a, int b) { return ctx->pairs[a].cells * ctx->pairs[a].nstrips > ctx->pairs[b].cells * ctx->pairs[b].nstrips; });
+    const std::vector<int> &pair_ids = dev.pair_ids;
     const size_t np = pair_ids.size();
     dev.tasks.assign(np, PairTask{});
     std::vector<size_t> in_off(np + 1, 0), sc_off(np + 1, 0);
@@ -362,6 +305,7 @@ bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids
     CK(cudaEventRecord(dev.ev[0], dev.st));
     CK(cudaMemcpyAsync(dev.in.ptr, dev.hin.ptr, dev.in_bytes, cudaMemcpyHostToDevice, dev.st));
     CK(cudaEventRecord(dev.ev[1], dev.st));
+    launch_pack((const PairTask *)dev.in.ptr, (int)np, dev.st);
     return true;
 }
 
@@ -577,8 +521,12 @@ extern "C" void age_destroy(age_ctx *ctx)
 
 extern "C" const char *age_last_error(const age_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+static double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 static int run_plan(age_ctx *ctx, age_result *out, size_t n)
 {
+    static const bool hprof = getenv("AGE_HOST_PROF") != nullptr;
+    double tp[6] = {0, 0, 0, 0, 0, 0};
     auto sub = make_subbatches(ctx);
     const int nd = (int)ctx->devs.size();
     std::vector<int> rc(nd, 0);
@@ -592,7 +540,14 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
     if (nd == 1) {
         Device &dev = ctx->devs[0];
         for (auto &ids : sub[0]) {
-            if (!stage_on_device(ctx, dev, ids) || !run_on_device(ctx, dev) || !fetch_from_device(ctx, dev)) { rc[0] = AGE_ERR_CUDA; break; }
+            double t0 = wall_ms();
+            bool ok = stage_on_device(ctx, dev, ids);
+            if (hprof) { cudaStreamSynchronize(dev.st); tp[0] += wall_ms() - t0; t0 = wall_ms(); }
+            ok = ok && run_on_device(ctx, dev);
+            if (hprof) { cudaStreamSynchronize(dev.st); tp[1] += wall_ms() - t0; t0 = wall_ms(); }
+            ok = ok && fetch_from_device(ctx, dev);
+            if (hprof) tp[2] += wall_ms() - t0;
+            if (!ok) { rc[0] = AGE_ERR_CUDA; break; }
             ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 2; ctx->stats.fill_launches += 1;
             add_timing(ctx, dev);
         }
@@ -605,7 +560,9 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
     for (int d = 0; d < nd; ++d)
         if (rc[d]) { ctx->err = ctx->devs[d].err; return rc[d]; }
     account(ctx);
+    double t0 = wall_ms();
     assemble(ctx, out, n);
+    if (hprof) fprintf(stderr, "[host prof] stage(pack+H2D) %.2f ms, kernels %.2f ms, fetch(D2H+copy) %.2f ms, assemble %.2f ms\n", tp[0], tp[1], tp[2], wall_ms() - t0);
     return 0;
 }
 
@@ -614,7 +571,9 @@ extern "C" int age_align_batch(age_ctx *ctx, const age_job *jobs, size_t n, age_
     if (!ctx || (!jobs && n) || (!out && n)) return AGE_ERR_ARG;
     ctx->stats = age_stats{};
     ctx->staged = false;
+    const double tb = wall_ms();
     build_plan(ctx, jobs, n);
+    if (getenv("AGE_HOST_PROF")) fprintf(stderr, "[host prof] plan %.2f ms\n", wall_ms() - tb);
     return run_plan(ctx, out, n);
 }
 

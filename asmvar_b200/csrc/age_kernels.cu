@@ -31,6 +31,73 @@ constexpr int SWEEP_WARPS = 4;
 __device__ unsigned long long g_prof[8];
 #define PROF_ADD(i, v) atomicAdd(&g_prof[i], (unsigned long long)(v))
 
+// ------------------------------------------------------------------------------------------------
+// pack: raw nucleotide strings -> the per-block column descriptors and per-row score tables of the sweep
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nuc_code(char ch)            // Scorer.hh:24-39 with Sequence.hh:138-150,182-188
+{
+    switch (ch) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    case 'U': case 'u': return 4;
+    default: return 5;                                       // scores 0 against everything
+    }
+}
+__device__ __forceinline__ int comp_code(int c) { return c < 4 ? 3 - c : (c == 4 ? 0 : 5); }   // complement: U -> A
+
+__global__ void __launch_bounds__(256)
+age_pack_kernel(const PairTask *__restrict__ pairs, int n_pairs)
+{
+    for (int pi = blockIdx.x; pi < n_pairs; pi += gridDim.x) {
+        const PairTask &T = pairs[pi];
+        const int len1 = T.len1, len2 = T.len2, nb = T.nb;
+        // column code of half k in direction dir: the forward fill of INVR and the reverse fill of INVL read the
+        // reverse complement of seq1 (AGEaligner.cpp:1000, :1050)
+        auto xcode = [&](int k, int dir, int c) -> int {
+            const char *raw = T.raw1[k];
+            if (!raw || c > len1) return 5;
+            const bool rc = dir > 0 ? (T.flag[k] & F_INVR) : (T.flag[k] & F_INVL);
+            return rc ? comp_code(nuc_code(raw[len1 - c])) : nuc_code(raw[c - 1]);
+        };
+        for (int idx = threadIdx.x; idx < 2 * (nb + 2); idx += blockDim.x) {
+            const int dir = idx < nb + 2 ? +1 : -1, b = idx < nb + 2 ? idx : idx - (nb + 2);
+            uint4 *dst = dir > 0 ? T.xblk_f : T.xblk_r;
+            if (b == 0 || b == nb + 1) { dst[b] = make_uint4(0, 0, 0x5B5B5B5Bu, 0); continue; }
+            uint32_t sel[W], info = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int c = dir > 0 ? W * (b - 1) + 1 + w : W * (nb - b + 1) - w;   // columns beyond len1 are padding
+                const int a = xcode(0, dir, c), e = xcode(1, dir, c);
+                if (a < 4 && e < 4) sel[w] = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + e) << 8) | ((uint32_t)((4 + e) | 8) << 12);
+                else { sel[w] = 0; info |= (1u | ((uint32_t)a << 1) | ((uint32_t)e << 4)) << (8 * w); }
+            }
+            dst[b] = make_uint4(sel[0] | (sel[1] << 16), sel[2] | (sel[3] << 16), info, 0);
+        }
+        for (int q = threadIdx.x; q < T.P; q += blockDim.x) {
+            uint32_t tab[2] = {0, 0};
+            int code[2] = {5, 5};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (!T.raw2[k] || q >= len2) continue;
+                const int yc = nuc_code(T.raw2[k][q]);
+                code[k] = yc;
+                if (yc >= 5) continue;
+                for (int x = 0; x < 4; ++x) tab[k] |= ((uint32_t)(2 * (x == yc ? T.match[k] : T.mismatch[k])) & 0xFFu) << (8 * x);
+            }
+            T.ytab[q] = make_uint2(tab[0], tab[1]);
+            T.ycode[q] = (uint8_t)(code[0] | (code[1] << 4));
+        }
+    }
+}
+
+void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st)
+{
+    if (n_pairs <= 0) return;
+    age_pack_kernel<<<std::min(n_pairs, 148 * 16), 256, 0, st>>>(d_pairs, n_pairs);
+}
+
 struct SweepSmem { WarpRings rings; DStage dstage; };
 
 __global__ void __launch_bounds__(SWEEP_WARPS * 32, SWEEP_OCC)

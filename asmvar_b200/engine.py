@@ -65,9 +65,10 @@ class Engine:
         if rc != 0:
             raise AgeError(f"{what} failed ({rc}): " + (self.lib.age_last_error(self.ctx) or b"").decode())
 
-    def align_raw(self, arr, n: int):
-        """age_align_batch over a prepared job array; returns the ctypes result array (valid until the next call)."""
-        res = (capi.AgeResult * max(1, n))()
+    def align_raw(self, arr, n: int, out=None):
+        """age_align_batch over a prepared job array; returns the ctypes result array (valid until the next call).
+        `out` may be a result array from an earlier call, to keep allocation out of a timed loop."""
+        res = out if out is not None else (capi.AgeResult * max(1, n))()
         self._check(self.lib.age_align_batch(self.ctx, arr, n, res), "age_align_batch")
         return res
 
