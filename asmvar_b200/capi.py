@@ -91,7 +91,7 @@ class AgeStats(C.Structure):
 # every symbol include/age_b200.h declares; tests check the library exports all of them
 EXPORTED_SYMBOLS = [
     "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged",
-    "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version",
+    "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version", "age_int16_peak",
 ]
 
 _lib = None
@@ -131,6 +131,8 @@ def load() -> C.CDLL:
     lib.age_revcom.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]
     lib.age_subst_score.restype = C.c_int
     lib.age_subst_score.argtypes = [C.c_char, C.c_char, C.c_int, C.c_int]
+    lib.age_int16_peak.restype = C.c_int
+    lib.age_int16_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     lib.age_version.restype = C.c_char_p
     lib.age_version.argtypes = []
     _lib = lib

@@ -734,4 +734,56 @@ void launch_pass2(const Pass2Params &p, cudaStream_t st)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// int16x2 SIMD issue-rate microbenchmark (denominator of bench.py's int_roofline)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+age_int16_peak_kernel(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[8];
+    const uint32_t b = seed * 0x00010001u + threadIdx.x, c = (seed ^ 0x5555u) | 0x00010001u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = (threadIdx.x + k * 977u) * 0x00030001u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                       // 8 independent chains, 6 SIMD / logic instructions each
+            uint32_t x = __vmaxs2(a[k], b);
+            x = __viaddmax_s16x2_relu(x, c, b);
+            x = (x ^ c) & 0xFFFEFFFEu;
+            x = __vadd2(x, b);
+            x = __vimax3_s16x2(x, a[k], c);
+            a[k] = x & 0x7FFF7FFFu;
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r ^= a[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 } // namespace age
+
+extern "C" int age_int16_peak(int device, double *giga_lane_instr_per_s)
+{
+    using namespace age;
+    if (!giga_lane_instr_per_s || cudaSetDevice(device) != cudaSuccess) return -2;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    uint32_t *d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * threads * 4) != cudaSuccess) return -2;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        age_int16_peak_kernel<<<blocks, threads>>>(d, iters, 3u + rep);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return -2; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *giga_lane_instr_per_s = (double)blocks * threads * iters * 8 * 6 / (best * 1e-3) / 1e9;
+    return 0;
+}

@@ -34,6 +34,11 @@ sys.path.insert(0, str(ROOT))
 
 SCORING = (1, -1, -10, -1)          # AgeOption.h:25-28 (AsmvarDetect defaults) = Test2/Run.sh
 ALG_BYTES_PER_CELL_UPDATE = 2.5     # indel = 5 B per matrix cell = 2.5 B per cell update
+KERNELS_PER_STEP = 5                # age_pack, age_sweep, age_select, age_presweep, age_pass2
+# s16x2 / logic instructions of the recurrence per cell pair: VIMNMX, PRMT, VIADDMNMX, LOP3, VIADD,
+# LOP3, VIMNMX3 in both sweeps, + VIADD, VIMNMX.U16x2 for the split sum in the reverse sweep  => (7 + 9) / 2 per pair-cell
+# visit, and a pair-cell visit is two cell updates
+SIMD_INSTR_PER_CELL_UPDATE = (7 + 9) / 2 / 2
 WORKLOAD = "C2 synthetic indel candidates: 5 kb windows, 2x500 bp flanks, -indel -both, 1/-1/-10/-1"
 
 
@@ -154,9 +159,9 @@ def reference_arm(args, rank: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1024, help="candidates per step per GPU")
+    ap.add_argument("--batch", type=int, default=2368, help="candidates per step per GPU (2368 = 148 SMs x 16 resident warps)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -208,7 +213,7 @@ def main():
         k_ms += st["kernel_ms"]; fill_ms += st["fill_ms"]
     barrier()
     wall_kernel = time.perf_counter() - t0
-    launches = args.steps * 2
+    launches = args.steps * KERNELS_PER_STEP
     clocks = sampler.stop() if rank == 0 else None
     res = eng.fetch(n)
     bad = sum(1 for i in range(n) if res[i].status != 0)
@@ -253,6 +258,13 @@ def main():
                          "kernel": "age_sweep_kernel", "peak_source": which,
                          "note": "algorithmic bytes = 2.5 B per cell update (SURVEY 8d); per-GPU figure"},
         }
+        peak = C.c_double(0.0)
+        if capi.load().age_int16_peak(local, C.byref(peak)) == 0 and peak.value > 0:
+            ach_i = SIMD_INSTR_PER_CELL_UPDATE * cu * args.steps / (fill_ms / 1e3) / 1e9
+            out["int_roofline"] = {"bound": "int16x2 SIMD issue", "achieved": ach_i, "peak": peak.value, "unit": "G lane-instr/s",
+                                   "frac": ach_i / peak.value, "kernel": "age_sweep_kernel",
+                                   "note": "achieved = 4 algorithmic s16x2/logic instructions per cell update x cell updates / sweep-kernel time; "
+                                           "peak = age_int16_peak microbenchmark on this GPU (independent chains of the same instruction mix)"}
         if world == 1 and not args.no_cpu:
             try:
                 cores = os.cpu_count() or 1

@@ -121,6 +121,12 @@ size_t age_format_alignment(const age_seqview *s1, const age_seqview *s2, const 
 void age_revcom(const char *in, int32_t n, char *out);
 int  age_subst_score(char a, char b, int match, int mismatch);
 
+/* Measurement helper (no counterpart in the reference): sustained issue rate of independent s16x2 SIMD chains
+ * (VIMNMX / VIADDMNMX / VIMNMX3 / VIADD.16x2 / LOP3, the instruction mix of the DP recurrence) on every SM of
+ * `device`, in 1e9 lane-instructions per second (one 32-bit SIMD instruction of one thread = 1).  This is the
+ * denominator of bench.py's int_roofline.  Returns 0 or AGE_ERR_CUDA. */
+int age_int16_peak(int device, double *giga_lane_instr_per_s);
+
 const char *age_version(void);
 
 #ifdef __cplusplus
