@@ -530,10 +530,15 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
     auto sub = make_subbatches(ctx);
     const int nd = (int)ctx->devs.size();
     std::vector<int> rc(nd, 0);
+    std::vector<age_stats> dstat(nd);
     auto worker = [&](int d) {
         Device &dev = ctx->devs[d];
         for (auto &ids : sub[d]) {
             if (!stage_on_device(ctx, dev, ids) || !run_on_device(ctx, dev) || !fetch_from_device(ctx, dev)) { rc[d] = AGE_ERR_CUDA; return; }
+            float ms = 0;
+            dstat[d].h2d_bytes += dev.in_bytes;
+            if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) dstat[d].fill_ms += ms;
+            if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) dstat[d].kernel_ms += ms;
         }
     };
     // timing is accumulated after the join (stats are not thread-safe)
@@ -548,14 +553,19 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
             ok = ok && fetch_from_device(ctx, dev);
             if (hprof) tp[2] += wall_ms() - t0;
             if (!ok) { rc[0] = AGE_ERR_CUDA; break; }
-            ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 2; ctx->stats.fill_launches += 1;
+            ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 5; ctx->stats.fill_launches += 1;
             add_timing(ctx, dev);
         }
     } else {
         std::vector<std::thread> th;
         for (int d = 0; d < nd; ++d) th.emplace_back(worker, d);
         for (auto &t : th) t.join();
-        for (int d = 0; d < nd; ++d) { ctx->stats.launches += 2 * sub[d].size(); ctx->stats.fill_launches += sub[d].size(); }
+        for (int d = 0; d < nd; ++d) {      // devices run concurrently: report the slowest one
+            ctx->stats.launches += 5 * sub[d].size(); ctx->stats.fill_launches += sub[d].size();
+            ctx->stats.h2d_bytes += dstat[d].h2d_bytes;
+            ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, dstat[d].kernel_ms);
+            ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, dstat[d].fill_ms);
+        }
     }
     for (int d = 0; d < nd; ++d)
         if (rc[d]) { ctx->err = ctx->devs[d].err; return rc[d]; }
@@ -612,7 +622,7 @@ extern "C" int age_run_staged(age_ctx *ctx)
         if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
         if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
     }
-    ctx->stats.launches += 2; ctx->stats.fill_launches += 1;
+    ctx->stats.launches += 5; ctx->stats.fill_launches += 1;
     return 0;
 }
 

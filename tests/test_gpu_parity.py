@@ -163,3 +163,17 @@ def test_batch_order_independent(eng):
     b = eng.align([jobs[i] for i in perm])
     for k, i in enumerate(perm):
         assert not diff_summary(b[k], a[i])
+
+
+def test_two_devices_same_results(eng):
+    """age_create over two GPUs shards the pairs (no collective, host gather): per-job results are identical"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from asmvar_b200 import engine
+    jobs = random_jobs(21, 96, (200, 1200), (40, 300), ["ACGT", "ACGTN"])
+    a = eng.align(jobs)
+    with engine.Engine([0, 1]) as e2:
+        b = e2.align(jobs)
+    for x, y in zip(a, b):
+        assert not diff_summary(y, x)
