@@ -164,7 +164,8 @@ struct View {
         if (lane == 0) sc.valid[plane * vwords + (i >> 5)] |= 1u << (i & 31);
         __syncwarp();
     }
-    __device__ void ensure(int plane, int s, int win, bool with_mp = false) const {
+    // (not inlined: one copy of the four compact re-sweeps per kernel, with the lane state in registers)
+    __device__ __noinline__ void ensure(int plane, int s, int win, bool with_mp = false) const {
         if (valid(with_mp ? 4 : plane, s, win)) return;
         const long long c0 = clock64();
         const TraceOut TO{sc.P[plane], sc.hot, with_mp ? sc.Mp : nullptr, 16 * half, max2};

@@ -392,7 +392,7 @@ struct TraceSmem {
 // hundred instructions.  Pass 2 is latency- and instruction-fetch-bound: a fully unrolled 32-cell body with the
 // trace code inlined overflows the instruction cache and runs several times slower.
 template <int DIR, int MODE>
-__device__ __noinline__ void sweep_window_compact(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, TraceSmem &X,
+__device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, TraceSmem &X,
                                                   const int win, const TraceOut &TO)
 {
     constexpr bool FWD = DIR > 0;
@@ -487,7 +487,7 @@ __device__ __noinline__ void sweep_window_compact(const StripCtx<DIR> &C, LaneSt
 
 // Recompute one window of one strip from its checkpoint, emitting the trace (pass 2).
 template <int DIR, int MODE>
-__device__ void sweep_window_trace(const PairTask &T, WarpRings &R, TraceSmem &X, const int lane, int s, int win, const TraceOut &TO)
+__device__ __forceinline__ void sweep_window_trace(const PairTask &T, WarpRings &R, TraceSmem &X, const int lane, int s, int win, const TraceOut &TO)
 {
     constexpr bool FWD = DIR > 0;
     const int si = FWD ? s : T.nstrips - 1 - s;
