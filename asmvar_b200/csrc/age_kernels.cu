@@ -251,6 +251,25 @@ struct View {
         tnext = __shfl_sync(0xFFFFFFFFu, code, n & 31);
         return n;
     }
+    // K7 helper.  A maxima-trace walk (plane 1 = FM stepping by -1, plane 3 = RM stepping by +1) that starts at (r, x)
+    // merges into the walk that starts at the next cell (r, x + dir) when it makes d >= 0 VERTICAL steps followed by a
+    // HORIZONTAL one and the neighbour's walk makes the same d VERTICAL steps first.  Both walks then share their
+    // endpoint, so traceBackMaxima + addBpoints of the first is a guaranteed duplicate of the second (:652-655).
+    // Evaluated for 32 consecutive start cells at once; lanes with in == false are ignored.
+    __device__ bool merges_into_next(int plane, int r, int x, int dir, bool in) const {
+        int d0 = 0, d1 = 0;
+        uint32_t c0 = T_STOP, c1 = T_STOP;
+        bool run0 = in, run1 = in;
+        for (int depth = 0; depth < 64; ++depth) {
+            ensure_lanes(plane, run0 ? r + depth * dir : -1, x);
+            ensure_lanes(plane, run1 ? r + depth * dir : -1, x + dir);
+            if (run0) { c0 = code_nc(plane, r + depth * dir, x); if (c0 == T_VERT) d0 = depth + 1; else run0 = false; }
+            if (run1) { c1 = code_nc(plane, r + depth * dir, x + dir); if (c1 == T_VERT) d1 = depth + 1; else run1 = false; }
+            if (!__any_sync(0xFFFFFFFFu, run0 || run1)) break;
+        }
+        if (!in || run0 || run1) return false;            // deeper ladders than 64 rows are walked one by one
+        return c0 == T_HORI && (d0 == 0 || d0 == d1);
+    }
     __device__ uint32_t code_at(int plane, int r, int c) const {      // warp-uniform single read
         if (interior(r, c)) ensure(plane, (r - 1) >> 8, win_of(plane, r, c));
         return code_nc(plane, r, c);
@@ -397,9 +416,9 @@ __device__ void indel_row_ranges(const View &V, int *rlo, int *rhi, int lane)
 }
 
 // K7 findInversionTDuplicationBPs (:472-538).  The reference walks every (j1, j2) pair; here the monotone
-// rows are binary-searched for the run of matching values and every H-chain of the maxima trace (whose
-// members share one traceBackMaxima endpoint, hence one addBpoints key) is tried once -- the later members
-// of a chain are guaranteed duplicates (:652-655) and change nothing.
+// rows are binary-searched for the run of matching values, and of the start cells whose traceBackMaxima walks
+// merge (View::merges_into_next: they share the endpoint, hence the addBpoints key) only the last one is walked --
+// the others are guaranteed duplicates (:652-655) and change nothing.
 __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
 {
     const int len1 = V.len1, len2 = V.len2, max2 = V.max2;
@@ -409,6 +428,7 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
     auto B = [&](int r) { return (r >= 1 && r <= len2) ? (int)((colR[r] >> sh) & 0xFFFF) : 0; };  // 2*Rmax[r][1]
     int n_add = 0;
     bool stop = false;
+    long long kc = clock64();
     for (int r = 0; r <= len2 && !stop; ++r) {                            // forward (:485-504)
         if (A(r) + B(r + 1) != max2) continue;
         if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
@@ -423,20 +443,30 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
                 // columns x in [1, len1+1] of row r+1, values non-increasing: first x with value <= tv
                 int lo = 1, hi = len1 + 2;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.R2(r + 1, mid) <= tv) hi = mid; else lo = mid + 1; }
-                int x = lo;
-                while (x <= len1 + 1 && V.R2(r + 1, x) == tv && !stop) {
-                    int xe = x;                                            // H-chain: its members share the endpoint
-                    for (;;) { uint32_t tn; const int len = V.run_len(3, r + 1, xe, 0, 1, T_HORI, tn); xe += len; if (len < 32) break; }
-                    int rg1 = xe, rg2 = r + 1, lg1 = j1, lg2 = r;
-                    walk_right(V, rg1, rg2);
-                    const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-                    if (res > 0) ++n_add;
-                    if (n_add >= MAX_BP / 2 || res < 0) stop = true;
-                    x = xe + 1;
+                if (V.R2(r + 1, lo) != tv) continue;
+                // the run of columns with value tv ends before the first x with value < tv
+                int l2 = lo, h2 = len1 + 2;
+                while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (V.R2(r + 1, mid) < tv) h2 = mid; else l2 = mid + 1; }
+                const int xhi = l2 - 1;
+                for (int xb = lo; xb <= xhi && !stop; xb += 32) {
+                    const int xi = xb + lane;
+                    const bool in = xi <= xhi;
+                    const bool mg = V.merges_into_next(3, r + 1, xi, +1, in);      // warp-collective: every lane calls it
+                    unsigned am = __ballot_sync(0xFFFFFFFFu, in && !mg);
+                    while (am && !stop) {                                  // walks that do not merge into their neighbour's
+                        const int x = xb + __ffs(am) - 1; am &= am - 1;
+                        int rg1 = x, rg2 = r + 1, lg1 = j1, lg2 = r;
+                        walk_right(V, rg1, rg2);
+                        const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+                        if (res > 0) ++n_add;
+                        if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+                    }
                 }
             }
         }
     }
+    if (lane == 0) PROF_ADD(1, clock64() - kc);
+    kc = clock64();
     n_add = 0; stop = false;
     for (int i2 = len2 + 1; i2 >= 1 && !stop; --i2) {                     // reverse (:515-534)
         if (A(i2 - 1) + B(i2) != max2) continue;
@@ -453,20 +483,29 @@ __device__ void invtdup_enumerate(const View &V, BpList &L, int lane)
                 // columns x in [0, len1] of row i2-1, values non-decreasing: last x with value <= tv
                 int lo = -1, hi = len1;
                 while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (V.F2(i2 - 1, mid) <= tv) lo = mid; else hi = mid - 1; }
-                int x = lo;
-                while (x >= 0 && V.F2(i2 - 1, x) == tv && !stop) {
-                    int xe = x;
-                    for (;;) { uint32_t tn; const int len = V.run_len(1, i2 - 1, xe, 0, -1, T_HORI, tn); xe -= len; if (len < 32) break; }
-                    int lg1 = xe, lg2 = i2 - 1, rg1 = j2, rg2 = i2;
-                    walk_left(V, lg1, lg2);
-                    const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-                    if (res > 0) ++n_add;
-                    if (n_add >= MAX_BP / 2 || res < 0) stop = true;
-                    x = xe - 1;
+                if (lo < 0 || V.F2(i2 - 1, lo) != tv) continue;
+                // the run of columns with value tv starts after the last x with value < tv
+                int l2 = -1, h2 = lo;
+                while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (V.F2(i2 - 1, mid) < tv) l2 = mid; else h2 = mid - 1; }
+                const int xlo = l2 + 1;
+                for (int xb = lo; xb >= xlo && !stop; xb -= 32) {
+                    const int xi = xb - lane;
+                    const bool in = xi >= xlo;
+                    const bool mg = V.merges_into_next(1, i2 - 1, xi, -1, in);
+                    unsigned am = __ballot_sync(0xFFFFFFFFu, in && !mg);
+                    while (am && !stop) {
+                        const int x = xb - (__ffs(am) - 1); am &= am - 1;
+                        int lg1 = x, lg2 = i2 - 1, rg1 = j2, rg2 = i2;
+                        walk_left(V, lg1, lg2);
+                        const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+                        if (res > 0) ++n_add;
+                        if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+                    }
                 }
             }
         }
     }
+    if (lane == 0) PROF_ADD(2, clock64() - kc);
 }
 
 // K11 findLeftBlocks (:752-808).  dst == nullptr: count only.  Blocks are produced last-first; a block is a maximal
@@ -520,7 +559,7 @@ __device__ P2Scratch carve_set(const PairTask &T, int set)
     sc.hot = (uint32_t *)base; base += p2_up(slots * 32 * 4);
     sc.Mp = T.k7 ? (uint32_t *)base : nullptr; base += T.k7 ? p2_up(slots * W * 2 * 32 * 16) : 0;
     sc.vwords = (int)p2_vwords(nwt);
-    sc.valid = (uint32_t *)base; base += p2_up((size_t)6 * sc.vwords * 4);
+    sc.valid = (uint32_t *)base; base += p2_up((size_t)7 * sc.vwords * 4);
     sc.rowrange = (int32_t *)base;
     return sc;
 }
@@ -572,9 +611,41 @@ age_select_kernel(Pass2Params prm)
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h);
-            for (int i = lane; i < 6 * sc.vwords; i += 32) sc.valid[i] = 0;
+            for (int i = lane; i < 7 * sc.vwords; i += 32) sc.valid[i] = 0;
             __syncwarp();
-            if (T.flag[h] != F_INDEL || max2[h] == 0) continue;
+            if (T.flag[h] != F_INDEL) {
+                // K7: the rows that tie at the maximum are scanned along their whole length (:485-534): queue every
+                // window of their strips -- the forward maxima trace of row r, the reverse one (with the maxima
+                // themselves) of row r+1
+                uint32_t *qf = sc.valid + 5 * sc.vwords, *qr = sc.valid + 6 * sc.vwords;
+                const int sh = 16 * h;
+                for (int rb = 0; rb <= len2; rb += 32) {
+                    const int r = rb + lane;
+                    bool tie = false;
+                    if (r <= len2) {
+                        const int a = r >= 1 ? (int)((T.Dlast[r] >> sh) & 0xFFFF) : 0, b = r + 1 <= len2 ? (int)((T.Rfirst[r + 1] >> sh) & 0xFFFF) : 0;
+                        tie = a + b == max2[h];
+                    }
+                    unsigned m = __ballot_sync(0xFFFFFFFFu, tie);
+                    while (m) {
+                        const int rr = rb + __ffs(m) - 1; m &= m - 1;
+                        for (int pass = 0; pass < 2; ++pass) {
+                            const int row = pass == 0 ? rr : rr + 1;                 // 1-based row whose strip is needed
+                            if (row < 1 || row > len2) continue;
+                            const int s = (row - 1) >> 8;
+                            uint32_t *qd = pass == 0 ? qf : qr;
+                            for (int w2 = lane; w2 < T.nwin; w2 += 32) {
+                                const int i = s * T.nwin + w2;
+                                if (atomicOr(&qd[i >> 5], 1u << (i & 31)) & (1u << (i & 31))) continue;
+                                const int at = atomicAdd(prm.queue_n, 1);
+                                if (at < prm.queue_cap) prm.queue[at] = make_uint2((uint32_t)item, (uint32_t)(h | ((pass == 0 ? 1 : 5) << 1) | (s << 4) | (w2 << 16)));
+                            }
+                        }
+                    }
+                }
+                continue;
+            }
+            if (max2[h] == 0) continue;
             // every reverse window with a tile at the maximum, and the forward windows over the same cells
             uint32_t *queued = sc.valid + 5 * sc.vwords;
             for (int wi = 0; wi < nwt; ++wi) {
@@ -617,13 +688,18 @@ age_presweep_kernel(Pass2Params prm)
         const PairTask &T = prm.pairs[q.x];
         const int h = q.y & 1, plane = (q.y >> 1) & 7, s = (q.y >> 4) & 0xFFF, win = q.y >> 16;
         const P2Scratch sc = carve_set(T, T.select ? 0 : h);
-        const TraceOut TO{sc.P[plane], sc.hot, nullptr, 16 * h, prm.hdr[q.x].max2[h]};
-        if (plane == 1) sweep_window_trace<+1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
-        else            sweep_window_trace<-1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
+        const bool with_mp = plane == 5;                     // reverse maxima trace + the maxima themselves (K7)
+        const int pl = plane == 1 ? 1 : 3;
+        const TraceOut TO{sc.P[pl], sc.hot, with_mp ? sc.Mp : nullptr, 16 * h, prm.hdr[q.x].max2[h]};
+        if (pl == 1) sweep_window_trace<+1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
+        else         sweep_window_trace<-1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
         __threadfence();
         __syncwarp();
         const int i = s * T.nwin + win;
-        if (lane == 0) atomicOr(&sc.valid[plane * sc.vwords + (i >> 5)], 1u << (i & 31));
+        if (lane == 0) {
+            atomicOr(&sc.valid[pl * sc.vwords + (i >> 5)], 1u << (i & 31));
+            if (with_mp) atomicOr(&sc.valid[4 * sc.vwords + (i >> 5)], 1u << (i & 31));
+        }
     }
 }
 
@@ -730,7 +806,7 @@ void launch_pass2(const Pass2Params &p, cudaStream_t st)
         cudaMemcpyFromSymbol(z, g_prof, sizeof(z));
         cudaMemcpy(&qn, p.queue_n, sizeof(int), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[p2 prof] pre-swept windows %d, slowest pair index %llu\n", qn, z[0] & 0xFFFFFF); z[0] = (z[0] >> 24) << 10;
-        fprintf(stderr, "[p2 prof] pairs %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | on-demand re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
+                fprintf(stderr, "[p2 prof] pairs %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | on-demand re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
                 p.n_pairs, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[6], z[5] / 1e6, z[7]);
     }
 }

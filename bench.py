@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--batch", type=int, default=2368, help="candidates per step per GPU (2368 = 148 SMs x 16 resident warps)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default, the configuration the metric is quoted on); c4 = -inv 20 kb x 4 kb; c5 = 50 kb x 10 kb -indel -both "
+                         "(extra measurements, not the headline)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
@@ -184,8 +187,18 @@ def main():
         dist.barrier()
     from asmvar_b200 import capi, engine, synth
 
-    cands = synth.indel_candidates(args.batch, seed=1002 + rank)
-    jobs = make_jobs(cands, capi.INDEL_FLAG)
+    global WORKLOAD
+    if args.workload == "c2":
+        cands = synth.indel_candidates(args.batch, seed=1002 + rank)
+        jobs = make_jobs(cands, capi.INDEL_FLAG)
+    elif args.workload == "c5":
+        WORKLOAD = "C5 synthetic long deletions: 50 kb windows, 10 kb contigs, -indel -both, 1/-1/-10/-1"
+        cands = synth.long_sv_candidates(args.batch, seed=1005 + rank)
+        jobs = make_jobs(cands, capi.INDEL_FLAG)
+    else:
+        WORKLOAD = "C4 synthetic inversions: 20 kb windows, 2 x 2 kb flanks, -inv, 1/-1/-10/-1"
+        cands = synth.inversion_candidates(args.batch, seed=1004 + rank)
+        jobs = [(w, q, capi.INVERSION_FLAG, *SCORING, -1) for w, q in cands]      # INVL + auxiliary INVR aligner per candidate
     cu = cell_updates(cands)
     eng = engine.Engine([local])
     arr, keep, n = eng.make_jobs(jobs)
@@ -265,7 +278,7 @@ def main():
                                    "frac": ach_i / peak.value, "kernel": "age_sweep_kernel",
                                    "note": "achieved = 4 algorithmic s16x2/logic instructions per cell update x cell updates / sweep-kernel time; "
                                            "peak = age_int16_peak microbenchmark on this GPU (independent chains of the same instruction mix)"}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "c2":
             try:
                 cores = os.cpu_count() or 1
                 sample = cands[: min(len(cands), max(cores, 8) * 2)]
