@@ -114,7 +114,7 @@ __host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t 
 
 // launchers (age_kernels.cu)
 void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st);
-void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cudaStream_t st);
+void launch_sweeps(const PairTask *d_pairs, int n_pairs, int max_strips, int32_t *d_counter, cudaStream_t st);
 void launch_pass2(const Pass2Params &p, cudaStream_t st);
 
 } // namespace age

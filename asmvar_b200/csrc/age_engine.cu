@@ -336,7 +336,9 @@ bool run_on_device(age_ctx *, Device &dev)
     OutLayout L = out_layout(dev, dev.outbuf.ptr);
     CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
     CK(cudaEventRecord(dev.ev[2], dev.st));
-    launch_sweeps((const PairTask *)dev.in.ptr, np, L.counters + 0, dev.st);
+    int max_strips = 1;
+    for (const PairTask &t : dev.tasks) max_strips = std::max(max_strips, (int)t.nstrips);
+    launch_sweeps((const PairTask *)dev.in.ptr, np, max_strips, L.counters + 0, dev.st);
     CK(cudaEventRecord(dev.ev[3], dev.st));
     launch_pass2(pass2_params(dev, L), dev.st);
     CK(cudaEventRecord(dev.ev[4], dev.st));

@@ -121,16 +121,59 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
     }
 }
 
-void launch_sweeps(const PairTask *d_pairs, int n_pairs, int32_t *d_counter, cudaStream_t st)
+// Long alignments / small batches: the NW warps of a CTA share one pair and run its strips as a pipeline
+// (warp w owns strips w, w + NW, ...; strip si trails strip si-1 by 32+ steps through the boundary rows in global memory).
+constexpr int MAX_STRIPS_LONG = 128;
+
+__global__ void __launch_bounds__(512, 1)
+age_sweep_long_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SweepSmem *sm = reinterpret_cast<SweepSmem *>(smem_raw);
+    __shared__ int prog[MAX_STRIPS_LONG];
+    __shared__ int s_item;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
+        for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog[i] = 0;
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_pairs) break;
+        const PairTask &T = pairs[item];
+        sweep_pair_fast<+1>(T, sm[w].rings, sm[w].dstage, lane, w, nw, prog);
+        __threadfence();
+        __syncthreads();
+        for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog[i] = 0;
+        __syncthreads();
+        sweep_pair_fast<-1>(T, sm[w].rings, sm[w].dstage, lane, w, nw, prog);
+        cp_async_wait_all();
+    }
+}
+
+void launch_sweeps(const PairTask *d_pairs, int n_pairs, int max_strips, int32_t *d_counter, cudaStream_t st)
 {
     if (n_pairs <= 0) return;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st);
+    // one warp per pair fills the GPU from ~sms * 16 pairs on; below that, share each pair among up to 16 warps
+    int nw = 1;
+    static const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;
+    while (nw < 16 && nw * 2 <= max_strips && n_pairs * nw * 2 <= sms * 16) nw *= 2;
+    if (force_nw) nw = force_nw;
+    if (max_strips > MAX_STRIPS_LONG) nw = 1;
+    if (nw > 1) {
+        const int smem = nw * (int)sizeof(SweepSmem);
+        cudaFuncSetAttribute(age_sweep_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        const int per_sm = std::max(1, std::min(16 / nw, 4));
+        age_sweep_long_kernel<<<std::min(n_pairs, sms * per_sm), nw * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
+        return;
+    }
     int blocks = (n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS;
     static const int occ = getenv("AGE_OCC") ? atoi(getenv("AGE_OCC")) : 8;
     if (blocks > sms * occ) blocks = sms * occ;              // persistent: the work counter feeds the warps
-    cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st);
     const int smem = SWEEP_WARPS * (int)sizeof(SweepSmem);
     cudaFuncSetAttribute(age_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     age_sweep_kernel<<<blocks, SWEEP_WARPS * 32, smem, st>>>(d_pairs, n_pairs, d_counter);

@@ -95,6 +95,7 @@ template <int DIR> struct StripCtx {
     uint32_t *tilemax;
     uint32_t *ckpt;
     bool first;                             // no boundary input: the strip starts at the matrix border
+    volatile int *prog_out;                 // multi-warp sweep: blocks of this strip's boundary row flushed so far (or null)
 
     __device__ __forceinline__ void init(const PairTask &T, int s_, int si, int lane_)
     {
@@ -116,6 +117,7 @@ template <int DIR> struct StripCtx {
         Dtail4 = (FWD && p == 31 && si + 1 == T.nstrips) ? reinterpret_cast<uint4 *>(T.Dtail) : nullptr;
         tilemax = T.tilemax;
         ckpt = FWD ? T.ckpt_f : T.ckpt_r;
+        prog_out = nullptr;
     }
 };
 
@@ -330,6 +332,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) C.bout[(size_t)pl * (nb + 1) + bb] = R.out[pl][lane];
                 }
+                if (C.prog_out) { __threadfence(); __syncwarp(); if (lane == 0) *C.prog_out = b31; }   // the next strip's warp may read them
                 __syncwarp();
             }
         }
@@ -346,26 +349,38 @@ __device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneSta
     else                        sweep_window<DIR, MODE, true>(C, S, R, DS, win, t0, t1, best, TO);
 }
 
-// The main sweep of one pair in one direction: all strips, all windows, checkpoints and tile maxima.
+// The main sweep of one pair in one direction: checkpoints, tile maxima, all windows of the strips si0, si0 + stride, ...
+// (in sweep order).  With stride > 1 several warps of one CTA share the pair (long alignments): strip si starts as soon
+// as the warp of strip si-1 has flushed the first boundary blocks and then runs 32+ steps behind it; `prog` (shared
+// memory, one counter per strip, zeroed by the caller) carries the number of flushed blocks.
 template <int DIR>
-__device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, const int lane)
+__device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, const int lane,
+                                const int si0 = 0, const int stride = 1, volatile int *prog = nullptr)
 {
     constexpr bool FWD = DIR > 0;
     const TraceOut none{nullptr, nullptr, nullptr, 0, 0};
-    for (int si = 0; si < T.nstrips; ++si) {
+    for (int si = si0; si < T.nstrips; si += stride) {
         const int s = FWD ? si : T.nstrips - 1 - si;
         StripCtx<DIR> C;
         C.init(T, s, si, lane);
+        if (prog) C.prog_out = prog + si;
+        volatile int *prog_in = (prog && !C.first) ? prog + si - 1 : nullptr;
+        auto wait_blocks = [&](int win) {       // boundary blocks of window `win` must have been flushed by the producer
+            if (!prog_in) return;
+            const int need = min(CKS * win + CKS, C.nb);
+            while (*prog_in < need) __nanosleep(200);
+            __threadfence();
+        };
         LaneState S;
         state_init(S, C.gborder);
         if (C.first) ring_fill_border(R, lane, C.gborder);
-        else ring_prefetch(C, R, 0, 0);
+        else { wait_blocks(0); ring_prefetch(C, R, 0, 0); }
         uint32_t best = 0;
         if (!FWD) dstage_fetch(C, DS, 1);
         for (int win = 0; win < C.nwin; ++win) {
             cp_async_wait_all();
             __syncwarp();
-            if (!C.first && win + 1 < C.nwin) ring_prefetch(C, R, win + 1, (win + 1) & 1);
+            if (!C.first && win + 1 < C.nwin) { wait_blocks(win + 1); ring_prefetch(C, R, win + 1, (win + 1) & 1); }
             state_save(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
             sweep_window_any<DIR, MODE_FAST>(C, S, R, DS, win, best, none);
             if (!FWD) { C.tilemax[(size_t)(s * C.nwin + win) * 32 + lane] = best; best = 0; }
