@@ -86,7 +86,7 @@ struct P2Scratch {
     uint2 *P[4];                         // 2-bit code planes FS, FM, RS, RM: [slots][32], 16 bits per block column
     uint32_t *hot;                       // [slots][32]: bit 8w+k = reverse cell holds Fmax + Rmax == max (with RM)
     uint32_t *Mp;                        // reverse maxima, same layout as D but unshifted (K7 only)
-    uint32_t *valid;                     // [7][vwords] window bits: the four planes, Mp, queued for the pre-sweep (fwd / rev)
+    uint32_t *valid;                     // [9][vwords] window bits: the four planes, Mp, queued for the pre-sweeps (FM, RM, FS, RS)
     int32_t *rowrange;                   // [2][len2 + 2]
     int32_t vwords;
 };
@@ -100,7 +100,7 @@ struct Pass2Params {
     PairHdr *hdr;
     Block *pool; int32_t pool_cap; int32_t *pool_used;
     uint2 *queue; int32_t queue_cap; int32_t *queue_n;   // pre-sweep work items {pair, half | plane << 1 | strip << 4 | window << 16}
-    int32_t *next;                       // work counters: [0] select, [1] pre-sweep, [2] pass 2
+    int32_t *next;                       // work counters: select, pre-sweep 1, enumerate, blocks, pre-sweep 2
 };
 
 // layout of one plane set (shared by host and device)
@@ -109,7 +109,7 @@ __host__ __device__ inline size_t p2_vwords(size_t nwt) { return (nwt + 31) / 32
 __host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t len2, int k7)
 {
     return 4 * p2_up(slots * 32 * 8) + p2_up(slots * 32 * 4) + (k7 ? p2_up(slots * W * 2 * 32 * 16) : 0) +
-           p2_up(7 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4);
+           p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4);
 }
 
 // launchers (age_kernels.cu)

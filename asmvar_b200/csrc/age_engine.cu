@@ -324,8 +324,8 @@ Pass2Params pass2_params(Device &dev, const OutLayout &L)
     Pass2Params p{};
     p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = (int)dev.tasks.size(); p.outs = L.outs;
     p.hdr = (PairHdr *)dev.aux.ptr;
-    p.queue = (uint2 *)(dev.aux.ptr + align_up(dev.tasks.size() * sizeof(PairHdr), 256)); p.queue_cap = dev.queue_cap; p.queue_n = L.counters + 8;
-    p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 4;
+    p.queue = (uint2 *)(dev.aux.ptr + align_up(dev.tasks.size() * sizeof(PairHdr), 256)); p.queue_cap = dev.queue_cap; p.queue_n = L.counters + 12;
+    p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 4;   // next: 8 ints
     return p;
 }
 
@@ -555,7 +555,7 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
             ok = ok && fetch_from_device(ctx, dev);
             if (hprof) tp[2] += wall_ms() - t0;
             if (!ok) { rc[0] = AGE_ERR_CUDA; break; }
-            ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 5; ctx->stats.fill_launches += 1;
+            ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 8; ctx->stats.fill_launches += 1;
             add_timing(ctx, dev);
         }
     } else {
@@ -563,7 +563,7 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
         for (int d = 0; d < nd; ++d) th.emplace_back(worker, d);
         for (auto &t : th) t.join();
         for (int d = 0; d < nd; ++d) {      // devices run concurrently: report the slowest one
-            ctx->stats.launches += 5 * sub[d].size(); ctx->stats.fill_launches += sub[d].size();
+            ctx->stats.launches += 8 * sub[d].size(); ctx->stats.fill_launches += sub[d].size();
             ctx->stats.h2d_bytes += dstat[d].h2d_bytes;
             ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, dstat[d].kernel_ms);
             ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, dstat[d].fill_ms);
@@ -624,7 +624,7 @@ extern "C" int age_run_staged(age_ctx *ctx)
         if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
         if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
     }
-    ctx->stats.launches += 5; ctx->stats.fill_launches += 1;
+    ctx->stats.launches += 8; ctx->stats.fill_launches += 1;
     return 0;
 }
 

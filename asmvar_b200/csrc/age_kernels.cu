@@ -10,7 +10,7 @@
 // age_sweep_kernel   the hot kernel: per pair, the forward sweep streams the shifted running maxima D to HBM,
 //                    the reverse sweep folds D back in and leaves one split maximum per (lane, window) tile.
 //                    Neither sweep keeps a trace; both leave a 5 KB lane-state checkpoint per window.
-// age_pass2_kernel   per pair, one warp: split maximum, -both / -inv winner selection, then for the winner only
+// age_enum_kernel /  per pair, one warp: split maximum, -both / -inv winner selection, then for the winner only
 //                    breakpoint enumeration and traceback.  Every trace bit it looks at comes from re-running
 //                    the sweep over the one window that holds it (MODE_TRACE), from that window's checkpoint.
 #include "age_sweep.cuh"
@@ -602,7 +602,7 @@ __device__ P2Scratch carve_set(const PairTask &T, int set)
     sc.hot = (uint32_t *)base; base += p2_up(slots * 32 * 4);
     sc.Mp = T.k7 ? (uint32_t *)base : nullptr; base += T.k7 ? p2_up(slots * W * 2 * 32 * 16) : 0;
     sc.vwords = (int)p2_vwords(nwt);
-    sc.valid = (uint32_t *)base; base += p2_up((size_t)7 * sc.vwords * 4);
+    sc.valid = (uint32_t *)base; base += p2_up((size_t)9 * sc.vwords * 4);
     sc.rowrange = (int32_t *)base;
     return sc;
 }
@@ -654,7 +654,7 @@ age_select_kernel(Pass2Params prm)
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h);
-            for (int i = lane; i < 7 * sc.vwords; i += 32) sc.valid[i] = 0;
+            for (int i = lane; i < 9 * sc.vwords; i += 32) sc.valid[i] = 0;
             __syncwarp();
             if (T.flag[h] != F_INDEL) {
                 // K7: the rows that tie at the maximum are scanned along their whole length (:485-534): queue every
@@ -716,7 +716,7 @@ age_select_kernel(Pass2Params prm)
 constexpr int PRE_WARPS = 4;
 
 __global__ void __launch_bounds__(PRE_WARPS * 32)
-age_presweep_kernel(Pass2Params prm)
+age_presweep_kernel(Pass2Params prm, int round)
 {
     __shared__ WarpRings rings[PRE_WARPS];
     __shared__ TraceSmem tsm[PRE_WARPS];
@@ -724,7 +724,7 @@ age_presweep_kernel(Pass2Params prm)
     const int n = min(*prm.queue_n, prm.queue_cap);
     for (;;) {
         int item = 0;
-        if (lane == 0) item = atomicAdd(prm.next + 1, 1);
+        if (lane == 0) item = atomicAdd(prm.next + (round ? 4 : 1), 1);
         item = __shfl_sync(0xFFFFFFFFu, item, 0);
         if (item >= n) break;
         const uint2 q = prm.queue[item];
@@ -732,10 +732,14 @@ age_presweep_kernel(Pass2Params prm)
         const int h = q.y & 1, plane = (q.y >> 1) & 7, s = (q.y >> 4) & 0xFFF, win = q.y >> 16;
         const P2Scratch sc = carve_set(T, T.select ? 0 : h);
         const bool with_mp = plane == 5;                     // reverse maxima trace + the maxima themselves (K7)
-        const int pl = plane == 1 ? 1 : 3;
+        const int pl = plane == 5 ? 3 : plane;
         const TraceOut TO{sc.P[pl], sc.hot, with_mp ? sc.Mp : nullptr, 16 * h, prm.hdr[q.x].max2[h]};
-        if (pl == 1) sweep_window_trace<+1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
-        else         sweep_window_trace<-1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO);
+        switch (pl) {
+        case 0:  sweep_window_trace<+1, MODE_TRACE_S>(T, rings[w], tsm[w], lane, s, win, TO); break;
+        case 1:  sweep_window_trace<+1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO); break;
+        case 2:  sweep_window_trace<-1, MODE_TRACE_S>(T, rings[w], tsm[w], lane, s, win, TO); break;
+        default: sweep_window_trace<-1, MODE_TRACE_M>(T, rings[w], tsm[w], lane, s, win, TO); break;
+        }
         __threadfence();
         __syncwarp();
         const int i = s * T.nwin + win;
@@ -746,8 +750,32 @@ age_presweep_kernel(Pass2Params prm)
     }
 }
 
+// Queue the windows a traceback from (r0, c0) will probably visit: the path runs along the diagonal (dir = -1: up-left
+// through the forward scores trace, plane 0; dir = +1: down-right through the reverse one, plane 2) for about as many
+// steps as the fragment scores.  A wrong guess costs nothing but time: windows the walk needs and that were not
+// pre-swept are re-swept on demand.
+__device__ void queue_path(const Pass2Params &prm, const View &V, int item, int plane, int r0, int c0, int dir, int steps)
+{
+    uint32_t *queued = V.sc.valid + (plane == 0 ? 7 : 8) * V.vwords;
+    steps = min(steps, dir < 0 ? min(r0, c0) : min(V.len2 - r0, V.len1 - c0) + 1);
+    for (int i0 = 0; i0 < steps; i0 += 32 * RPT) {
+        const int i = i0 + V.lane * RPT;
+        if (i >= steps) continue;
+        const int r = r0 + dir * i;
+        for (int dc = -12; dc <= 12; dc += 12) {               // gaps shift the path off the diagonal by a few columns
+            const int c = c0 + dir * i + dc;
+            if (!V.interior(r, c)) continue;
+            const int s = (r - 1) >> 8, win = V.win_of(plane, r, c), bit = s * V.nwin + win;
+            if (atomicOr(&queued[bit >> 5], 1u << (bit & 31)) & (1u << (bit & 31))) continue;
+            const int at = atomicAdd(prm.queue_n, 1);
+            if (at < prm.queue_cap) prm.queue[at] = make_uint2((uint32_t)item, (uint32_t)(V.half | (plane << 1) | (s << 4) | (win << 16)));
+        }
+    }
+}
+
+// ---- enumerate: breakpoints of the selected aligner(s) (K5-K9), then the work list of the traceback windows ----------
 __global__ void __launch_bounds__(P2_WARPS * 32, P2_OCC)
-age_pass2_kernel(Pass2Params prm)
+age_enum_kernel(Pass2Params prm)
 {
     __shared__ int bp_s[P2_WARPS][MAX_BP][4];
     __shared__ WarpRings rings[P2_WARPS];
@@ -761,14 +789,12 @@ age_pass2_kernel(Pass2Params prm)
         const PairTask &T = prm.pairs[item];
         const int len1 = T.len1, len2 = T.len2;
         const PairHdr hd = prm.hdr[item];
-        const int max2[2] = {hd.max2[0], hd.max2[1]};
-        const bool need[2] = {hd.need[0] != 0, hd.need[1] != 0};
         long long pc = clock64();
         const long long pair_c0 = pc;
         for (int h = 0; h < 2; ++h) {
-            if (!need[h]) continue;
+            if (!hd.need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h);
-            const View V{&T, sc, &rings[w], &tsm[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, max2[h], sc.vwords};
+            const View V{&T, sc, &rings[w], &tsm[w], len1, len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
             __syncwarp();
@@ -782,17 +808,54 @@ age_pass2_kernel(Pass2Params prm)
                 if (lane == 0) PROF_ADD(2, clock64() - pc);
             } else invtdup_enumerate(V, L, lane);
             __syncwarp();
-            // ---- K10: blocks of bpoint 0 and of the alternative shown by printAlignment (:287-306) ----
-            // (the walks are executed by the whole warp: a trace window that is not resident is re-swept by all lanes)
             if (lane == 0) {
                 O.status = 0;
-                O.score = max2[h] >> 1;
+                O.score = hd.max2[h] >> 1;
                 O.n_bp = L.n;
-                for (int i = 0; i < L.n; ++i)
-                    for (int k = 0; k < 4; ++k) O.bp[i][k] = L.bp[i][k];
             }
+            for (int i = lane; i < L.n * 4; i += 32) O.bp[i >> 2][i & 3] = L.bp[i >> 2][i & 3];
+            // the tracebacks of bpoint 0 and of the alternative printAlignment shows (the last one, normally)
+            for (int which = 0; which < 2; ++which) {
+                const int idx = which == 0 ? 0 : L.n - 1;
+                if (which == 1 && idx < 1) break;
+                const int lg1 = L.bp[idx][0], lg2 = L.bp[idx][1], rg1 = L.bp[idx][2], rg2 = L.bp[idx][3];
+                const int fl = V.F2(lg2, lg1) >> 1, fr = max((hd.max2[h] >> 1) - fl, 0);     // scores of the two fragments
+                queue_path(prm, V, item, 0, lg2, lg1, -1, fl + fl / 4 + 64);
+                queue_path(prm, V, item, 2, rg2, rg1, +1, fr + fr / 4 + 64);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) atomicMax(&g_prof[0], ((unsigned long long)(clock64() - pair_c0) >> 10 << 24) | (unsigned long long)item);
+    }
+}
+
+// ---- blocks: K10-K12 tracebacks of bpoint 0 and of the alternative shown by printAlignment (:287-306) ---------------------
+// (the walks are executed by the whole warp: a trace window that is not resident is re-swept by all lanes)
+__global__ void __launch_bounds__(P2_WARPS * 32, P2_OCC)
+age_blocks_kernel(Pass2Params prm)
+{
+    __shared__ int bp_s[P2_WARPS][MAX_BP][4];
+    __shared__ WarpRings rings[P2_WARPS];
+    __shared__ TraceSmem tsm[P2_WARPS];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(prm.next + 3, 1);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= prm.n_pairs) break;
+        const PairTask &T = prm.pairs[item];
+        const PairHdr hd = prm.hdr[item];
+        for (int h = 0; h < 2; ++h) {
+            if (!hd.need[h]) continue;
+            const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+            const View V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
+            AlignerOut &O = prm.outs[T.out[h]];
+            BpList L{O.n_bp, bp_s[w]};
+            __syncwarp();
+            for (int i = lane; i < L.n * 4; i += 32) L.bp[i >> 2][i & 3] = O.bp[i >> 2][i & 3];
+            __syncwarp();
             int alt = -1;
-            pc = clock64();
+            const long long pc = clock64();
             for (int which = 0; which < 2; ++which) {
                 int idx = 0, nl = 0, nr = 0;
                 if (which == 0) {
@@ -824,7 +887,6 @@ age_pass2_kernel(Pass2Params prm)
             if (lane == 0) { O.alt_index = alt; PROF_ADD(3, clock64() - pc); }
             __syncwarp();
         }
-        if (lane == 0) atomicMax(&g_prof[0], ((unsigned long long)(clock64() - pair_c0) >> 10 << 24) | (unsigned long long)item);
     }
 }
 
@@ -836,12 +898,15 @@ void launch_pass2(const Pass2Params &p, cudaStream_t st)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     static const bool prof = getenv("AGE_P2_PROF") != nullptr;
     if (prof) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(g_prof, z, sizeof(z)); }
-    cudaMemsetAsync(p.next, 0, 4 * sizeof(int32_t), st);
+    cudaMemsetAsync(p.next, 0, 8 * sizeof(int32_t), st);
     cudaMemsetAsync(p.queue_n, 0, sizeof(int32_t), st);
     const int nb = (p.n_pairs + 3) / 4;
     age_select_kernel<<<std::min(nb, sms * 8), SEL_WARPS * 32, 0, st>>>(p);
-    age_presweep_kernel<<<sms * 4, PRE_WARPS * 32, 0, st>>>(p);
-    age_pass2_kernel<<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
+    age_presweep_kernel<<<sms * 4, PRE_WARPS * 32, 0, st>>>(p, 0);      // windows along the split row / column (maxima trace)
+    cudaMemsetAsync(p.queue_n, 0, sizeof(int32_t), st);
+    age_enum_kernel<<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
+    age_presweep_kernel<<<sms * 4, PRE_WARPS * 32, 0, st>>>(p, 1);      // windows along the traceback paths (scores trace)
+    age_blocks_kernel<<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
     if (prof) {
         unsigned long long z[8];
         int qn = 0;

@@ -34,7 +34,7 @@ sys.path.insert(0, str(ROOT))
 
 SCORING = (1, -1, -10, -1)          # AgeOption.h:25-28 (AsmvarDetect defaults) = Test2/Run.sh
 ALG_BYTES_PER_CELL_UPDATE = 2.5     # indel = 5 B per matrix cell = 2.5 B per cell update
-KERNELS_PER_STEP = 5                # age_pack, age_sweep, age_select, age_presweep, age_pass2
+KERNELS_PER_STEP = 8                # age_pack, age_sweep, age_select, age_presweep x2, age_enum, age_blocks (+ the pack of the stage call)
 # s16x2 / logic instructions of the recurrence per cell pair: VIMNMX, PRMT, VIADDMNMX, LOP3, VIADD,
 # LOP3, VIMNMX3 in both sweeps, + VIADD, VIMNMX.U16x2 for the split sum in the reverse sweep  => (7 + 9) / 2 per pair-cell
 # visit, and a pair-cell visit is two cell updates
@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=2368, help="candidates per step per GPU (2368 = 148 SMs x 16 resident warps)")
+    ap.add_argument("--batch", type=int, default=3552, help="candidates per step per GPU (3552 = 1.5 pairs per resident warp: 148 SMs x 16 warps; the longest-first deal needs more pairs than warps to balance)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
