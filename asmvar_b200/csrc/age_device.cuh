@@ -88,6 +88,7 @@ struct P2Scratch {
     uint32_t *Mp;                        // reverse maxima, same layout as D but unshifted (K7 only)
     uint32_t *valid;                     // [9][vwords] window bits: the four planes, Mp, queued for the pre-sweeps (FM, RM, FS, RS)
     int32_t *rowrange;                   // [2][len2 + 2]
+    int32_t *hotlist;                    // [1 + nwt] number and indices (strip * nwin + window) of the reverse windows at the maximum
     int32_t vwords;
 };
 
@@ -109,7 +110,7 @@ __host__ __device__ inline size_t p2_vwords(size_t nwt) { return (nwt + 31) / 32
 __host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t len2, int k7)
 {
     return 4 * p2_up(slots * 32 * 8) + p2_up(slots * 32 * 4) + (k7 ? p2_up(slots * W * 2 * 32 * 16) : 0) +
-           p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4);
+           p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4) + p2_up((nwt + 1) * 4);
 }
 
 // launchers (age_kernels.cu)

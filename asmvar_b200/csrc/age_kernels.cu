@@ -220,7 +220,7 @@ struct View {
         }
         set_valid(plane, s, win);
         if (with_mp) set_valid(4, s, win);
-        if (lane == 0) { PROF_ADD(4 + (plane >> 1), clock64() - c0); PROF_ADD(6 + (plane >> 1), 1); }
+        if (lane == 0) PROF_ADD(4 + (plane >> 1), clock64() - c0);
     }
     __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)
         for (int win = 0; win < nwin; ++win) ensure(3, s, win, true);
@@ -425,25 +425,41 @@ __device__ void indel_row_ranges(const View &V, int *rlo, int *rhi, int lane)
         __syncwarp();
         return;
     }
-    const int nwt = T.nstrips * T.nwin;
-    for (int wi = 0; wi < nwt; ++wi) {
-        const bool hot = (int)((T.tilemax[(size_t)wi * 32 + lane] >> (16 * V.half)) & 0xFFFF) == max2;
-        if (!__any_sync(0xFFFFFFFFu, hot)) continue;
+    const int nhot = V.sc.hotlist[0];                                 // written by the select kernel
+    for (int hi = 0; hi < nhot; ++hi) {
+        const int wi = V.sc.hotlist[1 + hi];
         const int s = wi / T.nwin, win = wi % T.nwin;
         V.ensure(3, s, win);
-        const int t1 = min(CKS * win + CKS, T.nsteps);
-        for (int t = CKS * win + 1; t <= t1; ++t) {
-            const int bq = t - 31 + lane;                             // logical reverse block of this lane
-            if (bq < 1 || bq > nb) continue;
-            uint32_t hw = V.sc.hot[((size_t)s * T.nsteps + (t - 1)) * 32 + lane];
-            while (hw) {
-                const int bit = __ffs(hw) - 1; hw &= hw - 1;
-                const int w = bit >> 3, k = bit & 7;
-                const int r = s * STRIP + lane * RPT + k + 1;         // reverse cell (r, c)
-                const int c = W * (nb + 1 - bq) - w;
-                if (r > len2 || c > len1) continue;                   // padding
-                atomicMin(&rlo[r - 1], c - 1); atomicMax(&rhi[r - 1], c - 1);
+        const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, T.nsteps);
+        uint32_t hw[CKS];
+#pragma unroll
+        for (int i = 0; i < CKS; ++i) {                               // the lane's hot words of all steps of the window, in flight together
+            const int t = t0 + i, bq = t - 31 + lane;                 // logical reverse block of this lane in step t
+            hw[i] = (t <= t1 && bq >= 1 && bq <= nb) ? __ldcg(V.sc.hot + ((size_t)s * T.nsteps + (t - 1)) * 32 + lane) : 0u;
+        }
+        // the hot cells of a lane lie in its own 8 rows: column ranges are gathered in registers, no atomics
+        int lo8[RPT], hi8[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) { lo8[k] = 0x7FFFFFFF; hi8[k] = -1; }
+#pragma unroll
+        for (int i = 0; i < CKS; ++i) {
+            const uint32_t x = hw[i];
+            if (x == 0) continue;
+            const int cb = W * (nb + 1 - (t0 + i - 31 + lane));       // reverse cell column of block column w is cb - w
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int c = cb - w;
+                if (c > len1) continue;                               // padding
+                const uint32_t byte = (x >> (8 * w)) & 0xFFu;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k)
+                    if ((byte >> k) & 1u) { lo8[k] = min(lo8[k], c - 1); hi8[k] = max(hi8[k], c - 1); }
             }
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = s * STRIP + lane * RPT + k + 1;             // reverse cell row; K6 row r - 1
+            if (hi8[k] >= 0 && r <= len2) { rlo[r - 1] = min(rlo[r - 1], lo8[k]); rhi[r - 1] = max(rhi[r - 1], hi8[k]); }
         }
     }
     __syncwarp();
@@ -603,7 +619,8 @@ __device__ P2Scratch carve_set(const PairTask &T, int set)
     sc.Mp = T.k7 ? (uint32_t *)base : nullptr; base += T.k7 ? p2_up(slots * W * 2 * 32 * 16) : 0;
     sc.vwords = (int)p2_vwords(nwt);
     sc.valid = (uint32_t *)base; base += p2_up((size_t)9 * sc.vwords * 4);
-    sc.rowrange = (int32_t *)base;
+    sc.rowrange = (int32_t *)base; base += p2_up(2 * ((size_t)T.len2 + 2) * 4);
+    sc.hotlist = (int32_t *)base;
     return sc;
 }
 
@@ -691,9 +708,12 @@ age_select_kernel(Pass2Params prm)
             if (max2[h] == 0) continue;
             // every reverse window with a tile at the maximum, and the forward windows over the same cells
             uint32_t *queued = sc.valid + 5 * sc.vwords;
+            int nhot = 0;
             for (int wi = 0; wi < nwt; ++wi) {
                 const bool hot = (int)((T.tilemax[(size_t)wi * 32 + lane] >> (16 * h)) & 0xFFFF) == max2[h];
                 if (!__any_sync(0xFFFFFFFFu, hot)) continue;
+                if (lane == 0) sc.hotlist[1 + nhot] = wi;
+                ++nhot;
                 if (lane >= 3) continue;
                 const int s = wi / T.nwin, win = wi % T.nwin;
                 // reverse steps t' of the window meet the forward steps nb+32-t' (same anti-diagonal)
@@ -708,6 +728,7 @@ age_select_kernel(Pass2Params prm)
                 const int at = atomicAdd(prm.queue_n, 1);
                 if (at < prm.queue_cap) prm.queue[at] = make_uint2((uint32_t)item, (uint32_t)(h | (plane << 1) | (s << 4) | (w2 << 16)));
             }
+            if (lane == 0) sc.hotlist[0] = nhot;
         }
     }
 }
@@ -802,10 +823,10 @@ age_enum_kernel(Pass2Params prm)
                 int *rlo = sc.rowrange, *rhi = sc.rowrange + (len2 + 2);
                 pc = clock64();
                 indel_row_ranges(V, rlo, rhi, lane);
-                if (lane == 0) PROF_ADD(1, clock64() - pc);
+                if (lane == 0) { PROF_ADD(1, clock64() - pc); atomicMax(&g_prof[6], ((unsigned long long)((clock64() - pc) >> 10) << 32) | ((unsigned long long)min(sc.hotlist[0], 4095) << 16) | (unsigned long long)(len2 & 0xFFFF)); }
                 pc = clock64();
                 indel_enumerate(V, L, rlo, rhi, lane);
-                if (lane == 0) PROF_ADD(2, clock64() - pc);
+                if (lane == 0) { PROF_ADD(2, clock64() - pc); atomicMax(&g_prof[7], (unsigned long long)(clock64() - pc)); }
             } else invtdup_enumerate(V, L, lane);
             __syncwarp();
             if (lane == 0) {
@@ -914,8 +935,8 @@ void launch_pass2(const Pass2Params &p, cudaStream_t st)
         cudaMemcpyFromSymbol(z, g_prof, sizeof(z));
         cudaMemcpy(&qn, p.queue_n, sizeof(int), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[p2 prof] pre-swept windows %d, slowest pair index %llu\n", qn, z[0] & 0xFFFFFF); z[0] = (z[0] >> 24) << 10;
-                fprintf(stderr, "[p2 prof] pairs %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | on-demand re-sweeps fwd %.1f (%llu win) rev %.1f (%llu win)\n",
-                p.n_pairs, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[6], z[5] / 1e6, z[7]);
+                fprintf(stderr, "[p2 prof] pairs %d | Mcycles: slowest pair %.1f ranges %.1f enumerate %.1f blocks %.1f | on-demand re-sweeps fwd %.1f rev %.1f | slowest ranges %.2f (hot windows %llu, len2 %llu) enumerate %.2f\n",
+                p.n_pairs, z[0] / 1e6, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[5] / 1e6, (double)((z[6] >> 32) << 10) / 1e6, (z[6] >> 16) & 0xFFFF, z[6] & 0xFFFF, z[7] / 1e6);
     }
 }
 
