@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstring>
+#include <cstddef>
 #include <string>
 #include <thread>
 #include <vector>
@@ -362,7 +363,7 @@ bool fetch_from_device(age_ctx *ctx, Device &dev)
                     if (hp.a[k] < 0) continue;
                     const Aligner &al = ctx->aligners[hp.a[k]];
                     const AlignerOut &o = H.outs[al.out];
-                    ctx->outs[hp.a[k]] = o;
+                    memcpy(&ctx->outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
                     std::vector<age_block> &b = ctx->blocks[hp.a[k]];
                     b.clear();
                     for (int q = 0; q < 4; ++q)
@@ -452,9 +453,11 @@ void assemble(age_ctx *ctx, age_result *out, size_t n)
     }
     for (size_t i = 0; i < n; ++i) {
         age_result &r = out[i];
-        memset(&r, 0, sizeof(r));
+        memset(&r, 0, offsetof(age_result, bp));          // header only: bp rows beyond n_bp are not part of the result
+        r.alt_index = -1; r.n_left = r.n_right = r.n_alt_left = r.n_alt_right = 0;
+        r.left = r.right = r.alt_left = r.alt_right = nullptr;
         r.status = ctx->job_status[i];
-        r.alt_index = -1; r.aux_score = -1;
+        r.aux_score = -1;
         if (r.status != AGE_OK) continue;
         const int m = main_of[i], x = aux_of[i];
         const AlignerOut &om = ctx->outs[m];
@@ -470,7 +473,7 @@ void assemble(age_ctx *ctx, age_result *out, size_t n)
         if (o.n_bp < 0) continue;                                  // lost the -both selection: score only
         r.detail = 1;
         r.n_bp = o.n_bp;
-        memcpy(r.bp, o.bp, sizeof(r.bp));
+        memcpy(r.bp, o.bp, sizeof(r.bp[0]) * (size_t)std::max(o.n_bp, 0));
         r.alt_index = o.alt_index;
         r.n_left = o.n_blk[0]; r.n_right = o.n_blk[1]; r.n_alt_left = o.n_blk[2]; r.n_alt_right = o.n_blk[3];
         const age_block *b = ctx->blocks[pick].data();
@@ -585,8 +588,10 @@ extern "C" int age_align_batch(age_ctx *ctx, const age_job *jobs, size_t n, age_
     ctx->staged = false;
     const double tb = wall_ms();
     build_plan(ctx, jobs, n);
-    if (getenv("AGE_HOST_PROF")) fprintf(stderr, "[host prof] plan %.2f ms\n", wall_ms() - tb);
-    return run_plan(ctx, out, n);
+    const double tplan = wall_ms() - tb;
+    const int rc = run_plan(ctx, out, n);
+    if (getenv("AGE_HOST_PROF")) fprintf(stderr, "[host prof] plan %.2f ms, age_align_batch total %.2f ms\n", tplan, wall_ms() - tb);
+    return rc;
 }
 
 extern "C" int age_stage(age_ctx *ctx, const age_job *jobs, size_t n)
