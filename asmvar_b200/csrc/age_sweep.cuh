@@ -95,6 +95,7 @@ template <int DIR> struct StripCtx {
     uint32_t *tilemax;
     uint32_t *ckpt;
     bool first;                             // no boundary input: the strip starts at the matrix border
+    bool live;                              // the lane's rows of D (q0 .. q0+7) include rows of the matrix: padding lanes skip the D traffic
     volatile int *prog_out;                 // multi-warp sweep: blocks of this strip's boundary row flushed so far (or null)
 
     __device__ __forceinline__ void init(const PairTask &T, int s_, int si, int lane_)
@@ -118,6 +119,7 @@ template <int DIR> struct StripCtx {
         tilemax = T.tilemax;
         ckpt = FWD ? T.ckpt_f : T.ckpt_r;
         prog_out = nullptr;
+        live = q0 <= T.len2;
     }
 };
 
@@ -195,7 +197,7 @@ __device__ __forceinline__ void ring_fill_border(WarpRings &R, int lane, uint32_
 template <int DIR>
 __device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS, int t)
 {
-    if (t <= C.nsteps) {
+    if (t <= C.nsteps && C.live) {
         const uint4 *src = C.D4 + ((C.sbase + (size_t)(C.nb + 31 - t)) * W) * 64 + C.lane;
 #pragma unroll
         for (int i = 0; i < W * 2; ++i) cp_async16(&DS.d[t & 1][i][C.lane], src + i * 32);
@@ -244,7 +246,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
             for (int w = 0; w < W; ++w) {
                 // ---- forward: D[w] = maxima at the previous column, rows shifted by one (entry 0 = row above) ----
                 const uint32_t upMprev = w == 0 ? S.pM : uM[w - 1];
-                if (FWD && !TRACE) {
+                if (FWD && !TRACE && C.live) {
                     uint4 *dst = C.D4 + (slot * W + w) * 64 + lane;
                     dst[0]  = make_uint4(upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
                     dst[32] = make_uint4(S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
@@ -274,7 +276,7 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                 }
                 // ---- the column ---------------------------------------------------------------------------------
                 uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
-                if (!FWD) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                if (!FWD && C.live) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
                 uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
                 uint32_t nibw = 0;
 #pragma unroll
@@ -459,7 +461,7 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
                 for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
             }
             uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
-            if (!FWD && TRACE_M) {              // shifted forward maxima of this column (for the hot bits)
+            if (!FWD && TRACE_M && C.live) {    // shifted forward maxima of this column (for the hot bits)
                 const uint4 *src = C.D4 + ((C.sbase + (size_t)(nb + 31 - t)) * W + (W - 1 - w)) * 64 + lane;
                 d0 = __ldcg(src); d1 = __ldcg(src + 32);
             }
