@@ -34,6 +34,9 @@ sys.path.insert(0, str(ROOT))
 
 SCORING = (1, -1, -10, -1)          # AgeOption.h:25-28 (AsmvarDetect defaults) = Test2/Run.sh
 ALG_BYTES_PER_CELL_UPDATE = 2.5     # indel = 5 B per matrix cell = 2.5 B per cell update
+# DRAM traffic of age_sweep_kernel from the committed `ncu --set full` capture (profiles/r1_sweep_kernel_ncu_key_metrics.txt):
+# dram__bytes_read.sum 93.39 GB + dram__bytes_write.sum 96.79 GB for one launch over 81.94 G cell updates
+NCU_DRAM_BYTES_PER_CELL_UPDATE = (93.392639e9 + 96.789729e9) / 81.94e9
 KERNELS_PER_STEP = 8                # age_pack, age_sweep, age_select, age_presweep x2, age_enum, age_blocks (+ the pack of the stage call)
 # s16x2 / logic instructions of the recurrence per cell pair: VIMNMX, PRMT, VIADDMNMX, LOP3, VIADD,
 # LOP3, VIMNMX3 in both sweeps, + VIADD, VIMNMX.U16x2 for the split sum in the reverse sweep  => (7 + 9) / 2 per pair-cell
@@ -267,9 +270,11 @@ def main():
                     "h2d_bytes_per_step": st["h2d_bytes"], "d2h_bytes_per_step": st["d2h_bytes"]},
             "gpu_launches": launches,
             "kernel_wall_ms_per_step": wall_ms / args.steps,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                         "traffic": NCU_DRAM_BYTES_PER_CELL_UPDATE * cu / 1e9 if args.workload == "c2" else None, "traffic_unit": "GB per launch",
                          "kernel": "age_sweep_kernel", "peak_source": which,
-                         "note": "algorithmic bytes = 2.5 B per cell update (SURVEY 8d); per-GPU figure"},
+                         "note": "achieved = 2.5 algorithmic B per cell update (SURVEY 8d) x cell updates of one launch / its CUDA-event time, per GPU; "
+                                 "traffic = ncu dram read+write of the committed capture (2.32 B per cell update) scaled to this launch"},
         }
         peak = C.c_double(0.0)
         if capi.load().age_int16_peak(local, C.byref(peak)) == 0 and peak.value > 0:
