@@ -288,6 +288,7 @@ bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids
     size_t nwt_total = 0;
     for (size_t i = 0; i < np; ++i) { const HostPair &hp = ctx->pairs[pair_ids[i]]; nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets; }
     dev.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
+    if (const char *e = getenv("AGE_QUEUE_CAP")) dev.queue_cap = std::max(1, atoi(e));   // test knob: a short work list forces on-demand re-sweeps
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
     dev.in_bytes = task_bytes + in_off[np];
     if (!dev.hin.ensure(dev.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }

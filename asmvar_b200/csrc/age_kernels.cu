@@ -160,9 +160,9 @@ void launch_sweeps(const PairTask *d_pairs, int n_pairs, int max_strips, int32_t
     cudaMemsetAsync(d_counter, 0, sizeof(int32_t), st);
     // one warp per pair fills the GPU from ~sms * 16 pairs on; below that, share each pair among up to 16 warps
     int nw = 1;
-    static const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;
+    const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;   // test knob: 1 = one warp per pair, 2..16 = pipelined
     while (nw < 16 && nw * 2 <= max_strips && n_pairs * nw * 2 <= sms * 16) nw *= 2;
-    if (force_nw) nw = force_nw;
+    if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) nw = force_nw;
     if (max_strips > MAX_STRIPS_LONG) nw = 1;
     if (nw > 1) {
         const int smem = nw * (int)sizeof(SweepSmem);
@@ -172,8 +172,7 @@ void launch_sweeps(const PairTask *d_pairs, int n_pairs, int max_strips, int32_t
         return;
     }
     int blocks = (n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS;
-    static const int occ = getenv("AGE_OCC") ? atoi(getenv("AGE_OCC")) : 8;
-    if (blocks > sms * occ) blocks = sms * occ;              // persistent: the work counter feeds the warps
+    if (blocks > sms * SWEEP_OCC) blocks = sms * SWEEP_OCC;  // persistent: the work counter feeds the warps
     const int smem = SWEEP_WARPS * (int)sizeof(SweepSmem);
     cudaFuncSetAttribute(age_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     age_sweep_kernel<<<blocks, SWEEP_WARPS * 32, smem, st>>>(d_pairs, n_pairs, d_counter);

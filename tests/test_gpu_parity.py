@@ -177,3 +177,27 @@ def test_two_devices_same_results(eng):
         b = e2.align(jobs)
     for x, y in zip(a, b):
         assert not diff_summary(y, x)
+
+
+@pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_QUEUE_CAP": "4"}])
+def test_golden_records_other_kernel_paths(eng, knob, monkeypatch):
+    """The same golden batch through the code paths a small batch does not take by itself: one warp per pair
+    (the kernel large batches use), 16 warps per pair (long alignments), and a work list too short for the
+    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand."""
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
+    jobs, owner = [], []
+    for ci, c in enumerate(CASES):
+        for j in case_jobs(c, len(jobs), True):
+            jobs.append(j); owner.append(ci)
+    res = eng.align(jobs)
+    by_case = {}
+    for r, ci in zip(res, owner):
+        by_case.setdefault(ci, []).append(r)
+    bad = []
+    for ci, c in enumerate(CASES):
+        it = iter(by_case[ci])
+        got = U.candidate_record(c, lambda *a: next(it))
+        if got.rstrip("\n") != c["expected"].rstrip("\n"):
+            bad.append(c["id"])
+    assert not bad, f"{knob}: {len(bad)} records differ from the reference: {bad[:20]}"
