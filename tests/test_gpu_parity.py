@@ -201,3 +201,36 @@ def test_golden_records_other_kernel_paths(eng, knob, monkeypatch):
         if got.rstrip("\n") != c["expected"].rstrip("\n"):
             bad.append(c["id"])
     assert not bad, f"{knob}: {len(bad)} records differ from the reference: {bad[:20]}"
+
+
+def test_geometry_boundaries(eng):
+    """Shapes that sit on the seams of the kernel geometry: strips of 256 rows, blocks of 4 columns, windows of
+    32 steps (128 columns), fewer blocks than lanes, single rows / columns."""
+    rng = np.random.default_rng(99)
+    len2s = [1, 2, 7, 8, 9, 255, 256, 257, 511, 512, 513, 768]
+    len1s = [1, 2, 3, 4, 5, 31, 32, 33, 124, 127, 128, 129, 132, 257, 1023, 1025]
+    jobs = []
+    for i, l2 in enumerate(len2s):
+        for k, l1 in enumerate(len1s):
+            if (i + k) % 3:               # a third of the grid is enough for one batch
+                continue
+            w = rand_seq(rng, l1, "ACGT")
+            # a contig that shares material with the window (so that scores are not trivial) cut or padded to l2
+            base = (w * (l2 // max(l1, 1) + 2))[: l2 + 7]
+            q = mutate(rng, base, 0.05, 0.02)[:l2]
+            if len(q) < l2:
+                q = q + rand_seq(rng, l2 - len(q), "ACGT")
+            flag = FLAGS[(i + 2 * k) % len(FLAGS)]
+            jobs.append((w, q, flag, *SCORINGS[(i + k) % len(SCORINGS)]))
+    check_against_oracle(eng, jobs)
+
+
+def test_scoring_corners(eng):
+    """gap extension dearer than gap opening (the flipped tag branch), large match scores, equal open / extend"""
+    rng = np.random.default_rng(5)
+    jobs = []
+    for sc in [(1, -1, -1, -3), (5, -4, -3, -3), (63, -63, -40, -2), (2, -1, -2, -7), (1, -3, -100, -1), (7, -2, -1, -1)]:
+        for flag in FLAGS:
+            w, q = sv_pair(rng, int(rng.integers(120, 420)), int(rng.integers(20, 60)), ["del", "ins", "tdup", "inv"][flag % 4])
+            jobs.append((w, q, flag, *sc))
+    check_against_oracle(eng, jobs)
