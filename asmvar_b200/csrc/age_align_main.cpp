@@ -16,7 +16,13 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +37,9 @@
 using namespace std;
 
 namespace {
+
+thread g_warm;                                 // early CUDA start-up (see warm_up_device)
+[[noreturn]] void die(int rc) { if (g_warm.joinable()) g_warm.join(); exit(rc); }
 
 struct Seq {                                   // the subset of class Sequence the CLI needs (Sequence.hh:20-215)
     string seq, name;
@@ -63,34 +72,58 @@ string upper(string s) { for (auto &c : s) c = (char)toupper((unsigned char)c); 
 // gz-aware whole-file reader (the reference uses gzstream, which also reads plain files)
 bool slurp(const string &file, string &out)
 {
+    out.clear();
+    FILE *fp = fopen(file.c_str(), "rb");
+    if (!fp) return false;
+    unsigned char magic[2] = {0, 0};
+    const size_t got = fread(magic, 1, 2, fp);
+    if (!(got == 2 && magic[0] == 0x1f && magic[1] == 0x8b)) {       // plain file: one read of the whole size
+        if (fseek(fp, 0, SEEK_END) == 0) {
+            const long sz = ftell(fp);
+            if (sz > 0) { out.resize((size_t)sz); rewind(fp); out.resize(fread(&out[0], 1, (size_t)sz, fp)); fclose(fp); return true; }
+        }
+        rewind(fp);                                                  // not seekable (pipe): fall through to the stream loop
+        char buf[1 << 16];
+        size_t n;
+        out.append((const char *)magic, got);
+        while ((n = fread(buf, 1, sizeof(buf), fp)) > 0) out.append(buf, n);
+        fclose(fp);
+        return true;
+    }
+    fclose(fp);
     gzFile f = gzopen(file.c_str(), "rb");
     if (!f) return false;
-    char buf[1 << 16];
+    gzbuffer(f, 1 << 20);
+    vector<char> buf(1 << 20);
     int n;
-    out.clear();
-    while ((n = gzread(f, buf, sizeof(buf))) > 0) out.append(buf, n);
+    while ((n = gzread(f, buf.data(), (unsigned)buf.size())) > 0) out.append(buf.data(), n);
     gzclose(f);
     return true;
 }
 
-// Fa::Load (Backup/Fa.h:27-50): per line the first whitespace-delimited token; '>' tokens start a record
-void load_fa(const string &file, map<string, string> &fa)
+inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }     // isspace() of the C locale
+
+// Fa::Load (Backup/Fa.h:27-50): per line the first whitespace-delimited token; '>' tokens start a record.
+// false = the file cannot be opened.
+bool load_fa(const string &file, map<string, string> &fa)
 {
     string data;
-    if (!slurp(file, data)) { cerr << "Cannot open file : " << file << endl; exit(1); }
+    if (!slurp(file, data)) return false;
     string id;
-    size_t i = 0;
-    const size_t n = data.size();
-    while (i < n) {
-        while (i < n && isspace((unsigned char)data[i])) ++i;          // operator>> skips leading white space
-        if (i >= n) break;
-        size_t j = i;
-        while (j < n && !isspace((unsigned char)data[j])) ++j;
-        if (data[i] == '>') { id.assign(data, i + 1, j - i - 1); fa[id].clear(); }
-        else fa[id].append(data, i, j - i);
-        while (j < n && data[j] != '\n') ++j;                          // getline drops the rest of the line
-        i = j + 1;
+    string *cur = nullptr;
+    const char *p = data.data(), *end = p + data.size();
+    while (p < end) {
+        while (p < end && is_space(*p)) ++p;                           // operator>> skips leading white space (and empty lines)
+        if (p >= end) break;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+        const char *le = nl ? nl : end;
+        const char *q = p;
+        while (q < le && !is_space(*q)) ++q;                           // the token ends at the first white space
+        if (*p == '>') { id.assign(p + 1, (size_t)(q - p - 1)); cur = &fa[id]; cur->clear(); }
+        else { if (!cur) cur = &fa[id]; cur->append(p, (size_t)(q - p)); }
+        p = nl ? nl + 1 : end;                                         // getline drops the rest of the line
     }
+    return true;
 }
 
 struct Candidate {                              // one record of the output
@@ -107,27 +140,77 @@ struct Options {
 };
 
 double now() { timeval t; gettimeofday(&t, nullptr); return t.tv_sec + t.tv_usec / 1e6; }
+const bool g_prof = getenv("AGE_CLI_PROF") != nullptr;          // stage times on stderr
+const double g_t0 = now();
+void prof(const char *what) { if (g_prof) fprintf(stderr, "[cli prof] %-28s at %.3f s\n", what, now() - g_t0); }
 
 age_ctx *g_ctx = nullptr;
-age_ctx *ctx()
+once_flag g_ctx_once;
+string g_ctx_error;
+void create_ctx()
 {
-    if (g_ctx) return g_ctx;
     vector<int> devs;
     if (const char *e = getenv("AGE_DEVICES")) {   // e.g. AGE_DEVICES=0,1,2,3
         stringstream ss(e); string tok;
         while (getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
     }
     g_ctx = age_create(devs.empty() ? nullptr : devs.data(), (int)devs.size());
-    if (!g_ctx) { cerr << "[ERROR] " << age_last_error(nullptr) << endl; exit(1); }
+    if (!g_ctx) g_ctx_error = age_last_error(nullptr);
+    prof("device context ready");
+}
+age_ctx *ctx()
+{
+    call_once(g_ctx_once, create_ctx);
+    if (!g_ctx) { cerr << "[ERROR] " << g_ctx_error << endl; die(1); }
     return g_ctx;
 }
+// CUDA start-up takes 0.3-3 s on a cold box: the batch dialect runs it beside the FASTA parsing
+void warm_up_device() { if (!g_warm.joinable()) g_warm = thread([] { call_once(g_ctx_once, create_ctx); }); }
 
-// Align a chunk of candidates on the GPU(s) and print their records in order.
-void flush_candidates(vector<Candidate> &cands, const Options &o, bool age_time)
-{
-    if (cands.empty()) return;
+// ---------------------------------------------------------------------------------------------------------
+// Candidate pipeline.  The reference aligns and prints one candidate at a time; here three stages overlap:
+//   main thread    cuts the windows out of the FASTA records (substr / revcom) and closes a chunk,
+//   device thread  runs age_align_batch() on chunk k+1,
+//   output thread  formats chunk k on the host cores (age_format_alignment is reentrant) and writes it in order.
+// stdout stays byte-identical to the serial loop; a fatal condition is reported after everything before it
+// has been printed, as in the reference.
+// ---------------------------------------------------------------------------------------------------------
+struct Chunk {
+    vector<Candidate> cands;
+    Options o;
+    bool age_time = true;
     vector<age_job> jobs;
-    for (Candidate &c : cands) {
+    vector<age_result> res;
+    vector<age_block> blocks;                   // deep copy: age_result block pointers die with the next batch
+    double per = 0;
+    string fatal;                               // device-stage failure, reported by the output stage
+};
+
+template <class T> class Channel {              // bounded hand-over between two stages
+public:
+    explicit Channel(size_t cap) : cap_(cap) {}
+    void push(T v) { unique_lock<mutex> l(m_); cv_.wait(l, [&] { return q_.size() < cap_; }); q_.push_back(std::move(v)); cv_.notify_all(); }
+    T pop() { unique_lock<mutex> l(m_); cv_.wait(l, [&] { return !q_.empty(); }); T v = std::move(q_.front()); q_.pop_front(); cv_.notify_all(); return v; }
+private:
+    size_t cap_; mutex m_; condition_variable cv_; deque<T> q_;
+};
+
+template <class F> void parallel_for(size_t n, F f)
+{
+    const size_t nt = min<size_t>(max(1u, min(32u, thread::hardware_concurrency())), (n + 15) / 16);
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    atomic<size_t> next{0};
+    vector<thread> th;
+    for (size_t t = 0; t < nt; ++t)
+        th.emplace_back([&] { for (;;) { const size_t i = next.fetch_add(8); if (i >= n) break; for (size_t k = i; k < min(n, i + 8); ++k) f(k); } });
+    for (auto &x : th) x.join();
+}
+
+// device stage: the jobs of a chunk through the C ABI
+void align_chunk(Chunk &ch)
+{
+    const Options &o = ch.o;
+    for (Candidate &c : ch.cands) {
         if (!c.ok) continue;
         auto add = [&](const Seq &a, const Seq &b) {
             age_job j;
@@ -136,55 +219,146 @@ void flush_candidates(vector<Candidate> &cands, const Options &o, bool age_time)
             j.flag = o.flag;
             j.match = (int16_t)o.match; j.mismatch = (int16_t)o.mismatch; j.gap_open = (int16_t)o.go; j.gap_extend = (int16_t)o.ge;
             j.partner = -1;
-            jobs.push_back(j);
-            return (int)jobs.size() - 1;
+            ch.jobs.push_back(j);
+            return (int)ch.jobs.size() - 1;
         };
         c.job[0] = add(c.s1, c.s2);
         if (o.both) {
             c.job[1] = add(c.s1, c.s3);
-            jobs[c.job[0]].partner = c.job[1];
-            jobs[c.job[1]].partner = c.job[0];
+            ch.jobs[c.job[0]].partner = c.job[1];
+            ch.jobs[c.job[1]].partner = c.job[0];
         }
     }
-    vector<age_result> res(jobs.size() ? jobs.size() : 1);
+    ch.res.resize(ch.jobs.size() ? ch.jobs.size() : 1);
     const double t0 = now();
-    if (!jobs.empty() && age_align_batch(ctx(), jobs.data(), jobs.size(), res.data()) != 0) {
-        cerr << "[ERROR] age_align_batch: " << age_last_error(g_ctx) << endl;
-        exit(1);
+    if (!ch.jobs.empty() && age_align_batch(ctx(), ch.jobs.data(), ch.jobs.size(), ch.res.data()) != 0) {
+        ch.fatal = string("[ERROR] age_align_batch: ") + age_last_error(g_ctx);
+        return;
     }
-    const double per = cands.empty() ? 0.0 : (now() - t0) / cands.size();
-    string buf;
-    for (Candidate &c : cands) {
-        fputs(c.header.c_str(), stdout);
+    ch.per = ch.cands.empty() ? 0.0 : (now() - t0) / ch.cands.size();
+    size_t nblk = 0;
+    for (size_t i = 0; i < ch.jobs.size(); ++i) { const age_result &r = ch.res[i]; nblk += r.n_left + r.n_right + r.n_alt_left + r.n_alt_right; }
+    ch.blocks.resize(nblk ? nblk : 1);
+    age_block *w = ch.blocks.data();
+    for (size_t i = 0; i < ch.jobs.size(); ++i) {
+        age_result &r = ch.res[i];
+        auto take = [&](const age_block *&p, int n) { if (n > 0) memcpy(w, p, sizeof(age_block) * (size_t)n); p = w; w += max(n, 0); };
+        take(r.left, r.n_left); take(r.right, r.n_right); take(r.alt_left, r.n_alt_left); take(r.alt_right, r.n_alt_right);
+    }
+}
+
+// output stage: records of a chunk in candidate order.  false = fatal, message already printed.
+bool print_chunk(Chunk &ch)
+{
+    if (!ch.fatal.empty()) { cerr << ch.fatal << endl; return false; }
+    const Options &o = ch.o;
+    const size_t n = ch.cands.size();
+    vector<string> text(n), note(n);
+    vector<char> bad(n, 0);
+    parallel_for(n, [&](size_t i) {
+        Candidate &c = ch.cands[i];
+        string &out = text[i];
+        out = c.header;
         if (c.ok) {
-            const age_result *r0 = &res[c.job[0]], *r1 = o.both ? &res[c.job[1]] : nullptr;
+            const age_result *r0 = &ch.res[c.job[0]], *r1 = o.both ? &ch.res[c.job[1]] : nullptr;
             for (const age_result *r : {r0, r1})
-                if (r && r->status < 0) {
-                    cerr << "[ERROR] alignment of '" << c.s1.name << "' vs '" << c.s2.name << "' is outside the supported range (status "
-                         << r->status << "): scores must fit 16 bits, gap penalties must be negative" << endl;
-                    exit(1);
+                if (r && r->status < 0 && !bad[i]) {
+                    bad[i] = 1;
+                    note[i] = "[ERROR] alignment of '" + c.s1.name + "' vs '" + c.s2.name + "' is outside the supported range (status " +
+                              to_string(r->status) + "): scores must fit 16 bits, gap penalties must be negative\n";
                 }
+            if (bad[i]) return;
             const bool ok0 = r0->status == AGE_OK, ok1 = r1 && r1->status == AGE_OK;
             int pick = -1;
             if (!o.both) pick = ok0 ? 0 : -1;
             else if (ok0 || ok1) pick = (ok0 && (!ok1 || r0->score >= r1->score)) ? 0 : 1;     // age_align.cpp:270-276
-            if (pick < 0) cerr << "No alignment made." << endl;
+            if (pick < 0) note[i] = "No alignment made.\n";
             else {
                 const Seq &q = pick ? c.s3 : c.s2;
                 const age_result *r = pick ? r1 : r0;
                 age_seqview v1{c.s1.seq.data(), (int32_t)c.s1.seq.size(), c.s1.name.c_str(), c.s1.start, c.s1.reverse ? 1 : 0};
                 age_seqview v2{q.seq.data(), (int32_t)q.seq.size(), q.name.c_str(), q.start, q.reverse ? 1 : 0};
-                const age_job &j = jobs[c.job[pick]];
-                buf.resize(8192 + 8 * (c.s1.seq.size() + q.seq.size()));
-                size_t n = age_format_alignment(&v1, &v2, &j, r, &buf[0], buf.size());
-                if (n >= buf.size()) { buf.resize(n + 1); n = age_format_alignment(&v1, &v2, &j, r, &buf[0], buf.size()); }
-                fwrite(buf.data(), 1, n, stdout);
+                const age_job &j = ch.jobs[c.job[pick]];
+                const size_t h = out.size();
+                out.resize(h + 8192 + 8 * (c.s1.seq.size() + q.seq.size()));
+                size_t m = age_format_alignment(&v1, &v2, &j, r, &out[h], out.size() - h);
+                if (m >= out.size() - h) { out.resize(h + m + 1); m = age_format_alignment(&v1, &v2, &j, r, &out[h], out.size() - h); }
+                out.resize(h + m);
             }
         }
-        if (age_time) printf("\nAlignment time is %g s\n\n", per);
+        if (ch.age_time) { char t[64]; snprintf(t, sizeof t, "\nAlignment time is %g s\n\n", ch.per); out += t; }
+    });
+    for (size_t i = 0; i < n; ++i) {
+        fwrite(text[i].data(), 1, text[i].size(), stdout);
+        if (!note[i].empty()) { fflush(stdout); cerr << note[i] << flush; }
+        if (bad[i]) return false;
     }
     fflush(stdout);
-    cands.clear();
+    return true;
+}
+
+extern double g_t_dev, g_t_out;
+class Pipeline {
+public:
+    Pipeline() : to_dev_(2), to_out_(2)
+    {
+        dev_ = thread([this] {
+            for (;;) {
+                unique_ptr<Chunk> ch = to_dev_.pop();
+                if (!ch) { to_out_.push(nullptr); return; }
+                const double t0 = now();
+                if (!failed_) align_chunk(*ch);
+                g_t_dev += now() - t0;
+                if (g_prof) fprintf(stderr, "[cli prof] chunk of %zu aligned in %.3f s\n", ch->cands.size(), now() - t0);
+                to_out_.push(std::move(ch));
+            }
+        });
+        out_ = thread([this] {
+            for (;;) {
+                unique_ptr<Chunk> ch = to_out_.pop();
+                if (!ch) return;
+                const double t0 = now();
+                if (!failed_ && !print_chunk(*ch)) { fflush(stdout); failed_ = true; }
+                g_t_out += now() - t0;
+            }
+        });
+    }
+    // hand a chunk over; exits the program (status 1) once an earlier chunk has failed
+    void submit(vector<Candidate> &cands, const Options &o, bool age_time)
+    {
+        if (!cands.empty()) {
+            unique_ptr<Chunk> ch(new Chunk());
+            ch->cands.swap(cands); ch->o = o; ch->age_time = age_time;
+            to_dev_.push(std::move(ch));
+        }
+        cands.clear();
+        if (failed_) { finish(); die(1); }
+    }
+    // drain both stages; true = everything was printed
+    bool finish()
+    {
+        if (dev_.joinable()) { to_dev_.push(nullptr); dev_.join(); out_.join(); }
+        return !failed_;
+    }
+    ~Pipeline() { finish(); }
+private:
+    Channel<unique_ptr<Chunk>> to_dev_, to_out_;
+    thread dev_, out_;
+    atomic<bool> failed_{false};
+};
+
+Pipeline *g_pipe = nullptr;
+double g_t_dev = 0, g_t_out = 0;
+Pipeline &pipe_() { if (!g_pipe) g_pipe = new Pipeline(); return *g_pipe; }
+
+// Queue a chunk of candidates (cleared on return).
+void flush_candidates(vector<Candidate> &cands, const Options &o, bool age_time) { pipe_().submit(cands, o, age_time); }
+// Wait until every queued record is on stdout; exits with status 1 if one of them was fatal.
+void drain_candidates()
+{
+    if (g_pipe && !g_pipe->finish()) die(1);
+    delete g_pipe; g_pipe = nullptr;
+    if (g_prof) fprintf(stderr, "[cli prof] drained at %.3f s; device stage busy %.3f s, output stage busy %.3f s\n", now() - g_t0, g_t_dev, g_t_out);
 }
 
 int mode_count(int flag)
@@ -194,7 +368,8 @@ int mode_count(int flag)
     return n;
 }
 
-const size_t CHUNK = 8192;                      // candidates per age_align_batch call
+// candidates per age_align_batch call: 1.5 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
+const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 3552); }();
 
 // ---------------------------------------------------------------------------------------------------------
 // batch dialect (age_align.cpp)
@@ -217,7 +392,7 @@ void batch_usage(const char *prog, const Options &o, const string &sel)
     cerr << "          -i, --indel            Indel.\n          -v, --inv              Inv.\n          -l, --invl             Invl.\n";
     cerr << "          -d, --tdup             tdup.\n          -r, --invr             Invr.\n";
     cerr << "          -h                    Output this help information.\n\n";
-    exit(1);
+    die(1);
 }
 
 int batch_main(int argc, char **argv)
@@ -249,7 +424,7 @@ int batch_main(int argc, char **argv)
         case 'r': invr = true; break;
         case 'd': tdup = true; break;
         case 'h': batch_usage(argv[0], o, sel); break;
-        default: cerr << "\n[ERROR]Unknow option: -" << (char)c << "\n" << endl; exit(1);
+        default: cerr << "\n[ERROR]Unknow option: -" << (char)c << "\n" << endl; die(1);
         }
     }
     if (argc > 1) varfile = argv[argc - 1];
@@ -266,16 +441,22 @@ int batch_main(int argc, char **argv)
     if (invr) o.flag |= AGE_INVR_FLAG;
     if (tdup) o.flag |= AGE_TDUPLICATION_FLAG;
     if (o.flag == 0) o.flag = AGE_INDEL_FLAG;                          // age_align.cpp:205
-    if (mode_count(o.flag) != 1) { cerr << "# [Error] In mode specification. More than one mode is specified.\n"; exit(1); }
+    if (mode_count(o.flag) != 1) { cerr << "# [Error] In mode specification. More than one mode is specified.\n"; die(1); }
 
+    warm_up_device();
     map<string, string> tfa, qfa;
-    load_fa(tfile, tfa);
-    load_fa(qfile, qfa);
+    bool qok = false;
+    thread qload([&] { qok = load_fa(qfile, qfa); });                  // both files are parsed side by side
+    const bool tok = load_fa(tfile, tfa);
+    qload.join();
+    if (!tok) { cerr << "Cannot open file : " << tfile << endl; die(1); }
+    if (!qok) { cerr << "Cannot open file : " << qfile << endl; die(1); }
     cerr << "# [INFO] Target fa and Query fa are loaded successfully." << local_time();
+    prof("fasta loaded");
 
     // variant table (age_align.cpp:169-190): tId tStart tEnd qId qStart qEnd info, '#' lines skipped
     string data;
-    if (!slurp(varfile, data)) { cerr << "# [ERROR] Cannot open file : " << varfile << endl; exit(1); }
+    if (!slurp(varfile, data)) { cerr << "# [ERROR] Cannot open file : " << varfile << endl; die(1); }
     struct Reg { string tid, qid, info; long long ts, te, qs, qe; };
     vector<Reg> regs;
     {
@@ -292,13 +473,14 @@ int batch_main(int argc, char **argv)
         }
     }
     cerr << "# [INFO] Variant regions are loaded successfully." << local_time();
+    prof("variant table parsed");
     if (regs.empty()) cerr << "[WARNING] The variant list is empty!\n";
 
     vector<Candidate> cands;
     for (const Reg &r : regs) {
         if (upper(sel) != "ALL" && upper(sel) != upper(r.tid)) continue;
-        if (!tfa.count(r.tid)) { flush_candidates(cands, o, true); cerr << "# [ERROR] " << r.tid << " is not in " << tfile << "\n"; exit(1); }
-        if (!qfa.count(r.qid)) { flush_candidates(cands, o, true); cerr << "# [ERROR] " << r.qid << " is not in " << qfile << "\n"; exit(1); }
+        if (!tfa.count(r.tid)) { flush_candidates(cands, o, true); drain_candidates(); cerr << "# [ERROR] " << r.tid << " is not in " << tfile << "\n"; die(1); }
+        if (!qfa.count(r.qid)) { flush_candidates(cands, o, true); drain_candidates(); cerr << "# [ERROR] " << r.qid << " is not in " << qfile << "\n"; die(1); }
         Candidate c;
         c.header = "# " + r.info + "\n";
         c.ok = substr(tfa[r.tid], r.tid, (int)r.ts, (int)r.te, c.s1) && substr(qfa[r.qid], r.qid, (int)r.qs, (int)r.qe, c.s2);
@@ -312,6 +494,8 @@ int batch_main(int argc, char **argv)
         if (cands.size() >= CHUNK) flush_candidates(cands, o, true);
     }
     flush_candidates(cands, o, true);
+    prof("all windows cut");
+    drain_candidates();
     cerr << "\n******************** AGE ALL DONE ********************\n";
     return 0;
 }
@@ -467,6 +651,7 @@ int orig_main(int argc, char **argv)
                 if (cands.size() >= CHUNK) flush_candidates(cands, o, true);
             }
         flush_candidates(cands, o, true);
+        drain_candidates();                     // keep stdout and the next command's messages in order
     }
     return 1;                                   // sic: the reference's original CLI exits with 1 (Trash/age_align.cpp:365)
 }
@@ -489,6 +674,9 @@ bool looks_original(int argc, char **argv)
 int main(int argc, char **argv)
 {
     const int rc = looks_original(argc, argv) ? orig_main(argc, argv) : batch_main(argc, argv);
+    if (g_warm.joinable()) g_warm.join();
+    prof("main done");
     if (g_ctx) age_destroy(g_ctx);
+    prof("context destroyed");
     return rc;
 }

@@ -28,14 +28,26 @@ thread_local std::string g_create_error;
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+const bool g_hprof = getenv("AGE_HOST_PROF") != nullptr;
+
+// Device / pinned arenas grow with 1/16 of headroom so that a stream of similar batches does not reallocate
+// (cudaMalloc of a ~100 GB arena costs a few hundred milliseconds).
 struct Arena {
     char *ptr = nullptr; size_t cap = 0;
     bool ensure(size_t n) {
         if (n <= cap) return true;
+        const double t0 = wall_ms();
         if (ptr) cudaFree(ptr);
         ptr = nullptr; cap = 0;
-        if (cudaMalloc(&ptr, n) != cudaSuccess) { cudaGetLastError(); return false; }
-        cap = n; return true;
+        size_t want = n + n / 16;
+        if (cudaMalloc(&ptr, want) != cudaSuccess) {
+            cudaGetLastError(); want = n;
+            if (cudaMalloc(&ptr, want) != cudaSuccess) { cudaGetLastError(); return false; }
+        }
+        cap = want;
+        if (g_hprof) fprintf(stderr, "[host prof] cudaMalloc %.1f MB: %.1f ms\n", want / 1e6, wall_ms() - t0);
+        return true;
     }
     void release() { if (ptr) cudaFree(ptr); ptr = nullptr; cap = 0; }
 };
@@ -43,10 +55,14 @@ struct PinnedBuf {
     char *ptr = nullptr; size_t cap = 0;
     bool ensure(size_t n) {
         if (n <= cap) return true;
+        const double t0 = wall_ms();
         if (ptr) cudaFreeHost(ptr);
         ptr = nullptr; cap = 0;
-        if (cudaMallocHost(&ptr, n) != cudaSuccess) { cudaGetLastError(); return false; }
-        cap = n; return true;
+        size_t want = n + n / 16;
+        if (cudaMallocHost(&ptr, want) != cudaSuccess) { cudaGetLastError(); return false; }
+        cap = want;
+        if (g_hprof) fprintf(stderr, "[host prof] cudaMallocHost %.1f MB: %.1f ms\n", want / 1e6, wall_ms() - t0);
+        return true;
     }
     void release() { if (ptr) cudaFreeHost(ptr); ptr = nullptr; cap = 0; }
 };
@@ -403,14 +419,14 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
 {
     const int nd = (int)ctx->devs.size();
     std::vector<std::vector<std::vector<int>>> res(nd);
-    std::vector<size_t> budget(nd);
-    for (int d = 0; d < nd; ++d) {
+    std::vector<size_t> budget(nd, 0);
+    auto query_budget = [&](int d) {             // cudaMemGetInfo costs milliseconds: only asked when a batch outgrows the arenas
         cudaSetDevice(ctx->devs[d].id);
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
         fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap + ctx->devs[d].aux.cap;
         budget[d] = (size_t)(0.85 * (double)fr);
-    }
+    };
     // longest-processing-time-first deal across devices
     std::vector<int> order(ctx->pairs.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
@@ -427,6 +443,13 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
         for (auto &v : per_dev) std::sort(v.begin(), v.end());
     }
     for (int d = 0; d < nd; ++d) {
+        size_t sc = 256, in = align_up(per_dev[d].size() * sizeof(PairTask), 256);
+        for (int pi : per_dev[d]) { sc += ctx->pairs[pi].scratch_bytes; in += ctx->pairs[pi].in_bytes; }
+        if (sc <= ctx->devs[d].scratch.cap && in <= ctx->devs[d].in.cap) {        // fits what is already allocated
+            if (!per_dev[d].empty()) res[d].push_back(per_dev[d]);
+            continue;
+        }
+        query_budget(d);
         std::vector<int> cur; size_t used = 0;
         for (int pi : per_dev[d]) {
             const size_t need = ctx->pairs[pi].scratch_bytes + ctx->pairs[pi].in_bytes + 4096;
@@ -496,6 +519,7 @@ extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
         return nullptr;
     }
     if (n_dev <= 0 || !device_ids) n_dev = 1;
+    const double t_create = wall_ms();
     age_ctx *ctx = new age_ctx();
     ctx->host_threads = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
     for (int i = 0; i < n_dev; ++i) {
@@ -509,6 +533,7 @@ extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
         for (int e = 0; ok && e < 6; ++e) ok = cudaEventCreate(&d.ev[e]) == cudaSuccess;
         if (!ok) { g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); age_destroy(ctx); return nullptr; }
     }
+    if (g_hprof) fprintf(stderr, "[host prof] age_create %.1f ms\n", wall_ms() - t_create);
     return ctx;
 }
 
@@ -527,13 +552,13 @@ extern "C" void age_destroy(age_ctx *ctx)
 
 extern "C" const char *age_last_error(const age_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-static double wall_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-
 static int run_plan(age_ctx *ctx, age_result *out, size_t n)
 {
     static const bool hprof = getenv("AGE_HOST_PROF") != nullptr;
     double tp[6] = {0, 0, 0, 0, 0, 0};
+    const double tsub = wall_ms();
     auto sub = make_subbatches(ctx);
+    tp[3] = wall_ms() - tsub;
     const int nd = (int)ctx->devs.size();
     std::vector<int> rc(nd, 0);
     std::vector<age_stats> dstat(nd);
@@ -578,7 +603,7 @@ static int run_plan(age_ctx *ctx, age_result *out, size_t n)
     account(ctx);
     double t0 = wall_ms();
     assemble(ctx, out, n);
-    if (hprof) fprintf(stderr, "[host prof] stage(pack+H2D) %.2f ms, kernels %.2f ms, fetch(D2H+copy) %.2f ms, assemble %.2f ms\n", tp[0], tp[1], tp[2], wall_ms() - t0);
+    if (hprof) fprintf(stderr, "[host prof] sub-batching %.2f ms, stage(pack+H2D) %.2f ms, kernels %.2f ms, fetch(D2H+copy) %.2f ms, assemble %.2f ms\n", tp[3], tp[0], tp[1], tp[2], wall_ms() - t0);
     return 0;
 }
 

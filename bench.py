@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--batch", type=int, default=3552, help="candidates per step per GPU (3552 = 1.5 pairs per resident warp: 148 SMs x 16 warps; the longest-first deal needs more pairs than warps to balance)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cli", action="store_true", help="skip the age_align process leg (FASTA in -> .age out)")
+    ap.add_argument("--cli-candidates", type=int, default=28416, help="candidates of the age_align process leg")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 (default, the configuration the metric is quoted on); c4 = -inv 20 kb x 4 kb; c5 = 50 kb x 10 kb -indel -both "
                          "(extra measurements, not the headline)")
@@ -283,6 +285,20 @@ def main():
                                    "frac": ach_i / peak.value, "kernel": "age_sweep_kernel",
                                    "note": "achieved = 4 algorithmic s16x2/logic instructions per cell update x cell updates / sweep-kernel time; "
                                            "peak = age_int16_peak microbenchmark on this GPU (independent chains of the same instruction mix)"}
+        eng.close()                               # the CLI leg below is a separate process and needs the HBM
+        eng = None
+        if world == 1 and not args.no_cli and args.workload == "c2":
+            try:
+                sys.path.insert(0, str(ROOT / "tools"))
+                import cli_throughput
+                m = cli_throughput.measure(args.cli_candidates, devices=str(local))
+                out["cli"] = {"value": m["realign_per_s"], "unit": "realignments/s", "candidates": m["candidates"], "seconds": m["seconds"],
+                              "fasta_bytes": m["fasta_bytes"], "age_bytes": m["age_bytes"], "cuda_startup_s": m.get("cuda_startup_s"),
+                              "steady_value": m.get("steady_realign_per_s"),
+                              "note": "whole age_align process, FASTA + variant table in -> .age text out (SURVEY 8d end-to-end), files in /dev/shm; "
+                                      "includes process and CUDA start-up; steady_value = candidates / time after the device context is ready"}
+            except Exception as e:
+                out["cli"] = {"value": None, "note": f"unavailable: {e}"}
         if world == 1 and not args.no_cpu and args.workload == "c2":
             try:
                 cores = os.cpu_count() or 1
@@ -295,7 +311,8 @@ def main():
             except Exception as e:   # the baseline is reported, never required for the GPU number
                 out["cpu_baseline"] = {"value": None, "unit": "realignments/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
         print(json.dumps(out), flush=True)
-    eng.close()
+    if eng is not None:
+        eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,47 @@
+#!/usr/bin/env python
+"""FASTA in -> .age out throughput of asmvar_b200/age_align (SURVEY 8(d) end-to-end figure) on C2 candidates."""
+import argparse, os, subprocess, sys, tempfile, time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def measure(n: int, devices: str = "0", chunk: int = 0, keep: str = "", verbose: bool = False) -> dict:
+    from asmvar_b200 import synth
+    cands = synth.indel_candidates(n, seed=1002)
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
+        t, q, v = synth.write_files(cands, Path(d), "cli")
+        env = dict(os.environ, AGE_DEVICES=devices, AGE_CLI_PROF="1")
+        if chunk:
+            env["AGE_CHUNK"] = str(chunk)
+        out = keep or os.path.join(d, "out.age")
+        cmd = [str(ROOT / "asmvar_b200" / "age_align"), "-i", "-b", "-m", "1", "-M", "-1", "-g", "-10", "-e", "-1", "-t", str(t), "-q", str(q), str(v)]
+        t0 = time.perf_counter()
+        with open(out, "wb") as fo:
+            p = subprocess.run(cmd, stdout=fo, stderr=subprocess.PIPE, env=env)
+        dt = time.perf_counter() - t0
+        if p.returncode != 0:
+            raise RuntimeError(p.stderr.decode()[-2000:])
+        ready = None
+        for line in p.stderr.decode().splitlines():
+            if line.startswith("[cli prof] device context ready"):
+                ready = float(line.split(" at ")[1].split()[0])
+            if verbose and line.startswith(("[cli prof]", "[host prof]")):
+                print(line, file=sys.stderr)
+        size = os.path.getsize(out)
+        in_bytes = sum(os.path.getsize(x) for x in (t, q, v))
+    res = {"candidates": n, "seconds": dt, "realign_per_s": n / dt, "age_bytes": size, "fasta_bytes": in_bytes}
+    if ready is not None and dt > ready:
+        res["cuda_startup_s"] = ready
+        res["steady_realign_per_s"] = n / (dt - ready)
+    return res
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-n", type=int, default=14208)
+    ap.add_argument("--devices", default="0")
+    ap.add_argument("--chunk", type=int, default=0)
+    a = ap.parse_args()
+    print(measure(a.n, a.devices, a.chunk, verbose=True))
