@@ -92,6 +92,7 @@ class AgeStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged",
     "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version", "age_int16_peak",
+    "age_submit", "age_collect", "age_in_flight",
 ]
 
 _lib = None
@@ -116,6 +117,12 @@ def load() -> C.CDLL:
     lib.age_last_error.argtypes = [vp]
     lib.age_align_batch.restype = C.c_int
     lib.age_align_batch.argtypes = [vp, C.POINTER(AgeJob), C.c_size_t, C.POINTER(AgeResult)]
+    lib.age_submit.restype = C.c_int
+    lib.age_submit.argtypes = [vp, C.POINTER(AgeJob), C.c_size_t]
+    lib.age_collect.restype = C.c_int
+    lib.age_collect.argtypes = [vp, C.POINTER(AgeResult), C.c_size_t]
+    lib.age_in_flight.restype = C.c_int
+    lib.age_in_flight.argtypes = [vp]
     lib.age_stage.restype = C.c_int
     lib.age_stage.argtypes = [vp, C.POINTER(AgeJob), C.c_size_t]
     lib.age_run_staged.restype = C.c_int

@@ -170,7 +170,7 @@ void warm_up_device() { if (!g_warm.joinable()) g_warm = thread([] { call_once(g
 // ---------------------------------------------------------------------------------------------------------
 // Candidate pipeline.  The reference aligns and prints one candidate at a time; here three stages overlap:
 //   main thread    cuts the windows out of the FASTA records (substr / revcom) and closes a chunk,
-//   device thread  runs age_align_batch() on chunk k+1,
+//   device thread  age_submit()s chunk k+1 while the kernels of chunk k run, then age_collect()s chunk k,
 //   output thread  formats chunk k on the host cores (age_format_alignment is reentrant) and writes it in order.
 // stdout stays byte-identical to the serial loop; a fatal condition is reported after everything before it
 // has been printed, as in the reference.
@@ -182,7 +182,8 @@ struct Chunk {
     vector<age_job> jobs;
     vector<age_result> res;
     vector<age_block> blocks;                   // deep copy: age_result block pointers die with the next batch
-    double per = 0;
+    double per = 0, t_submit = 0;
+    bool submitted = false;
     string fatal;                               // device-stage failure, reported by the output stage
 };
 
@@ -206,8 +207,8 @@ template <class F> void parallel_for(size_t n, F f)
     for (auto &x : th) x.join();
 }
 
-// device stage: the jobs of a chunk through the C ABI
-void align_chunk(Chunk &ch)
+// device stage, first half: the jobs of a chunk go to the device (age_submit does not wait for the kernels)
+void submit_chunk(Chunk &ch)
 {
     const Options &o = ch.o;
     for (Candidate &c : ch.cands) {
@@ -230,12 +231,18 @@ void align_chunk(Chunk &ch)
         }
     }
     ch.res.resize(ch.jobs.size() ? ch.jobs.size() : 1);
-    const double t0 = now();
-    if (!ch.jobs.empty() && age_align_batch(ctx(), ch.jobs.data(), ch.jobs.size(), ch.res.data()) != 0) {
-        ch.fatal = string("[ERROR] age_align_batch: ") + age_last_error(g_ctx);
-        return;
-    }
-    ch.per = ch.cands.empty() ? 0.0 : (now() - t0) / ch.cands.size();
+    ch.t_submit = now();
+    if (ch.jobs.empty()) return;
+    if (age_submit(ctx(), ch.jobs.data(), ch.jobs.size()) != 0) { ch.fatal = string("[ERROR] age_submit: ") + age_last_error(g_ctx); return; }
+    ch.submitted = true;
+}
+
+// device stage, second half: wait for the chunk's results; block lists are copied out of the context
+void collect_chunk(Chunk &ch)
+{
+    if (!ch.submitted) return;
+    if (age_collect(ctx(), ch.res.data(), ch.jobs.size()) != 0) { ch.fatal = string("[ERROR] age_collect: ") + age_last_error(g_ctx); return; }
+    ch.per = ch.cands.empty() ? 0.0 : (now() - ch.t_submit) / ch.cands.size();
     size_t nblk = 0;
     for (size_t i = 0; i < ch.jobs.size(); ++i) { const age_result &r = ch.res[i]; nblk += r.n_left + r.n_right + r.n_alt_left + r.n_alt_right; }
     ch.blocks.resize(nblk ? nblk : 1);
@@ -303,14 +310,19 @@ public:
     Pipeline() : to_dev_(2), to_out_(2)
     {
         dev_ = thread([this] {
+            unique_ptr<Chunk> prev;                                   // submitted, not yet collected
             for (;;) {
                 unique_ptr<Chunk> ch = to_dev_.pop();
-                if (!ch) { to_out_.push(nullptr); return; }
                 const double t0 = now();
-                if (!failed_) align_chunk(*ch);
+                if (ch && !failed_) submit_chunk(*ch);                // chunk k+1 is uploaded while the kernels of chunk k run
+                if (prev) {
+                    if (!failed_) collect_chunk(*prev);
+                    if (g_prof) fprintf(stderr, "[cli prof] chunk of %zu collected after %.3f s\n", prev->cands.size(), now() - prev->t_submit);
+                    to_out_.push(std::move(prev));
+                }
                 g_t_dev += now() - t0;
-                if (g_prof) fprintf(stderr, "[cli prof] chunk of %zu aligned in %.3f s\n", ch->cands.size(), now() - t0);
-                to_out_.push(std::move(ch));
+                if (!ch) { to_out_.push(nullptr); return; }
+                prev = std::move(ch);
             }
         });
         out_ = thread([this] {

@@ -4,6 +4,8 @@
 // batched GPU execution: jobs are validated, expanded into single-mode aligners (-inv = INVL + auxiliary
 // INVR, AGEaligner.cpp:72-77,136-144), paired by shape, packed, swept and enumerated on the device(s), and
 // the compact results (score, breakpoints, diagonal blocks) are gathered on the host in input order.
+// Two batches can be in flight (age_submit / age_collect): while the kernels of one run, the next one is planned,
+// packed and copied to the device on a second stream, and the results of the previous one are read back.
 // There is no CPU implementation of the alignment here: without a usable CUDA device age_create() fails.
 #include "age_b200.h"
 #include "age_device.cuh"
@@ -83,19 +85,40 @@ struct HostPair {
     double cells;
 };
 
+// What one batch in flight owns on one device.  The big scratch arena (D planes, checkpoints, trace planes) is
+// shared by both slots of a device: kernels of consecutive batches run back to back on one stream.
+struct Slot {
+    Arena in, outbuf, aux;
+    PinnedBuf hin, hout;
+    cudaEvent_t ev[7] = {};      // 0/1 H2D begin/end (cp), 2 kernels begin, 3 sweeps end, 4 kernels end (st), 5/6 D2H begin/end (rb)
+    std::vector<int> pair_ids;   // the sub-batch resident in this slot
+    std::vector<PairTask> tasks;
+    std::vector<size_t> sc_off;
+    int n_outs = 0, pool_cap = 0, queue_cap = 0;
+    size_t in_bytes = 0, out_bytes = 0;
+};
+
 struct Device {
     int id = 0;
-    cudaStream_t st = nullptr;
-    Arena in, scratch, outbuf, aux;
-    int queue_cap = 0;
-    PinnedBuf hin, hout;
-    cudaEvent_t ev[6] = {};
-    // the sub-batch currently resident on this device
-    std::vector<int> pair_ids;
-    std::vector<PairTask> tasks;
-    int n_outs = 0, pool_cap = 0;
-    size_t in_bytes = 0;
+    cudaStream_t st = nullptr;   // kernels
+    cudaStream_t cp = nullptr;   // host -> device copies of the next batch
+    cudaStream_t rb = nullptr;   // device -> host read-back of the previous one
+    Arena scratch;
+    Slot slot[2];
     std::string err;
+};
+
+// The plan and the gathered results of one batch
+struct Batch {
+    size_t n_jobs = 0;
+    std::vector<int> job_status;
+    std::vector<Aligner> aligners;
+    std::vector<HostPair> pairs;
+    std::vector<AlignerOut> outs;                 // per aligner (global index)
+    std::vector<std::vector<age_block>> blocks;   // per aligner: left | right | alt_left | alt_right
+    std::vector<char> on_dev;                     // devices that hold an asynchronous sub-batch of this batch
+    age_stats stats{};
+    int state = 0;                                // 0 free, 1 in flight on the devices, 2 results gathered (oversize batch, run synchronously)
 };
 
 } // namespace
@@ -103,14 +126,10 @@ struct Device {
 struct age_ctx {
     std::vector<Device> devs;
     std::string err;
-    age_stats stats{};
-    // plan of the current batch
-    const age_job *jobs = nullptr; size_t n_jobs = 0;
-    std::vector<int> job_status;
-    std::vector<Aligner> aligners;
-    std::vector<HostPair> pairs;
-    std::vector<AlignerOut> outs;                 // per aligner (global index)
-    std::vector<std::vector<age_block>> blocks;   // per aligner: left | right | alt_left | alt_right
+    age_stats stats{};                            // of the batch collected last
+    Batch batch[2];
+    int head = 0;                                 // slot of the next age_submit
+    int in_flight = 0;
     bool staged = false;
     int host_threads = 1;
 };
@@ -142,11 +161,11 @@ int check_range(const age_job &j)
     return AGE_OK;
 }
 
-void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
+void build_plan(Batch *B, const age_job *jobs, size_t n)
 {
-    ctx->jobs = jobs; ctx->n_jobs = n;
-    ctx->job_status.assign(n, AGE_OK);
-    ctx->aligners.clear(); ctx->pairs.clear();
+    B->n_jobs = n;
+    B->job_status.assign(n, AGE_OK);
+    B->aligners.clear(); B->pairs.clear();
     for (size_t i = 0; i < n; ++i) {
         const age_job &j = jobs[i];
         int st = AGE_OK;
@@ -154,19 +173,19 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
         if (!j.seq1 || !j.seq2 || j.len1 <= 0 || j.len2 <= 0) st = AGE_NOT_ALIGNED;        // AGEaligner.cpp:68
         else if (!inv && !single_mode(j.flag)) st = AGE_NOT_ALIGNED;                         // AGEaligner.cpp:69
         else st = check_range(j);
-        ctx->job_status[i] = st;
+        B->job_status[i] = st;
         if (st != AGE_OK) continue;
         if (inv) {
-            ctx->aligners.push_back({(int)i, 0, F_INVL, -1});
-            ctx->aligners.push_back({(int)i, 1, F_INVR, -1});
-        } else ctx->aligners.push_back({(int)i, 0, j.flag, -1});
+            B->aligners.push_back({(int)i, 0, F_INVL, -1});
+            B->aligners.push_back({(int)i, 1, F_INVR, -1});
+        } else B->aligners.push_back({(int)i, 0, j.flag, -1});
     }
     // pair aligners of identical shape and scoring.  Selection pairs first: INVL+INVR of one -inv job
     // (AGEaligner.cpp:136-154) and mutual -both partners (age_align.cpp:264-278) share a warp, and only the
     // half that the reference would print is enumerated and traced back.
     struct Key { int32_t v[6]; };
     auto key = [&](int a) {
-        const age_job &j = jobs[ctx->aligners[a].job];
+        const age_job &j = jobs[B->aligners[a].job];
         return Key{{j.len1, j.len2, j.match, j.mismatch, j.gap_open, j.gap_extend}};
     };
     auto less = [&](int x, int y) { const Key a = key(x), b = key(y); return std::lexicographical_compare(a.v, a.v + 6, b.v, b.v + 6); };
@@ -174,11 +193,11 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
     auto add_pair = [&](int a0, int a1, int select) {
         HostPair hp{};
         hp.a[0] = a0; hp.a[1] = a1; hp.select = select;
-        const age_job &j = jobs[ctx->aligners[a0].job];
+        const age_job &j = jobs[B->aligners[a0].job];
         hp.len1 = j.len1; hp.len2 = j.len2;
         hp.nstrips = (j.len2 + STRIP - 1) / STRIP; hp.P = hp.nstrips * STRIP;
         hp.nb = (j.len1 + W - 1) / W; hp.nsteps = hp.nb + 31; hp.nwin = (hp.nsteps + CKS - 1) / CKS;
-        hp.k7 = (ctx->aligners[a0].flag != F_INDEL) || (a1 >= 0 && ctx->aligners[a1].flag != F_INDEL);
+        hp.k7 = (B->aligners[a0].flag != F_INDEL) || (a1 >= 0 && B->aligners[a1].flag != F_INDEL);
         const size_t slots = (size_t)hp.nstrips * hp.nsteps;                 // (strip, step) slots of the diagonal-major planes
         hp.in_bytes = 2 * (align_up((size_t)j.len1, 16) + align_up((size_t)j.len2, 16));   // raw sequences of both halves
         hp.scratch_bytes = align_up(slots * W * 2 * 32 * 16, 256) +
@@ -191,40 +210,40 @@ void build_plan(age_ctx *ctx, const age_job *jobs, size_t n)
         hp.set_bytes = p2_set_bytes(slots, (size_t)hp.nstrips * hp.nwin, (size_t)j.len2, hp.k7);
         hp.scratch_bytes += hp.nsets * hp.set_bytes;
         hp.cells = (double)j.len1 * j.len2;
-        ctx->pairs.push_back(hp);
+        B->pairs.push_back(hp);
     };
     std::vector<int> first_of(n, -1);
-    for (size_t a = 0; a < ctx->aligners.size(); ++a) if (ctx->aligners[a].role == 0) first_of[ctx->aligners[a].job] = (int)a;
-    std::vector<char> used(ctx->aligners.size(), 0);
-    for (size_t a = 0; a < ctx->aligners.size(); ++a) {
-        const Aligner &al = ctx->aligners[a];
+    for (size_t a = 0; a < B->aligners.size(); ++a) if (B->aligners[a].role == 0) first_of[B->aligners[a].job] = (int)a;
+    std::vector<char> used(B->aligners.size(), 0);
+    for (size_t a = 0; a < B->aligners.size(); ++a) {
+        const Aligner &al = B->aligners[a];
         if (used[a] || al.role != 0) continue;
         const age_job &j = jobs[al.job];
         if (j.flag == F_INV) { add_pair((int)a, (int)a + 1, 1); used[a] = used[a + 1] = 1; continue; }
         const int pj = j.partner;
-        if (pj > al.job && (size_t)pj < n && jobs[pj].partner == al.job && ctx->job_status[pj] == AGE_OK &&
+        if (pj > al.job && (size_t)pj < n && jobs[pj].partner == al.job && B->job_status[pj] == AGE_OK &&
             jobs[pj].flag != F_INV && same((int)a, first_of[pj])) {
             add_pair((int)a, first_of[pj], 1); used[a] = used[first_of[pj]] = 1;
         }
     }
     std::vector<int> order;
-    for (size_t i = 0; i < ctx->aligners.size(); ++i) if (!used[i]) order.push_back((int)i);
+    for (size_t i = 0; i < B->aligners.size(); ++i) if (!used[i]) order.push_back((int)i);
     std::stable_sort(order.begin(), order.end(), less);
     for (size_t i = 0; i < order.size();) {
         if (i + 1 < order.size() && same(order[i + 1], order[i])) { add_pair(order[i], order[i + 1], 0); i += 2; }
         else { add_pair(order[i], -1, 0); i += 1; }
     }
-    ctx->outs.assign(ctx->aligners.size(), AlignerOut{});
-    ctx->blocks.assign(ctx->aligners.size(), {});
+    B->outs.assign(B->aligners.size(), AlignerOut{});
+    B->blocks.assign(B->aligners.size(), {});
 }
 
 uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
 
 // Copy the raw sequences of pair `pi` into the pinned host blob at `h` (device address `d`) and fill its task record.
 // The column descriptors and row tables are derived from the raw strings on the device (age_pack_kernel).
-void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
+void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, PairTask &T)
 {
-    const HostPair &hp = ctx->pairs[pi];
+    const HostPair &hp = B->pairs[pi];
     memset(&T, 0, sizeof(T));
     T.len1 = hp.len1; T.len2 = hp.len2; T.nstrips = hp.nstrips; T.P = hp.P;
     T.select = hp.select; T.nb = hp.nb; T.nsteps = hp.nsteps; T.nwin = hp.nwin;
@@ -234,8 +253,8 @@ void pack_pair(age_ctx *ctx, int pi, char *h, char *d, PairTask &T)
     for (int k = 0; k < 2; ++k) {
         T.flag[k] = 0; T.out[k] = -1;
         if (hp.a[k] < 0) continue;
-        const Aligner &al = ctx->aligners[hp.a[k]];
-        const age_job &j = ctx->jobs[al.job];
+        const Aligner &al = B->aligners[hp.a[k]];
+        const age_job &j = jobs[al.job];
         T.flag[k] = al.flag; T.out[k] = al.out;
         if (k == 1 && first_seq1 == j.seq1) T.raw1[1] = T.raw1[0];          // -both / -inv halves share the window
         else { memcpy(h + off, j.seq1, hp.len1); T.raw1[k] = d + off; off += align_up(hp.len1, 16); first_seq1 = j.seq1; }
@@ -282,177 +301,209 @@ void assign_scratch(const HostPair &hp, char *s, PairTask &T)
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
-// stage one sub-batch (pair ids) on a device: pack, copy inputs, lay out scratch
-bool stage_on_device(age_ctx *ctx, Device &dev, const std::vector<int> &pair_ids_in)
+size_t out_bytes_of(int n_outs, int pool_cap)
+{
+    return align_up((size_t)n_outs * sizeof(AlignerOut), 256) + align_up((size_t)pool_cap * sizeof(Block), 256) + 256;
+}
+
+// stage one sub-batch (pair ids) in a slot of a device: pack, copy inputs (copy stream), lay out scratch
+bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, Slot &sl, const std::vector<int> &pair_ids_in)
 {
     CK(cudaSetDevice(dev.id));
     // longest pairs first: the persistent sweep kernel hands out pairs in this order, so its tail is made of short ones
-    dev.pair_ids = pair_ids_in;
-    std::stable_sort(dev.pair_ids.begin(), dev.pair_ids.end(), [&](int a, int b) { return ctx->pairs[a].cells * ctx->pairs[a].nstrips > ctx->pairs[b].cells * ctx->pairs[b].nstrips; });
-    const std::vector<int> &pair_ids = dev.pair_ids;
+    sl.pair_ids = pair_ids_in;
+    std::stable_sort(sl.pair_ids.begin(), sl.pair_ids.end(), [&](int a, int b) { return B.pairs[a].cells * B.pairs[a].nstrips > B.pairs[b].cells * B.pairs[b].nstrips; });
+    const std::vector<int> &pair_ids = sl.pair_ids;
     const size_t np = pair_ids.size();
-    dev.tasks.assign(np, PairTask{});
-    std::vector<size_t> in_off(np + 1, 0), sc_off(np + 1, 0);
+    sl.tasks.assign(np, PairTask{});
+    std::vector<size_t> in_off(np + 1, 0);
+    sl.sc_off.assign(np + 1, 0);
     int n_outs = 0;
-    for (size_t i = 0; i < np; ++i) {
-        HostPair &hp = ctx->pairs[pair_ids[i]];
-        in_off[i + 1] = in_off[i] + hp.in_bytes;
-        sc_off[i + 1] = sc_off[i] + hp.scratch_bytes;
-        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) ctx->aligners[hp.a[k]].out = n_outs++;
-    }
-    dev.n_outs = n_outs;
     size_t nwt_total = 0;
-    for (size_t i = 0; i < np; ++i) { const HostPair &hp = ctx->pairs[pair_ids[i]]; nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets; }
-    dev.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
-    if (const char *e = getenv("AGE_QUEUE_CAP")) dev.queue_cap = std::max(1, atoi(e));   // test knob: a short work list forces on-demand re-sweeps
+    for (size_t i = 0; i < np; ++i) {
+        HostPair &hp = B.pairs[pair_ids[i]];
+        in_off[i + 1] = in_off[i] + hp.in_bytes;
+        sl.sc_off[i + 1] = sl.sc_off[i] + hp.scratch_bytes;
+        nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets;
+        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.aligners[hp.a[k]].out = n_outs++;
+    }
+    sl.n_outs = n_outs;
+    sl.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
+    if (const char *e = getenv("AGE_QUEUE_CAP")) sl.queue_cap = std::max(1, atoi(e));   // test knob: a short work list forces on-demand re-sweeps
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
-    dev.in_bytes = task_bytes + in_off[np];
-    if (!dev.hin.ensure(dev.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
-    if (!dev.in.ensure(dev.in_bytes)) { dev.err = "device allocation failed (inputs)"; return false; }
-    if (!dev.scratch.ensure(sc_off[np] + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
-    dev.pool_cap = n_outs * 96 + 4096;
-    const size_t out_bytes = align_up((size_t)n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
-    if (!dev.outbuf.ensure(out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
-    if (!dev.hout.ensure(out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
-    if (!dev.aux.ensure(align_up(np * sizeof(PairHdr), 256) + (size_t)dev.queue_cap * sizeof(uint2))) { dev.err = "device allocation failed (work list)"; return false; }
+    sl.in_bytes = task_bytes + in_off[np];
+    if (!sl.hin.ensure(sl.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
+    if (!sl.in.ensure(sl.in_bytes)) { dev.err = "device allocation failed (inputs)"; return false; }
+    if (sl.sc_off[np] + 256 > dev.scratch.cap) {
+        CK(cudaStreamSynchronize(dev.st));               // the batch in flight still works in the arena that is about to move
+        if (!dev.scratch.ensure(sl.sc_off[np] + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
+    }
+    sl.pool_cap = n_outs * 96 + 4096;
+    if (const char *e = getenv("AGE_POOL_CAP")) sl.pool_cap = std::max(1, atoi(e));     // test knob: a small block pool forces the overflow re-run
+    sl.out_bytes = out_bytes_of(n_outs, sl.pool_cap);
+    if (!sl.outbuf.ensure(sl.out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
+    if (!sl.hout.ensure(sl.out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
+    if (!sl.aux.ensure(align_up(np * sizeof(PairHdr), 256) + (size_t)sl.queue_cap * sizeof(uint2))) { dev.err = "device allocation failed (work list)"; return false; }
     parallel_for(ctx->host_threads, np, [&](size_t i) {
-        pack_pair(ctx, pair_ids[i], dev.hin.ptr + task_bytes + in_off[i], dev.in.ptr + task_bytes + in_off[i], dev.tasks[i]);
-        assign_scratch(ctx->pairs[pair_ids[i]], dev.scratch.ptr + sc_off[i], dev.tasks[i]);
+        pack_pair(&B, jobs, pair_ids[i], sl.hin.ptr + task_bytes + in_off[i], sl.in.ptr + task_bytes + in_off[i], sl.tasks[i]);
+        assign_scratch(B.pairs[pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
     });
-    memcpy(dev.hin.ptr, dev.tasks.data(), np * sizeof(PairTask));
-    CK(cudaEventRecord(dev.ev[0], dev.st));
-    CK(cudaMemcpyAsync(dev.in.ptr, dev.hin.ptr, dev.in_bytes, cudaMemcpyHostToDevice, dev.st));
-    CK(cudaEventRecord(dev.ev[1], dev.st));
-    launch_pack((const PairTask *)dev.in.ptr, (int)np, dev.st);
+    memcpy(sl.hin.ptr, sl.tasks.data(), np * sizeof(PairTask));
+    CK(cudaEventRecord(sl.ev[0], dev.cp));
+    CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.in_bytes, cudaMemcpyHostToDevice, dev.cp));
+    CK(cudaEventRecord(sl.ev[1], dev.cp));
+    CK(cudaStreamWaitEvent(dev.st, sl.ev[1], 0));
+    launch_pack((const PairTask *)sl.in.ptr, (int)np, dev.st);
     return true;
 }
 
 struct OutLayout { AlignerOut *outs; Block *pool; int32_t *counters; };
-OutLayout out_layout(Device &dev, char *base)
+OutLayout out_layout(const Slot &sl, char *base)
 {
     OutLayout L;
     L.outs = (AlignerOut *)base;
-    L.pool = (Block *)(base + align_up((size_t)dev.n_outs * sizeof(AlignerOut), 256));
-    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)dev.pool_cap * sizeof(Block), 256));
+    L.pool = (Block *)(base + align_up((size_t)sl.n_outs * sizeof(AlignerOut), 256));
+    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)sl.pool_cap * sizeof(Block), 256));
     return L;
 }
 
-Pass2Params pass2_params(Device &dev, const OutLayout &L)
+Pass2Params pass2_params(Slot &sl, const OutLayout &L)
 {
     Pass2Params p{};
-    p.pairs = (const PairTask *)dev.in.ptr; p.n_pairs = (int)dev.tasks.size(); p.outs = L.outs;
-    p.hdr = (PairHdr *)dev.aux.ptr;
-    p.queue = (uint2 *)(dev.aux.ptr + align_up(dev.tasks.size() * sizeof(PairHdr), 256)); p.queue_cap = dev.queue_cap; p.queue_n = L.counters + 12;
-    p.pool = L.pool; p.pool_cap = dev.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 4;   // next: 8 ints
+    p.pairs = (const PairTask *)sl.in.ptr; p.n_pairs = (int)sl.tasks.size(); p.outs = L.outs;
+    p.hdr = (PairHdr *)sl.aux.ptr;
+    p.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)); p.queue_cap = sl.queue_cap; p.queue_n = L.counters + 12;
+    p.pool = L.pool; p.pool_cap = sl.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 4;   // next: 8 ints
     return p;
 }
 
-bool run_on_device(age_ctx *, Device &dev)
+// all kernels of the slot's sub-batch on the compute stream
+bool run_on_device(Device &dev, Slot &sl)
 {
     CK(cudaSetDevice(dev.id));
-    const int np = (int)dev.tasks.size();
-    OutLayout L = out_layout(dev, dev.outbuf.ptr);
+    const int np = (int)sl.tasks.size();
+    OutLayout L = out_layout(sl, sl.outbuf.ptr);
     CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
-    CK(cudaEventRecord(dev.ev[2], dev.st));
+    CK(cudaEventRecord(sl.ev[2], dev.st));
     int max_strips = 1;
-    for (const PairTask &t : dev.tasks) max_strips = std::max(max_strips, (int)t.nstrips);
-    launch_sweeps((const PairTask *)dev.in.ptr, np, max_strips, L.counters + 0, dev.st);
-    CK(cudaEventRecord(dev.ev[3], dev.st));
-    launch_pass2(pass2_params(dev, L), dev.st);
-    CK(cudaEventRecord(dev.ev[4], dev.st));
+    for (const PairTask &t : sl.tasks) max_strips = std::max(max_strips, (int)t.nstrips);
+    launch_sweeps((const PairTask *)sl.in.ptr, np, max_strips, L.counters + 0, dev.st);
+    CK(cudaEventRecord(sl.ev[3], dev.st));
+    launch_pass2(pass2_params(sl, L), dev.st);
+    CK(cudaEventRecord(sl.ev[4], dev.st));
     CK(cudaGetLastError());
     return true;
 }
 
-bool fetch_from_device(age_ctx *ctx, Device &dev)
+// result read-back on the copy stream, behind the kernels
+bool enqueue_fetch(Device &dev, Slot &sl)
+{
+    CK(cudaSetDevice(dev.id));
+    CK(cudaStreamWaitEvent(dev.rb, sl.ev[4], 0));
+    CK(cudaEventRecord(sl.ev[5], dev.rb));
+    CK(cudaMemcpyAsync(sl.hout.ptr, sl.outbuf.ptr, sl.out_bytes, cudaMemcpyDeviceToHost, dev.rb));
+    CK(cudaEventRecord(sl.ev[6], dev.rb));
+    return true;
+}
+
+// The block pool of the slot was too small: run its sub-batch again with a larger one.  A later batch may have used
+// (or moved) the scratch arena in the meantime, so the sweeps are repeated as well; the packed inputs are still resident.
+bool rerun_with_pool(Batch &B, Device &dev, Slot &sl, int pool_cap)
+{
+    CK(cudaStreamSynchronize(dev.st));
+    CK(cudaStreamSynchronize(dev.rb));
+    sl.pool_cap = pool_cap;
+    sl.out_bytes = out_bytes_of(sl.n_outs, sl.pool_cap);
+    if (!sl.outbuf.ensure(sl.out_bytes) || !sl.hout.ensure(sl.out_bytes)) { dev.err = "allocation failed (block pool)"; return false; }
+    if (sl.sc_off.back() + 256 > dev.scratch.cap && !dev.scratch.ensure(sl.sc_off.back() + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
+    for (size_t i = 0; i < sl.tasks.size(); ++i) assign_scratch(B.pairs[sl.pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
+    memcpy(sl.hin.ptr, sl.tasks.data(), sl.tasks.size() * sizeof(PairTask));
+    CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, dev.st));
+    launch_pack((const PairTask *)sl.in.ptr, (int)sl.tasks.size(), dev.st);
+    return run_on_device(dev, sl) && enqueue_fetch(dev, sl);
+}
+
+// wait for the slot's results and gather them into the batch
+bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
 {
     CK(cudaSetDevice(dev.id));
     for (int attempt = 0; attempt < 4; ++attempt) {
-        const size_t out_bytes = align_up((size_t)dev.n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
-        CK(cudaMemcpyAsync(dev.hout.ptr, dev.outbuf.ptr, out_bytes, cudaMemcpyDeviceToHost, dev.st));
-        CK(cudaEventRecord(dev.ev[5], dev.st));
-        CK(cudaStreamSynchronize(dev.st));
-        OutLayout H = out_layout(dev, dev.hout.ptr);
-        if (H.counters[2] <= dev.pool_cap) {
-            for (size_t i = 0; i < dev.pair_ids.size(); ++i) {
-                const HostPair &hp = ctx->pairs[dev.pair_ids[i]];
-                for (int k = 0; k < 2; ++k) {
-                    if (hp.a[k] < 0) continue;
-                    const Aligner &al = ctx->aligners[hp.a[k]];
-                    const AlignerOut &o = H.outs[al.out];
-                    memcpy(&ctx->outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
-                    std::vector<age_block> &b = ctx->blocks[hp.a[k]];
-                    b.clear();
-                    for (int q = 0; q < 4; ++q)
-                        for (int x = 0; x < o.n_blk[q]; ++x) {
-                            const Block &s = H.pool[o.blk_off[q] + x];
-                            b.push_back(age_block{s.start1, s.start2, s.length});
-                        }
-                }
-            }
-            ctx->stats.d2h_bytes += out_bytes;
-            return true;
+        CK(cudaEventSynchronize(sl.ev[6]));
+        OutLayout H = out_layout(sl, sl.hout.ptr);
+        if (H.counters[2] > sl.pool_cap) {
+            if (!rerun_with_pool(B, dev, sl, H.counters[2] + 4096)) return false;
+            st.launches += 9; st.fill_launches += 1;
+            continue;
         }
-        // block pool overflow: enlarge and repeat pass 2 (the sweep outputs are still resident)
-        dev.pool_cap = H.counters[2] + 4096;
-        const size_t nb = align_up((size_t)dev.n_outs * sizeof(AlignerOut), 256) + align_up((size_t)dev.pool_cap * sizeof(Block), 256) + 256;
-        if (!dev.outbuf.ensure(nb) || !dev.hout.ensure(nb)) { dev.err = "allocation failed (block pool)"; return false; }
-        OutLayout L = out_layout(dev, dev.outbuf.ptr);
-        CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
-        launch_pass2(pass2_params(dev, L), dev.st);
+        for (size_t i = 0; i < sl.pair_ids.size(); ++i) {
+            const HostPair &hp = B.pairs[sl.pair_ids[i]];
+            for (int k = 0; k < 2; ++k) {
+                if (hp.a[k] < 0) continue;
+                const Aligner &al = B.aligners[hp.a[k]];
+                const AlignerOut &o = H.outs[al.out];
+                memcpy(&B.outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
+                std::vector<age_block> &b = B.blocks[hp.a[k]];
+                b.clear();
+                for (int q = 0; q < 4; ++q)
+                    for (int x = 0; x < o.n_blk[q]; ++x) {
+                        const Block &s = H.pool[o.blk_off[q] + x];
+                        b.push_back(age_block{s.start1, s.start2, s.length});
+                    }
+            }
+        }
+        float ms = 0;
+        st.h2d_bytes += sl.in_bytes; st.d2h_bytes += sl.out_bytes;
+        if (cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[1]) == cudaSuccess) st.h2d_ms += ms;
+        if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) st.fill_ms += ms;
+        if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) st.kernel_ms += ms;
+        if (cudaEventElapsedTime(&ms, sl.ev[5], sl.ev[6]) == cudaSuccess) st.d2h_ms += ms;
+        st.launches += 8; st.fill_launches += 1;
+        return true;
     }
     dev.err = "block pool overflow";
     return false;
 }
 
-void add_timing(age_ctx *ctx, Device &dev)
-{
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, dev.ev[0], dev.ev[1]) == cudaSuccess) ctx->stats.h2d_ms += ms;
-    if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) ctx->stats.fill_ms += ms;
-    if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) ctx->stats.kernel_ms += ms;
-    if (cudaEventElapsedTime(&ms, dev.ev[4], dev.ev[5]) == cudaSuccess) ctx->stats.d2h_ms += ms;
-}
-
 // split the pairs of the plan into per-device sub-batches that fit the scratch budget
-std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
+std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx, const Batch &B, int slot)
 {
     const int nd = (int)ctx->devs.size();
     std::vector<std::vector<std::vector<int>>> res(nd);
     std::vector<size_t> budget(nd, 0);
     auto query_budget = [&](int d) {             // cudaMemGetInfo costs milliseconds: only asked when a batch outgrows the arenas
-        cudaSetDevice(ctx->devs[d].id);
+        Device &dev = ctx->devs[d];
+        cudaSetDevice(dev.id);
         size_t fr = 0, tot = 0;
         cudaMemGetInfo(&fr, &tot);
-        fr += ctx->devs[d].scratch.cap + ctx->devs[d].in.cap + ctx->devs[d].outbuf.cap + ctx->devs[d].aux.cap;
+        fr += dev.scratch.cap + dev.slot[slot].in.cap + dev.slot[slot].outbuf.cap + dev.slot[slot].aux.cap;
         budget[d] = (size_t)(0.85 * (double)fr);
     };
     // longest-processing-time-first deal across devices
-    std::vector<int> order(ctx->pairs.size());
+    std::vector<int> order(B.pairs.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::vector<std::vector<int>> per_dev(nd);
     if (nd == 1) per_dev[0] = order;
     else {
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ctx->pairs[a].cells > ctx->pairs[b].cells; });
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return B.pairs[a].cells > B.pairs[b].cells; });
         std::vector<double> load(nd, 0.0);
         for (int pi : order) {
             int best = 0;
             for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
-            per_dev[best].push_back(pi); load[best] += ctx->pairs[pi].cells;
+            per_dev[best].push_back(pi); load[best] += B.pairs[pi].cells;
         }
         for (auto &v : per_dev) std::sort(v.begin(), v.end());
     }
     for (int d = 0; d < nd; ++d) {
         size_t sc = 256, in = align_up(per_dev[d].size() * sizeof(PairTask), 256);
-        for (int pi : per_dev[d]) { sc += ctx->pairs[pi].scratch_bytes; in += ctx->pairs[pi].in_bytes; }
-        if (sc <= ctx->devs[d].scratch.cap && in <= ctx->devs[d].in.cap) {        // fits what is already allocated
+        for (int pi : per_dev[d]) { sc += B.pairs[pi].scratch_bytes; in += B.pairs[pi].in_bytes; }
+        if (sc <= ctx->devs[d].scratch.cap && in <= ctx->devs[d].slot[slot].in.cap) {        // fits what is already allocated
             if (!per_dev[d].empty()) res[d].push_back(per_dev[d]);
             continue;
         }
         query_budget(d);
         std::vector<int> cur; size_t used = 0;
         for (int pi : per_dev[d]) {
-            const size_t need = ctx->pairs[pi].scratch_bytes + ctx->pairs[pi].in_bytes + 4096;
+            const size_t need = B.pairs[pi].scratch_bytes + B.pairs[pi].in_bytes + 4096;
             if (!cur.empty() && used + need > budget[d]) { res[d].push_back(cur); cur.clear(); used = 0; }
             cur.push_back(pi); used += need;
         }
@@ -461,18 +512,19 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx)
     return res;
 }
 
-void account(age_ctx *ctx)
+void account(Batch &B)
 {
-    ctx->stats.n_aligners += ctx->aligners.size();
-    for (const HostPair &hp : ctx->pairs)
-        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) ctx->stats.cell_updates += (uint64_t)(2.0 * hp.cells);
+    B.stats.n_aligners = B.aligners.size();
+    B.stats.cell_updates = 0;
+    for (const HostPair &hp : B.pairs)
+        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.stats.cell_updates += (uint64_t)(2.0 * hp.cells);
 }
 
-void assemble(age_ctx *ctx, age_result *out, size_t n)
+void assemble(const Batch &B, age_result *out, size_t n)
 {
     std::vector<int> main_of(n, -1), aux_of(n, -1);
-    for (size_t a = 0; a < ctx->aligners.size(); ++a) {
-        const Aligner &al = ctx->aligners[a];
+    for (size_t a = 0; a < B.aligners.size(); ++a) {
+        const Aligner &al = B.aligners[a];
         (al.role ? aux_of : main_of)[al.job] = (int)a;
     }
     for (size_t i = 0; i < n; ++i) {
@@ -480,29 +532,120 @@ void assemble(age_ctx *ctx, age_result *out, size_t n)
         memset(&r, 0, offsetof(age_result, bp));          // header only: bp rows beyond n_bp are not part of the result
         r.alt_index = -1; r.n_left = r.n_right = r.n_alt_left = r.n_alt_right = 0;
         r.left = r.right = r.alt_left = r.alt_right = nullptr;
-        r.status = ctx->job_status[i];
+        r.status = B.job_status[i];
         r.aux_score = -1;
         if (r.status != AGE_OK) continue;
         const int m = main_of[i], x = aux_of[i];
-        const AlignerOut &om = ctx->outs[m];
+        const AlignerOut &om = B.outs[m];
         r.main_score = om.score;
         int pick = m;
         if (x >= 0) {
-            r.aux_score = ctx->outs[x].score;
-            if (ctx->outs[x].score > om.score) { pick = x; r.used_aux = 1; }       // AGEaligner.cpp:151,181-184
+            r.aux_score = B.outs[x].score;
+            if (B.outs[x].score > om.score) { pick = x; r.used_aux = 1; }       // AGEaligner.cpp:151,181-184
         }
-        const AlignerOut &o = ctx->outs[pick];
+        const AlignerOut &o = B.outs[pick];
         if (o.status != 0) { r.status = AGE_ERR_CUDA; continue; }
-        r.score = o.score; r.flag = ctx->aligners[pick].flag;
+        r.score = o.score; r.flag = B.aligners[pick].flag;
         if (o.n_bp < 0) continue;                                  // lost the -both selection: score only
         r.detail = 1;
         r.n_bp = o.n_bp;
         memcpy(r.bp, o.bp, sizeof(r.bp[0]) * (size_t)std::max(o.n_bp, 0));
         r.alt_index = o.alt_index;
         r.n_left = o.n_blk[0]; r.n_right = o.n_blk[1]; r.n_alt_left = o.n_blk[2]; r.n_alt_right = o.n_blk[3];
-        const age_block *b = ctx->blocks[pick].data();
+        const age_block *b = B.blocks[pick].data();
         r.left = b; r.right = b + r.n_left; r.alt_left = r.right + r.n_right; r.alt_right = r.alt_left + r.n_alt_left;
     }
+}
+
+// devices run concurrently: report the slowest one for the time-like fields, sums for the counters
+void merge_stats(age_stats &to, const std::vector<age_stats> &per_dev)
+{
+    for (const age_stats &s : per_dev) {
+        to.kernel_ms = std::max(to.kernel_ms, s.kernel_ms); to.fill_ms = std::max(to.fill_ms, s.fill_ms);
+        to.h2d_ms = std::max(to.h2d_ms, s.h2d_ms); to.d2h_ms = std::max(to.d2h_ms, s.d2h_ms);
+        to.h2d_bytes += s.h2d_bytes; to.d2h_bytes += s.d2h_bytes; to.launches += s.launches; to.fill_launches += s.fill_launches;
+    }
+}
+
+template <class F> bool for_each_device(age_ctx *ctx, F f)        // f(d) -> bool, one host thread per device
+{
+    const int nd = (int)ctx->devs.size();
+    std::vector<char> ok(nd, 1);
+    if (nd == 1) ok[0] = f(0);
+    else {
+        std::vector<std::thread> th;
+        for (int d = 0; d < nd; ++d) th.emplace_back([&, d] { ok[d] = f(d); });
+        for (auto &t : th) t.join();
+    }
+    for (int d = 0; d < nd; ++d) if (!ok[d]) { ctx->err = ctx->devs[d].err; return false; }
+    return true;
+}
+
+// plan + stage + launch; the batch lands in slot ctx->head
+int submit(age_ctx *ctx, const age_job *jobs, size_t n)
+{
+    const int s = ctx->head;
+    Batch &B = ctx->batch[s];
+    if (B.state != 0) { ctx->err = "two batches are already in flight: call age_collect first"; return AGE_ERR_ARG; }
+    const double t0 = wall_ms();
+    B.stats = age_stats{};
+    build_plan(&B, jobs, n);
+    const double t1 = wall_ms();
+    auto sub = make_subbatches(ctx, B, s);
+    const int nd = (int)ctx->devs.size();
+    bool single = true;
+    for (int d = 0; d < nd; ++d) single = single && sub[d].size() <= 1;
+    B.on_dev.assign(nd, 0);
+    std::vector<age_stats> dstat(nd);
+    bool ok;
+    if (single) {                 // the common case: asynchronous, collected later
+        ok = for_each_device(ctx, [&](int d) {
+            if (sub[d].empty()) return true;
+            Device &dev = ctx->devs[d];
+            B.on_dev[d] = 1;
+            return stage_on_device(ctx, B, jobs, dev, dev.slot[s], sub[d][0]) && run_on_device(dev, dev.slot[s]) && enqueue_fetch(dev, dev.slot[s]);
+        });
+        B.state = 1;
+    } else {                      // larger than the device memory: piece by piece, synchronously
+        ok = for_each_device(ctx, [&](int d) {
+            Device &dev = ctx->devs[d];
+            for (auto &ids : sub[d])
+                if (!stage_on_device(ctx, B, jobs, dev, dev.slot[s], ids) || !run_on_device(dev, dev.slot[s]) || !enqueue_fetch(dev, dev.slot[s]) ||
+                    !finish_fetch(B, dev, dev.slot[s], dstat[d])) return false;
+            return true;
+        });
+        merge_stats(B.stats, dstat);
+        B.state = 2;
+    }
+    if (!ok) { B.state = 0; return AGE_ERR_CUDA; }
+    ctx->head ^= 1; ctx->in_flight += 1;
+    if (g_hprof) fprintf(stderr, "[host prof] submit: plan %.2f ms, sub-batching + stage + launch %.2f ms\n", t1 - t0, wall_ms() - t1);
+    return 0;
+}
+
+// wait for the oldest batch in flight and hand its results out
+int collect(age_ctx *ctx, age_result *out, size_t n)
+{
+    if (ctx->in_flight <= 0) { ctx->err = "no batch in flight"; return AGE_ERR_ARG; }
+    const int s = ctx->in_flight == 2 ? ctx->head : ctx->head ^ 1;
+    Batch &B = ctx->batch[s];
+    if (n != B.n_jobs) { ctx->err = "age_collect: n differs from the submitted batch"; return AGE_ERR_ARG; }
+    const double t0 = wall_ms();
+    bool ok = true;
+    if (B.state == 1) {
+        const int nd = (int)ctx->devs.size();
+        std::vector<age_stats> dstat(nd);
+        ok = for_each_device(ctx, [&](int d) { return !B.on_dev[d] || finish_fetch(B, ctx->devs[d], ctx->devs[d].slot[s], dstat[d]); });
+        merge_stats(B.stats, dstat);
+    }
+    B.state = 0; ctx->in_flight -= 1;
+    if (!ok) return AGE_ERR_CUDA;
+    const double t1 = wall_ms();
+    account(B);
+    assemble(B, out, n);
+    ctx->stats = B.stats;
+    if (g_hprof) fprintf(stderr, "[host prof] collect: wait + gather %.2f ms, assemble %.2f ms; kernels %.2f ms\n", t1 - t0, wall_ms() - t1, B.stats.kernel_ms);
+    return 0;
 }
 
 } // namespace
@@ -529,8 +672,11 @@ extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
         ctx->devs.push_back(d);
     }
     for (Device &d : ctx->devs) {
-        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) == cudaSuccess;
-        for (int e = 0; ok && e < 6; ++e) ok = cudaEventCreate(&d.ev[e]) == cudaSuccess;
+        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.rb, cudaStreamNonBlocking) == cudaSuccess;
+        for (Slot &sl : d.slot)
+            for (int e = 0; ok && e < 7; ++e) ok = cudaEventCreate(&sl.ev[e]) == cudaSuccess;
         if (!ok) { g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); age_destroy(ctx); return nullptr; }
     }
     if (g_hprof) fprintf(stderr, "[host prof] age_create %.1f ms\n", wall_ms() - t_create);
@@ -543,98 +689,72 @@ extern "C" void age_destroy(age_ctx *ctx)
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
         if (d.st) cudaStreamSynchronize(d.st);
-        d.in.release(); d.scratch.release(); d.outbuf.release(); d.aux.release(); d.hin.release(); d.hout.release();
-        for (auto &e : d.ev) if (e) cudaEventDestroy(e);
+        if (d.cp) cudaStreamSynchronize(d.cp);
+        if (d.rb) cudaStreamSynchronize(d.rb);
+        d.scratch.release();
+        for (Slot &sl : d.slot) {
+            sl.in.release(); sl.outbuf.release(); sl.aux.release(); sl.hin.release(); sl.hout.release();
+            for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
+        }
         if (d.st) cudaStreamDestroy(d.st);
+        if (d.cp) cudaStreamDestroy(d.cp);
+        if (d.rb) cudaStreamDestroy(d.rb);
     }
     delete ctx;
 }
 
 extern "C" const char *age_last_error(const age_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-static int run_plan(age_ctx *ctx, age_result *out, size_t n)
+extern "C" int age_submit(age_ctx *ctx, const age_job *jobs, size_t n)
 {
-    static const bool hprof = getenv("AGE_HOST_PROF") != nullptr;
-    double tp[6] = {0, 0, 0, 0, 0, 0};
-    const double tsub = wall_ms();
-    auto sub = make_subbatches(ctx);
-    tp[3] = wall_ms() - tsub;
-    const int nd = (int)ctx->devs.size();
-    std::vector<int> rc(nd, 0);
-    std::vector<age_stats> dstat(nd);
-    auto worker = [&](int d) {
-        Device &dev = ctx->devs[d];
-        for (auto &ids : sub[d]) {
-            if (!stage_on_device(ctx, dev, ids) || !run_on_device(ctx, dev) || !fetch_from_device(ctx, dev)) { rc[d] = AGE_ERR_CUDA; return; }
-            float ms = 0;
-            dstat[d].h2d_bytes += dev.in_bytes;
-            if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) dstat[d].fill_ms += ms;
-            if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) dstat[d].kernel_ms += ms;
-        }
-    };
-    // timing is accumulated after the join (stats are not thread-safe)
-    if (nd == 1) {
-        Device &dev = ctx->devs[0];
-        for (auto &ids : sub[0]) {
-            double t0 = wall_ms();
-            bool ok = stage_on_device(ctx, dev, ids);
-            if (hprof) { cudaStreamSynchronize(dev.st); tp[0] += wall_ms() - t0; t0 = wall_ms(); }
-            ok = ok && run_on_device(ctx, dev);
-            if (hprof) { cudaStreamSynchronize(dev.st); tp[1] += wall_ms() - t0; t0 = wall_ms(); }
-            ok = ok && fetch_from_device(ctx, dev);
-            if (hprof) tp[2] += wall_ms() - t0;
-            if (!ok) { rc[0] = AGE_ERR_CUDA; break; }
-            ctx->stats.h2d_bytes += dev.in_bytes; ctx->stats.launches += 8; ctx->stats.fill_launches += 1;
-            add_timing(ctx, dev);
-        }
-    } else {
-        std::vector<std::thread> th;
-        for (int d = 0; d < nd; ++d) th.emplace_back(worker, d);
-        for (auto &t : th) t.join();
-        for (int d = 0; d < nd; ++d) {      // devices run concurrently: report the slowest one
-            ctx->stats.launches += 8 * sub[d].size(); ctx->stats.fill_launches += sub[d].size();
-            ctx->stats.h2d_bytes += dstat[d].h2d_bytes;
-            ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, dstat[d].kernel_ms);
-            ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, dstat[d].fill_ms);
-        }
-    }
-    for (int d = 0; d < nd; ++d)
-        if (rc[d]) { ctx->err = ctx->devs[d].err; return rc[d]; }
-    account(ctx);
-    double t0 = wall_ms();
-    assemble(ctx, out, n);
-    if (hprof) fprintf(stderr, "[host prof] sub-batching %.2f ms, stage(pack+H2D) %.2f ms, kernels %.2f ms, fetch(D2H+copy) %.2f ms, assemble %.2f ms\n", tp[3], tp[0], tp[1], tp[2], wall_ms() - t0);
-    return 0;
+    if (!ctx || (!jobs && n)) return AGE_ERR_ARG;
+    ctx->staged = false;
+    return submit(ctx, jobs, n);
 }
+
+extern "C" int age_collect(age_ctx *ctx, age_result *out, size_t n)
+{
+    if (!ctx || (!out && n)) return AGE_ERR_ARG;
+    return collect(ctx, out, n);
+}
+
+extern "C" int age_in_flight(const age_ctx *ctx) { return ctx ? ctx->in_flight : 0; }
 
 extern "C" int age_align_batch(age_ctx *ctx, const age_job *jobs, size_t n, age_result *out)
 {
     if (!ctx || (!jobs && n) || (!out && n)) return AGE_ERR_ARG;
-    ctx->stats = age_stats{};
+    if (ctx->in_flight) { ctx->err = "age_align_batch: batches are in flight (age_submit without age_collect)"; return AGE_ERR_ARG; }
     ctx->staged = false;
     const double tb = wall_ms();
-    build_plan(ctx, jobs, n);
-    const double tplan = wall_ms() - tb;
-    const int rc = run_plan(ctx, out, n);
-    if (getenv("AGE_HOST_PROF")) fprintf(stderr, "[host prof] plan %.2f ms, age_align_batch total %.2f ms\n", tplan, wall_ms() - tb);
+    int rc = submit(ctx, jobs, n);
+    if (rc == 0) rc = collect(ctx, out, n);
+    if (g_hprof) fprintf(stderr, "[host prof] age_align_batch total %.2f ms\n", wall_ms() - tb);
     return rc;
 }
 
+// ---- split form: inputs staged once, kernels repeatable (measurement) --------------------------------------
 extern "C" int age_stage(age_ctx *ctx, const age_job *jobs, size_t n)
 {
     if (!ctx || (!jobs && n)) return AGE_ERR_ARG;
-    ctx->stats = age_stats{};
+    if (ctx->in_flight) { ctx->err = "age_stage: batches are in flight"; return AGE_ERR_ARG; }
     ctx->staged = false;
-    build_plan(ctx, jobs, n);
-    auto sub = make_subbatches(ctx);
+    ctx->head = 0;
+    Batch &B = ctx->batch[0];
+    B.stats = age_stats{};
+    build_plan(&B, jobs, n);
+    auto sub = make_subbatches(ctx, B, 0);
+    B.on_dev.assign(ctx->devs.size(), 0);
     for (size_t d = 0; d < ctx->devs.size(); ++d) {
         if (sub[d].size() > 1) { ctx->err = "batch does not fit in device memory in one piece; use age_align_batch"; return AGE_ERR_ARG; }
         Device &dev = ctx->devs[d];
-        if (sub[d].empty()) { dev.pair_ids.clear(); dev.tasks.clear(); dev.n_outs = 0; continue; }
-        if (!stage_on_device(ctx, dev, sub[d][0])) { ctx->err = dev.err; return AGE_ERR_CUDA; }
-        ctx->stats.h2d_bytes += dev.in_bytes;
+        Slot &sl = dev.slot[0];
+        if (sub[d].empty()) { sl.pair_ids.clear(); sl.tasks.clear(); sl.n_outs = 0; continue; }
+        if (!stage_on_device(ctx, B, jobs, dev, sl, sub[d][0])) { ctx->err = dev.err; return AGE_ERR_CUDA; }
+        B.on_dev[d] = 1;
+        B.stats.h2d_bytes += sl.in_bytes;
     }
-    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.st); }
+    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.cp); cudaStreamSynchronize(dev.st); }
+    ctx->stats = B.stats;
     ctx->staged = true;
     return 0;
 }
@@ -642,18 +762,22 @@ extern "C" int age_stage(age_ctx *ctx, const age_job *jobs, size_t n)
 extern "C" int age_run_staged(age_ctx *ctx)
 {
     if (!ctx || !ctx->staged) return AGE_ERR_ARG;
-    for (Device &dev : ctx->devs) {
-        if (dev.tasks.empty()) continue;
-        if (!run_on_device(ctx, dev)) { ctx->err = dev.err; return AGE_ERR_CUDA; }
+    Batch &B = ctx->batch[0];
+    for (size_t d = 0; d < ctx->devs.size(); ++d) {
+        Device &dev = ctx->devs[d];
+        if (!B.on_dev[d]) continue;
+        if (!run_on_device(dev, dev.slot[0])) { ctx->err = dev.err; return AGE_ERR_CUDA; }
     }
     ctx->stats.kernel_ms = 0; ctx->stats.fill_ms = 0;
-    for (Device &dev : ctx->devs) {
-        if (dev.tasks.empty()) continue;
+    for (size_t d = 0; d < ctx->devs.size(); ++d) {
+        Device &dev = ctx->devs[d];
+        if (!B.on_dev[d]) continue;
+        Slot &sl = dev.slot[0];
         cudaSetDevice(dev.id);
         if (cudaStreamSynchronize(dev.st) != cudaSuccess) { ctx->err = cudaGetErrorString(cudaGetLastError()); return AGE_ERR_CUDA; }
         float ms = 0;
-        if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
-        if (cudaEventElapsedTime(&ms, dev.ev[2], dev.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
+        if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
+        if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
     }
     ctx->stats.launches += 8; ctx->stats.fill_launches += 1;
     return 0;
@@ -661,14 +785,18 @@ extern "C" int age_run_staged(age_ctx *ctx)
 
 extern "C" int age_fetch(age_ctx *ctx, age_result *out, size_t n)
 {
-    if (!ctx || !ctx->staged || n != ctx->n_jobs || (!out && n)) return AGE_ERR_ARG;
-    for (Device &dev : ctx->devs) {
-        if (dev.tasks.empty()) continue;
-        if (!fetch_from_device(ctx, dev)) { ctx->err = dev.err; return AGE_ERR_CUDA; }
+    if (!ctx || !ctx->staged || n != ctx->batch[0].n_jobs || (!out && n)) return AGE_ERR_ARG;
+    Batch &B = ctx->batch[0];
+    age_stats scratch_stats{};
+    for (size_t d = 0; d < ctx->devs.size(); ++d) {
+        Device &dev = ctx->devs[d];
+        if (!B.on_dev[d]) continue;
+        if (!enqueue_fetch(dev, dev.slot[0]) || !finish_fetch(B, dev, dev.slot[0], scratch_stats)) { ctx->err = dev.err; return AGE_ERR_CUDA; }
     }
-    ctx->stats.n_aligners = 0; ctx->stats.cell_updates = 0;
-    account(ctx);
-    assemble(ctx, out, n);
+    ctx->stats.d2h_bytes = scratch_stats.d2h_bytes;
+    account(B);
+    ctx->stats.n_aligners = B.stats.n_aligners; ctx->stats.cell_updates = B.stats.cell_updates;
+    assemble(B, out, n);
     return 0;
 }
 
@@ -679,4 +807,4 @@ extern "C" int age_get_stats(const age_ctx *ctx, age_stats *st)
     return 0;
 }
 
-extern "C" const char *age_version(void) { return "age-b200 0.1 (sm_100a)"; }
+extern "C" const char *age_version(void) { return "age-b200 0.2 (sm_100a)"; }

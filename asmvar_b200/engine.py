@@ -80,6 +80,36 @@ class Engine:
     def aligner_summary(self, seq1: bytes, seq2: bytes, flag: int, match: int, mismatch: int, go: int, ge: int) -> dict:
         return self.align([(seq1, seq2, flag, match, mismatch, go, ge)])[0]
 
+    # streaming form: up to two batches in flight (age_submit / age_collect)
+    def submit(self, arr, n: int):
+        self._check(self.lib.age_submit(self.ctx, arr, n), "age_submit")
+
+    def collect(self, n: int, out=None):
+        """Results of the oldest batch in flight (block pointers valid until the second submit after its own)."""
+        res = out if out is not None else (capi.AgeResult * max(1, n))()
+        self._check(self.lib.age_collect(self.ctx, res, n), "age_collect")
+        return res
+
+    def in_flight(self) -> int:
+        return self.lib.age_in_flight(self.ctx)
+
+    def align_stream(self, batches: Iterable[Iterable[tuple]]):
+        """The candidate loop of age_align.cpp:231-293 over a stream of batches: yields one list of result
+        summaries per batch, in order, with the next batch already on the device while one is computed."""
+        pending = []
+        for jobs in batches:
+            arr, keep, n = self.make_jobs(jobs)
+            self.submit(arr, n)
+            pending.append(n)
+            if len(pending) == 2:
+                n0 = pending.pop(0)
+                res = self.collect(n0)
+                yield [res[i].summary() for i in range(n0)]
+        while pending:
+            n0 = pending.pop(0)
+            res = self.collect(n0)
+            yield [res[i].summary() for i in range(n0)]
+
     # split form used by bench.py (inputs resident in HBM when the timed region starts)
     def stage(self, arr, n: int):
         self._check(self.lib.age_stage(self.ctx, arr, n), "age_stage")

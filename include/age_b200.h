@@ -68,7 +68,7 @@ typedef struct {
     int32_t alt_index;                  /* bpoint shown under ALTERNATIVE REGION(S), -1 if none (AGEaligner.cpp:287-306) */
     int32_t n_left, n_right;            /* findLeftBlocks / findRightBlocks of bpoint 0 (AGEaligner.cpp:752-860) */
     int32_t n_alt_left, n_alt_right;    /* the same for bpoint alt_index */
-    const age_block *left, *right, *alt_left, *alt_right;  /* owned by the ctx, valid until the next batch call */
+    const age_block *left, *right, *alt_left, *alt_right;  /* owned by the ctx, valid until the next age_align_batch / age_stage call (age_submit: see there) */
 } age_result;
 
 /* A Sequence header: name, 1-based start coordinate and orientation (Sequence.hh:22-31). */
@@ -101,6 +101,16 @@ const char *age_last_error(const age_ctx *ctx);   /* ctx may be NULL: error of t
  * n independent AGEaligner::align() calls executed as length-binned GPU batches.
  * jobs and out are HOST arrays; returns 0 or a negative AGE_ERR_* (per-job status in out[i].status). */
 int age_align_batch(age_ctx *ctx, const age_job *jobs, size_t n, age_result *out);
+
+/* Streaming form of age_align_batch (the shape SURVEY 8(b) proposes for the C ABI): up to TWO batches may be in flight.
+ * age_submit plans, packs and copies a batch and launches its kernels without waiting (jobs and the sequences they
+ * point to may be released when it returns); age_collect waits for the OLDEST batch in flight and fills out[0..n-1]
+ * (n = that batch's job count).  While the kernels of one batch run, the host prepares and uploads the next one and
+ * the results of the previous one are read back.  The block pointers of a collected batch stay valid until the second
+ * age_submit after its own.  age_align_batch(jobs, n, out) == age_submit + age_collect with nothing else in flight. */
+int age_submit(age_ctx *ctx, const age_job *jobs, size_t n);
+int age_collect(age_ctx *ctx, age_result *out, size_t n);
+int age_in_flight(const age_ctx *ctx);
 
 /* Split form of age_align_batch for measurement with inputs resident in HBM:
  * stage = host packing + host->device copy; run = kernels only (repeatable); fetch = device->host + result assembly. */
