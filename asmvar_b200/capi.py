@@ -80,6 +80,20 @@ class AgeSeqView(C.Structure):
                 ("start", C.c_int32), ("reverse", C.c_int32)]
 
 
+class AgeFragment(C.Structure):
+    _fields_ = [("start1", C.c_int32), ("end1", C.c_int32), ("start2", C.c_int32), ("end2", C.c_int32),
+                ("n_aligned", C.c_int32), ("n_identic", C.c_int32), ("n_gap", C.c_int32), ("text_off", C.c_int32), ("text_len", C.c_int32)]
+
+
+class AgeAlignInfo(C.Structure):
+    _fields_ = [("score", C.c_int32), ("strand", C.c_int32), ("is_alternative_align", C.c_int32), ("n_identity", C.c_int32),
+                ("identity", (C.c_int32 * 2) * 3), ("ci_start1", C.c_int32 * 2), ("ci_end1", C.c_int32 * 2),
+                ("ci_start2", C.c_int32 * 2), ("ci_end2", C.c_int32 * 2),
+                ("homo_run_atbp1", C.c_int32), ("homo_run_atbp2", C.c_int32), ("homo_run_inbp1", C.c_int32),
+                ("homo_run_inbp2", C.c_int32), ("homo_run_outbp1", C.c_int32), ("homo_run_outbp2", C.c_int32),
+                ("n_frag", C.c_int32), ("frag", AgeFragment * 2)]
+
+
 class AgeStats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("fill_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
@@ -92,7 +106,7 @@ class AgeStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged",
     "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version", "age_int16_peak",
-    "age_submit", "age_collect", "age_in_flight",
+    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment",
 ]
 
 _lib = None
@@ -134,6 +148,9 @@ def load() -> C.CDLL:
     lib.age_format_alignment.restype = C.c_size_t
     lib.age_format_alignment.argtypes = [C.POINTER(AgeSeqView), C.POINTER(AgeSeqView), C.POINTER(AgeJob),
                                          C.POINTER(AgeResult), C.c_char_p, C.c_size_t]
+    lib.age_describe_alignment.restype = C.c_size_t
+    lib.age_describe_alignment.argtypes = [C.POINTER(AgeSeqView), C.POINTER(AgeSeqView), C.POINTER(AgeResult), C.POINTER(AgeAlignInfo),
+                                           C.c_char_p, C.c_size_t]
     lib.age_revcom.restype = None
     lib.age_revcom.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]
     lib.age_subst_score.restype = C.c_int
@@ -155,3 +172,27 @@ def format_alignment(s1: AgeSeqView, s2: AgeSeqView, job: AgeJob, res: AgeResult
         buf = C.create_string_buffer(n + 1)
         lib.age_format_alignment(C.byref(s1), C.byref(s2), C.byref(job), C.byref(res), buf, n + 1)
     return buf.raw[:n].decode("latin-1")
+
+
+def describe_alignment(s1: AgeSeqView, s2: AgeSeqView, res: AgeResult) -> dict:
+    """age_describe_alignment as a dict shaped like AsmvarDetect's AlignResult (src/AsmvarDetect/AGEaligner.h:91-150)."""
+    lib = load()
+    info = AgeAlignInfo()
+    cap = 64 + 6 * (s1.len + s2.len)
+    buf = C.create_string_buffer(cap)
+    n = lib.age_describe_alignment(C.byref(s1), C.byref(s2), C.byref(res), C.byref(info), buf, cap)
+    if n > cap:
+        buf = C.create_string_buffer(n)
+        lib.age_describe_alignment(C.byref(s1), C.byref(s2), C.byref(res), C.byref(info), buf, n)
+    raw = buf.raw
+    frags = []
+    for k in range(info.n_frag):
+        f = info.frag[k]
+        t = [raw[f.text_off + i * (f.text_len + 1): f.text_off + i * (f.text_len + 1) + f.text_len].decode("latin-1") for i in range(3)]
+        frags.append({"start1": f.start1, "end1": f.end1, "start2": f.start2, "end2": f.end2, "seq1": t[0], "seq2": t[1], "info": t[2],
+                      "n_aligned": f.n_aligned, "n_identic": f.n_identic, "n_gap": f.n_gap})
+    return {"score": info.score, "strand": chr(info.strand), "is_alternative_align": info.is_alternative_align,
+            "identity": [[info.identity[i][0], info.identity[i][1]] for i in range(info.n_identity)],
+            "ci_start1": list(info.ci_start1), "ci_end1": list(info.ci_end1), "ci_start2": list(info.ci_start2), "ci_end2": list(info.ci_end2),
+            "homo_run": [info.homo_run_atbp1, info.homo_run_atbp2, info.homo_run_inbp1, info.homo_run_inbp2, info.homo_run_outbp1, info.homo_run_outbp2],
+            "map": frags}

@@ -391,6 +391,98 @@ size_t format_alignment(const age_seqview *v1, const age_seqview *v2, const age_
     return o.n;
 }
 
+// AGEaligner::SetAlignResult of the AsmvarDetect flavour (src/AsmvarDetect/AGEaligner.cpp:179-332): the same quantities
+// printAlignment() prints, as numbers.  Text (ali1 / ali2 / mapInfo per fragment) goes to `text`.
+size_t describe_alignment(const age_seqview *v1, const age_seqview *v2, const age_result *res, age_align_info *info, char *text, size_t cap)
+{
+    memset(info, 0, sizeof(*info));
+    info->score = res->score;                                   // score(): the aux score only if strictly greater
+    info->strand = '.';
+    const int flag = res->flag;
+    SeqHdr s1{v1->seq, v1->len, v1->start, v1->reverse != 0};
+    SeqHdr s2{v2->seq, v2->len, v2->start, v2->reverse != 0};
+    std::string rc;
+    SeqHdr s1rc = s1;
+    if (flag & (AGE_INVL_FLAG | AGE_INVR_FLAG)) {
+        rc.resize((size_t)s1.len);
+        for (int i = 0; i < s1.len; i++) rc[(size_t)i] = complement(s1.seq[s1.len - 1 - i]);
+        s1rc.seq = rc.data();
+        s1rc.start = s1.reverse ? s1.start - (s1.len - 1) : s1.start + (s1.len - 1);
+        s1rc.reverse = !s1.reverse;
+    }
+    std::vector<Frag> frags;
+    build_frags(s1, s1rc, s2, flag, res->left, res->n_left, res->right, res->n_right, frags);
+    const int n_frg = (int)frags.size();
+    info->n_frag = n_frg;
+    Out o{text, cap, 0};
+    int n_ali = 0, n_id = 0;
+    for (int k = 0; k < n_frg; k++) {
+        const Frag &f = frags[k];
+        age_fragment &g = info->frag[k];
+        g.start1 = f.start1; g.end1 = f.end1; g.start2 = f.start2; g.end2 = f.end2;
+        g.text_off = (int32_t)o.n; g.text_len = (int32_t)f.a1.size();
+        for (size_t i = 0; i < f.a1.size(); i++) {              // AliFragment::countAligned
+            g.n_aligned++;
+            if (same_nuc(f.a1[i], f.a2[i])) g.n_identic++;
+            if (is_gap(f.a1[i]) || is_gap(f.a2[i])) g.n_gap++;
+        }
+        n_ali += g.n_aligned; n_id += g.n_identic;
+        o.put(f.a1.data(), f.a1.size()); o.put('\0');
+        o.put(f.a2.data(), f.a2.size()); o.put('\0');
+        for (size_t i = 0; i < f.a1.size(); i++)                // AliFragment::mapInfo (AGEaligner.h:318-334)
+            o.put(same_nuc(f.a1[i], f.a2[i]) ? '|' : (!is_gap(f.a1[i]) && !is_gap(f.a2[i])) ? '.' : ' ');
+        o.put('\0');
+    }
+    if (n_ali > 0) {
+        info->identity[info->n_identity][0] = n_id; info->identity[info->n_identity][1] = (int)(100. * n_id / n_ali + 0.5);
+        info->n_identity++;
+        info->strand = info->frag[0].start2 > info->frag[0].end2 ? '-' : '+';
+    }
+    if (n_frg > 1) {
+        for (int k = 0; k < n_frg; k++) {
+            info->identity[info->n_identity][0] = info->frag[k].n_identic;
+            info->identity[info->n_identity][1] = (int)(100.0 * info->frag[k].n_identic / info->frag[k].n_aligned + 0.5);
+            info->n_identity++;
+        }
+        info->is_alternative_align = res->n_bp > 1;
+        const int inc1 = s1.reverse ? -1 : 1, inc2 = s2.reverse ? -1 : 1;
+        struct CI { bool any = false; int lo = 0, hi = 0; void add(int a, int b) { if (!any) { lo = a; hi = b; any = true; } else { if (lo > a) lo = a; if (hi < b) hi = b; } } };
+        CI cs1, ce1, cs2, ce2;                                  // Boundary(): min of the firsts, max of the seconds
+        const Frag &f = frags[0], &nx = frags[1];
+        int s, e, left = 0, right = 0, h;
+        if (excised_range(flag, s1.reverse, f, nx, s, e, 0, 1)) {                       // at the breakpoints
+            h = at_identity(s1, inc1 * (s - s1.start), inc1 * (e - s1.start), left, right);
+            info->homo_run_atbp1 = h;
+            if (h > 0) { cs1.add(s + inc1 * left, s + inc1 * (right - 1)); ce1.add(e + inc1 * left, e + inc1 * (right - 1)); }
+            s = f.end2 + inc2; e = nx.start2; left = right = 0;
+            h = at_identity(s2, inc2 * (s - s2.start), inc2 * (e - s2.start), left, right);
+            info->homo_run_atbp2 = h;
+            if (h > 0) { cs2.add(s + inc2 * left, s + inc2 * (right - 1)); ce2.add(e + inc2 * left, e + inc2 * (right - 1)); }
+        }
+        if (excised_range(flag, s1.reverse, f, nx, s, e, -1, 1)) {                      // outside
+            h = outside_identity(s1, inc1 * (s - s1.start), inc1 * (e - s1.start));
+            info->homo_run_outbp1 = h;
+            if (h > 0) { cs1.add(s - inc1 * (h - 1), s); ce1.add(e, e + inc1 * (h - 1)); }
+            s = f.end2; e = nx.start2;
+            h = outside_identity(s2, inc2 * (s - s2.start), inc2 * (e - s2.start));
+            info->homo_run_outbp2 = h;
+            if (h > 0) { cs2.add(s - inc2 * (h - 1), s); ce2.add(e, e + inc2 * (h - 1)); }
+        }
+        if (excised_range(flag, s1.reverse, f, nx, s, e)) {                             // inside
+            h = inside_identity(s1, inc1 * (s - s1.start), inc1 * (e - s1.start));
+            info->homo_run_inbp1 = h;
+            if (h > 0) { cs1.add(s, s + inc1 * (h - 1)); ce1.add(e - inc1 * (h - 1), e); }
+            s = f.end2 + inc2; e = nx.start2 - inc2;
+            h = inside_identity(s2, inc2 * (s - s2.start), inc2 * (e - s2.start));
+            info->homo_run_inbp2 = h;
+            if (h > 0) { cs2.add(s, s + inc2 * (h - 1)); ce2.add(e - inc2 * (h - 1), e); }
+        }
+        info->ci_start1[0] = cs1.lo; info->ci_start1[1] = cs1.hi; info->ci_end1[0] = ce1.lo; info->ci_end1[1] = ce1.hi;
+        info->ci_start2[0] = cs2.lo; info->ci_start2[1] = cs2.hi; info->ci_end2[0] = ce2.lo; info->ci_end2[1] = ce2.hi;
+    }
+    return o.n;
+}
+
 } // namespace age
 
 extern "C" size_t age_format_alignment(const age_seqview *s1, const age_seqview *s2, const age_job *job,
@@ -398,6 +490,13 @@ extern "C" size_t age_format_alignment(const age_seqview *s1, const age_seqview 
 {
     if (!s1 || !s2 || !job || !res) return 0;
     return age::format_alignment(s1, s2, job, res, buf, cap);
+}
+
+extern "C" size_t age_describe_alignment(const age_seqview *s1, const age_seqview *s2, const age_result *res,
+                                         age_align_info *info, char *text, size_t cap)
+{
+    if (!s1 || !s2 || !res || !info) return 0;
+    return age::describe_alignment(s1, s2, res, info, text, cap);
 }
 
 extern "C" void age_revcom(const char *in, int32_t n, char *out)

@@ -127,6 +127,32 @@ int age_get_stats(const age_ctx *ctx, age_stats *st);
 size_t age_format_alignment(const age_seqview *s1, const age_seqview *s2, const age_job *job,
                             const age_result *res, char *buf, size_t cap);
 
+/* Replaces: AGEaligner::SetAlignResult() / align_result() of the AsmvarDetect flavour (src/AsmvarDetect/AGEaligner.cpp:179-332,
+ * AGEaligner.h:91-150): the numbers printAlignment() prints, without going through text.  One age_fragment per aligned
+ * fragment (MapData pair + AliFragment::countAligned); its gapped strings are written to the caller's `text` buffer as
+ * three NUL-terminated strings of text_len characters each, starting at text_off: ali1, ali2, mapInfo ('|' '.' ' ').
+ * Returns the number of text bytes needed (truncated if > cap).  When res->used_aux is set the reference's
+ * SetAlignResult() prints the auxiliary record instead and leaves AlignResult at its defaults; that quirk is the
+ * caller's (include/age_shim.hh reproduces it), this function describes whatever alignment `res` holds. */
+typedef struct {
+    int32_t start1, end1, start2, end2;
+    int32_t n_aligned, n_identic, n_gap;
+    int32_t text_off, text_len;
+} age_fragment;
+typedef struct {
+    int32_t score;                      /* AlignResult::_score */
+    int32_t strand;                     /* '+', '-' or '.' */
+    int32_t is_alternative_align;       /* _n_bpoints > 1 (two fragments only) */
+    int32_t n_identity;                 /* entries of _identity: total, then per fragment if there are two */
+    int32_t identity[3][2];             /* (identical bases, percent) */
+    int32_t ci_start1[2], ci_end1[2], ci_start2[2], ci_end2[2];
+    int32_t homo_run_atbp1, homo_run_atbp2, homo_run_inbp1, homo_run_inbp2, homo_run_outbp1, homo_run_outbp2;
+    int32_t n_frag;
+    age_fragment frag[2];
+} age_align_info;
+size_t age_describe_alignment(const age_seqview *s1, const age_seqview *s2, const age_result *res,
+                              age_align_info *info, char *text, size_t cap);
+
 /* Replaces: Sequence::revcom() string part (Sequence.hh:195-197) and Scorer lookup (Scorer.hh:24-39). */
 void age_revcom(const char *in, int32_t n, char *out);
 int  age_subst_score(char a, char b, int match, int mismatch);

@@ -12,9 +12,11 @@
 
 #include "age_b200.h"
 
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace age_b200 {
@@ -63,12 +65,36 @@ private:
     short _match, _mismatch, _gap_open, _gap_extend;
 };
 
-class AGEaligner {                                // AGEaligner.hh:69-126
+// AsmvarDetect's structured result (src/AsmvarDetect/AGEaligner.h:70-150): same member names and defaults
+class MapData {
+public:
+    MapData() : _start(0), _end(0) {}
+    std::string _id;
+    int _start, _end;
+    std::string _sequence;
+};
+
+class AlignResult {
+public:
+    AlignResult() : _score(-1), _strand('.'), _is_alternative_align(false), _ci_start1(0, 0), _ci_end1(0, 0), _ci_start2(0, 0), _ci_end2(0, 0),
+                    _homo_run_atbp1(0), _homo_run_atbp2(0), _homo_run_inbp1(0), _homo_run_inbp2(0), _homo_run_outbp1(0), _homo_run_outbp2(0) {}
+    std::string _id1, _id2;
+    int _score;
+    char _strand;
+    bool _is_alternative_align;
+    std::vector<std::pair<int, int> > _identity;              // <identical bases, identity %>: average, left, right
+    std::pair<int, int> _ci_start1, _ci_end1, _ci_start2, _ci_end2;
+    int _homo_run_atbp1, _homo_run_atbp2, _homo_run_inbp1, _homo_run_inbp2, _homo_run_outbp1, _homo_run_outbp2;
+    std::vector<std::pair<MapData, MapData> > _map;           // first -> seq1, second -> seq2
+    std::vector<std::string> _map_info;
+};
+
+class AGEaligner {                                // AGEaligner.hh:69-126, src/AsmvarDetect/AGEaligner.h:152-227
 public:
     static const int INDEL_FLAG = AGE_INDEL_FLAG, TDUPLICATION_FLAG = AGE_TDUPLICATION_FLAG, INVERSION_FLAG = AGE_INVERSION_FLAG,
                      INVR_FLAG = AGE_INVR_FLAG, INVL_FLAG = AGE_INVL_FLAG;
 
-    AGEaligner(Sequence &s1, Sequence &s2) : _s1(s1), _s2(s2), _aligned(false) {}
+    AGEaligner(Sequence &s1, Sequence &s2) : _s1(s1), _s2(s2), _aligned(false), _is_set_align_result(false) {}
 
     // AGEaligner.cpp:65-147.  false = nothing to align (empty sequence, no mode).  Jobs outside the 16-bit score range
     // of the GPU kernels throw: the reference would wrap silently (AGEaligner.hh:86).
@@ -91,11 +117,8 @@ public:
     int score() const { return _aligned ? _res.score : 0; }                  // AGEaligner.cpp:149-154
     void printAlignment(std::ostream &os = std::cout) {                        // AGEaligner.cpp:179-380
         if (!_aligned) return;
-        age_result r = _res;
-        const age_block *b = _blocks.data();
-        r.left = b; r.right = b + r.n_left; r.alt_left = r.right + r.n_right; r.alt_right = r.alt_left + r.n_alt_left;
-        const age_seqview v1{_s1.sequence().data(), (int32_t)_s1.sequence().size(), _s1.name().c_str(), _s1.start(), _s1.reverse() ? 1 : 0};
-        const age_seqview v2{_s2.sequence().data(), (int32_t)_s2.sequence().size(), _s2.name().c_str(), _s2.start(), _s2.reverse() ? 1 : 0};
+        const age_result r = owned_result();
+        const age_seqview v1 = view1(), v2 = view2();
         std::string buf(8192 + 8 * (_s1.sequence().size() + _s2.sequence().size()), '\0');
         size_t n = age_format_alignment(&v1, &v2, &_job, &r, &buf[0], buf.size());
         if (n >= buf.size()) { buf.resize(n + 1); n = age_format_alignment(&v1, &v2, &_job, &r, &buf[0], buf.size()); }
@@ -103,17 +126,70 @@ public:
     }
     const age_result &result() const { return _res; }                         // breakpoints and blocks, without re-parsing text
 
+    // src/AsmvarDetect/AGEaligner.cpp:179-332.  As there: when the auxiliary INVR aligner of -inv scored higher, its
+    // record is printed and the AlignResult keeps its defaults.
+    void SetAlignResult(std::ostream &os = std::cout) {
+        _is_set_align_result = true;
+        _align_result = AlignResult();
+        if (!_aligned) return;
+        if (_res.used_aux) { printAlignment(os); return; }
+        const age_result r = owned_result();
+        const age_seqview v1 = view1(), v2 = view2();
+        age_align_info info;
+        std::string text(64 + 6 * (_s1.sequence().size() + _s2.sequence().size()), '\0');
+        size_t n = age_describe_alignment(&v1, &v2, &r, &info, &text[0], text.size());
+        if (n > text.size()) { text.resize(n); age_describe_alignment(&v1, &v2, &r, &info, &text[0], text.size()); }
+        AlignResult &a = _align_result;
+        a._score = info.score;
+        a._id1 = _s1.name(); a._id2 = _s2.name();
+        a._strand = (char)info.strand;
+        a._is_alternative_align = info.is_alternative_align != 0;
+        for (int i = 0; i < info.n_identity; ++i) a._identity.push_back(std::make_pair((int)info.identity[i][0], (int)info.identity[i][1]));
+        a._ci_start1 = std::make_pair((int)info.ci_start1[0], (int)info.ci_start1[1]); a._ci_end1 = std::make_pair((int)info.ci_end1[0], (int)info.ci_end1[1]);
+        a._ci_start2 = std::make_pair((int)info.ci_start2[0], (int)info.ci_start2[1]); a._ci_end2 = std::make_pair((int)info.ci_end2[0], (int)info.ci_end2[1]);
+        a._homo_run_atbp1 = info.homo_run_atbp1; a._homo_run_atbp2 = info.homo_run_atbp2;
+        a._homo_run_inbp1 = info.homo_run_inbp1; a._homo_run_inbp2 = info.homo_run_inbp2;
+        a._homo_run_outbp1 = info.homo_run_outbp1; a._homo_run_outbp2 = info.homo_run_outbp2;
+        for (int k = 0; k < info.n_frag; ++k) {
+            const age_fragment &f = info.frag[k];
+            MapData m1, m2;
+            m1._id = a._id1; m2._id = a._id2;
+            m1._start = f.start1; m1._end = f.end1; m2._start = f.start2; m2._end = f.end2;
+            m1._sequence.assign(text, (size_t)f.text_off, (size_t)f.text_len);
+            m2._sequence.assign(text, (size_t)f.text_off + f.text_len + 1, (size_t)f.text_len);
+            a._map.push_back(std::make_pair(m1, m2));
+            a._map_info.push_back(text.substr((size_t)f.text_off + 2 * ((size_t)f.text_len + 1), (size_t)f.text_len));
+        }
+    }
+    AlignResult align_result() const {            // src/AsmvarDetect/AGEaligner.h:194-201
+        if (!_is_set_align_result) {
+            std::cerr << "[ERROR] You should Call SetAlignResult() first before ";
+            std::cerr << "calling align_result() or the align_result would be empty\n";
+            exit(1);
+        }
+        return _align_result;
+    }
+
     static age_ctx *context() {                   // one context per process (the reference has no such state)
         static age_ctx *ctx = age_create(nullptr, 0);
         if (!ctx) throw std::runtime_error(age_last_error(nullptr));
         return ctx;
     }
 private:
+    age_result owned_result() const {             // _res with the block pointers redirected to our copies
+        age_result r = _res;
+        const age_block *b = _blocks.data();
+        r.left = b; r.right = b + r.n_left; r.alt_left = r.right + r.n_right; r.alt_right = r.alt_left + r.n_alt_left;
+        return r;
+    }
+    age_seqview view1() const { return age_seqview{_s1.sequence().data(), (int32_t)_s1.sequence().size(), _s1.name().c_str(), _s1.start(), _s1.reverse() ? 1 : 0}; }
+    age_seqview view2() const { return age_seqview{_s2.sequence().data(), (int32_t)_s2.sequence().size(), _s2.name().c_str(), _s2.start(), _s2.reverse() ? 1 : 0}; }
     Sequence &_s1, &_s2;
     age_job _job;
     age_result _res;
     std::vector<age_block> _blocks;
-    bool _aligned;
+    bool _aligned, _is_set_align_result;
+    AlignResult _align_result;
 };
 
 } // namespace age_b200

@@ -15,6 +15,8 @@
 #   oracle/_ref/age_align_ref        batch CLI (src/AsmvarAGE/src/age_align.cpp),  -O2, no OpenMP
 #   oracle/_ref/age_align_ref_orig   original CLI (src/AsmvarAGE/src/Trash/age_align.cpp), -O2, no OpenMP
 #   oracle/_ref/age_align_ref_omp    batch CLI with -fopenmp -DOMP (2 threads / alignment, as shipped)
+#   oracle/_ref/age_detect_dump      oracle/detect_dump.cpp (ours) around the AsmvarDetect flavour of the aligner
+#                                    (src/AsmvarDetect/AGEaligner.{h,cpp}): dumps AlignResult for golden vectors
 set -euo pipefail
 REF=${AGE_REFERENCE_ROOT:-/root/reference}
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -49,5 +51,12 @@ FLAGS='-DAGE_VERSION="v0.8" -DAGE_TIME -w -O2'
 ( cd "$STAGE/batch" && g++ $FLAGS AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref" )
 ( cd "$STAGE/batch" && g++ $FLAGS -fopenmp -DOMP AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref_omp" )
 ( cd "$STAGE/orig"  && g++ $FLAGS AGEaligner.cpp age_align.cpp -o "$OUT/age_align_ref_orig" )
+DET="$REF/src/AsmvarDetect"
+if [ -f "$DET/AGEaligner.cpp" ]; then
+  mkdir -p "$STAGE/detect"
+  cp "$DET"/{AGEaligner.cpp,AGEaligner.h,Sequence.h,Scorer.h} "$STAGE/detect/"
+  patch_tbm "$STAGE/detect/AGEaligner.cpp"
+  ( cd "$STAGE/detect" && g++ -w -O2 -I. AGEaligner.cpp "$HERE/detect_dump.cpp" -o "$OUT/age_detect_dump" )
+fi
 rm -rf "$STAGE"
 echo "built: $(ls "$OUT")"
