@@ -26,6 +26,7 @@ public:
     Sequence(const std::string &seq, const std::string &name = "", int start = 1, bool rev = false)
         : _seq(seq), _name(name), _start(start), _reverse(rev) {}
     std::string &sequence() { return _seq; }
+    const std::string &sequence() const { return _seq; }
     const std::string &name() const { return _name; }
     int start() const { return _start; }
     bool reverse() const { return _reverse; }
@@ -99,19 +100,33 @@ public:
     // AGEaligner.cpp:65-147.  false = nothing to align (empty sequence, no mode).  Jobs outside the 16-bit score range
     // of the GPU kernels throw: the reference would wrap silently (AGEaligner.hh:86).
     bool align(Scorer &scr, int flag) {
-        _job.seq1 = _s1.sequence().data(); _job.len1 = (int32_t)_s1.sequence().size();
-        _job.seq2 = _s2.sequence().data(); _job.len2 = (int32_t)_s2.sequence().size();
-        _job.flag = flag;
-        _job.match = scr.getMatch(); _job.mismatch = scr.getMismatch(); _job.gap_open = scr.getGapOpen(); _job.gap_extend = scr.getGapExtend();
-        _job.partner = -1;
-        if (age_align_batch(context(), &_job, 1, &_res) != 0) throw std::runtime_error(age_last_error(context()));
+        const age_job job = make_job(scr, flag);
+        age_result res;
+        if (age_align_batch(context(), &job, 1, &res) != 0) throw std::runtime_error(age_last_error(context()));
+        return adopt(job, res);
+    }
+    // The two halves of align() for callers that batch: make_job() describes this aligner's work, adopt() takes the
+    // result of that job out of an age_align_batch / age_collect result array (copies the block lists).
+    age_job make_job(Scorer &scr, int flag) const {
+        age_job j;
+        j.seq1 = _s1.sequence().data(); j.len1 = (int32_t)_s1.sequence().size();
+        j.seq2 = _s2.sequence().data(); j.len2 = (int32_t)_s2.sequence().size();
+        j.flag = flag;
+        j.match = scr.getMatch(); j.mismatch = scr.getMismatch(); j.gap_open = scr.getGapOpen(); j.gap_extend = scr.getGapExtend();
+        j.partner = -1;
+        return j;
+    }
+    bool adopt(const age_job &job, const age_result &res) {
+        _job = job; _res = res;
+        _is_set_align_result = false;
         if (_res.status < 0) throw std::range_error("AGEaligner: job outside the supported score range");
         _aligned = _res.status == AGE_OK;
         // the block arrays belong to the context until its next batch: keep copies
-        _blocks.assign(_res.left, _res.left + _res.n_left);
-        _blocks.insert(_blocks.end(), _res.right, _res.right + _res.n_right);
-        _blocks.insert(_blocks.end(), _res.alt_left, _res.alt_left + _res.n_alt_left);
-        _blocks.insert(_blocks.end(), _res.alt_right, _res.alt_right + _res.n_alt_right);
+        _blocks.clear();
+        if (_res.n_left) _blocks.insert(_blocks.end(), _res.left, _res.left + _res.n_left);
+        if (_res.n_right) _blocks.insert(_blocks.end(), _res.right, _res.right + _res.n_right);
+        if (_res.n_alt_left) _blocks.insert(_blocks.end(), _res.alt_left, _res.alt_left + _res.n_alt_left);
+        if (_res.n_alt_right) _blocks.insert(_blocks.end(), _res.alt_right, _res.alt_right + _res.n_alt_right);
         return _aligned;
     }
     int score() const { return _aligned ? _res.score : 0; }                  // AGEaligner.cpp:149-154

@@ -17,6 +17,8 @@
 #   oracle/_ref/age_align_ref_omp    batch CLI with -fopenmp -DOMP (2 threads / alignment, as shipped)
 #   oracle/_ref/age_detect_dump      oracle/detect_dump.cpp (ours) around the AsmvarDetect flavour of the aligner
 #                                    (src/AsmvarDetect/AGEaligner.{h,cpp}): dumps AlignResult for golden vectors
+#   oracle/_ref/age_recall_dump      oracle/recall_dump.cpp (ours) around src/AsmvarDetect/VarUnit.cpp:
+#                                    VarUnit::ReAlignAndReCallVar text + re-called variants for golden vectors
 set -euo pipefail
 REF=${AGE_REFERENCE_ROOT:-/root/reference}
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
@@ -57,6 +59,10 @@ if [ -f "$DET/AGEaligner.cpp" ]; then
   cp "$DET"/{AGEaligner.cpp,AGEaligner.h,Sequence.h,Scorer.h} "$STAGE/detect/"
   patch_tbm "$STAGE/detect/AGEaligner.cpp"
   ( cd "$STAGE/detect" && g++ -w -O2 -I. AGEaligner.cpp "$HERE/detect_dump.cpp" -o "$OUT/age_detect_dump" )
+  # VarUnit::ReAlignAndReCallVar / class AgeAlignment (VarUnit.cpp) around the same aligner
+  cp "$DET"/{VarUnit.cpp,VarUnit.h,AgeOption.h,Region.h,Region.cpp,Fa.h,utility.h,utility.cpp,gzstream.h,gzstream.cpp} "$STAGE/detect/" 2>/dev/null || true
+  ( cd "$STAGE/detect" && g++ -w -O2 -I. AGEaligner.cpp VarUnit.cpp Region.cpp "$HERE/recall_dump.cpp" -o "$OUT/age_recall_dump" ) \
+    || ( cd "$STAGE/detect" && g++ -w -O2 -I. AGEaligner.cpp VarUnit.cpp Region.cpp utility.cpp gzstream.cpp "$HERE/recall_dump.cpp" -lz -o "$OUT/age_recall_dump" )
 fi
 rm -rf "$STAGE"
 echo "built: $(ls "$OUT")"
