@@ -61,19 +61,27 @@ age_pack_kernel(const PairTask *__restrict__ pairs, int n_pairs)
             const bool rc = dir > 0 ? (T.flag[k] & F_INVR) : (T.flag[k] & F_INVL);
             return rc ? comp_code(nuc_code(raw[len1 - c])) : nuc_code(raw[c - 1]);
         };
-        for (int idx = threadIdx.x; idx < 2 * (nb + 2); idx += blockDim.x) {
-            const int dir = idx < nb + 2 ? +1 : -1, b = idx < nb + 2 ? idx : idx - (nb + 2);
+        // .w of a descriptor = the N / IUPAC flags of the 32 blocks of its aligned group (bit b & 31 = block b has such a
+        // column): the steady-state sweep takes its per-step branch from these bits and not from the descriptor it has just
+        // loaded (age_sweep.cuh, sweep_window_steady)
+        for (int dir = +1; dir >= -1; dir -= 2) {
             uint4 *dst = dir > 0 ? T.xblk_f : T.xblk_r;
-            if (b == 0 || b == nb + 1) { dst[b] = make_uint4(0, 0, 0x5B5B5B5Bu, 0); continue; }
-            uint32_t sel[W], info = 0;
+            for (int base = 0; base < nb + 2; base += blockDim.x) {          // blockDim.x is a multiple of 32: warps cover aligned groups
+                const int b = base + threadIdx.x;
+                uint32_t sel[W] = {0, 0, 0, 0}, info = 0;
+                if (b == 0 || b == nb + 1) info = 0x5B5B5B5Bu;
+                else if (b <= nb) {
 #pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const int c = dir > 0 ? W * (b - 1) + 1 + w : W * (nb - b + 1) - w;   // columns beyond len1 are padding
-                const int a = xcode(0, dir, c), e = xcode(1, dir, c);
-                if (a < 4 && e < 4) sel[w] = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + e) << 8) | ((uint32_t)((4 + e) | 8) << 12);
-                else { sel[w] = 0; info |= (1u | ((uint32_t)a << 1) | ((uint32_t)e << 4)) << (8 * w); }
+                    for (int w = 0; w < W; ++w) {
+                        const int c = dir > 0 ? W * (b - 1) + 1 + w : W * (nb - b + 1) - w;   // columns beyond len1 are padding
+                        const int a = xcode(0, dir, c), e = xcode(1, dir, c);
+                        if (a < 4 && e < 4) sel[w] = (uint32_t)a | ((uint32_t)(a | 8) << 4) | ((uint32_t)(4 + e) << 8) | ((uint32_t)((4 + e) | 8) << 12);
+                        else { sel[w] = 0; info |= (1u | ((uint32_t)a << 1) | ((uint32_t)e << 4)) << (8 * w); }
+                    }
+                }
+                const uint32_t group = __ballot_sync(0xFFFFFFFFu, (info & 0x01010101u) != 0);
+                if (b <= nb + 1) dst[b] = make_uint4(sel[0] | (sel[1] << 16), sel[2] | (sel[3] << 16), info, group);
             }
-            dst[b] = make_uint4(sel[0] | (sel[1] << 16), sel[2] | (sel[3] << 16), info, 0);
         }
         for (int q = threadIdx.x; q < T.P; q += blockDim.x) {
             uint32_t tab[2] = {0, 0};

@@ -6,6 +6,7 @@
 // t-p (4 columns) in step t and hands the H/G/M values of its bottom row to lane p+1 with warp shuffles.
 #pragma once
 #include "age_device.cuh"
+#include <type_traits>
 
 namespace age {
 
@@ -341,13 +342,148 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
     }
 }
 
+__device__ __forceinline__ void stcg16(uint4 *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{   // the D stream is written once and read once, much later: keep it out of L1
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// The steady-state window of the main sweep (every lane active in every step, 32 <= t0, t1 <= nb): sweep_window with
+// GUARD = false, MODE_FAST, written for instruction count -- running pointers instead of per-step address arithmetic,
+// no clamps on the column descriptors (1 <= t - p <= nb throughout), and the N / IUPAC test hoisted out of the
+// column loop (one copy of the step body without it, one with it).
+template <int DIR>
+__device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
+                                                    const int t0, const int t1, uint32_t &best)
+{
+    constexpr bool FWD = DIR > 0;
+    const int lane = C.lane, p = C.p, nb = C.nb;
+    const int buf = win & 1;
+    // Column descriptors: only the selectors (.x, .y) are loaded per step, one step ahead.  The per-step "has an N / IUPAC
+    // column" branch must NOT depend on that load: ptxas schedules the test right behind the LDG (to free its register) and
+    // every step then waits a full memory latency (37 % of all stall samples of the kernel before this change).  The flags
+    // of the lane's 32 blocks of this window come from the .w words instead (see age_pack_kernel), once per window.
+    const uint4 *xp = C.xblk + (t0 - p);
+    uint32_t spec;
+    {
+        const uint32_t a = __ldg(&xp[0].w), b = __ldg(&xp[t1 - t0].w);
+        spec = __funnelshift_r(a, b, (t0 - p) & 31);
+        if (t1 - t0 < 31) spec &= (1u << (t1 - t0 + 1)) - 1u;
+    }
+    uint2 xnext = __ldg(reinterpret_cast<const uint2 *>(xp));
+    // forward: D slot of step t; reverse: D slot of the step fetched next (t + 1), i.e. forward step nb + 32 - (t + 1)
+    uint4 *dptr = C.D4 + ((C.sbase + (size_t)(FWD ? t0 - 1 : nb + 30 - t0)) * W) * 64 + lane;
+    const bool live = C.live;
+
+    for (int t = t0; t <= t1; ++t) {
+        uint4 xb = make_uint4(xnext.x, xnext.y, 0, 0);
+        xnext = __ldg(reinterpret_cast<const uint2 *>(++xp));
+        const bool special = spec & 1u;
+        spec >>= 1;
+        if (special) xb.z = __ldg(&xp[-1].z);
+        if (!FWD) {
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < W * 2; ++i) cp_async16(&DS.d[(t + 1) & 1][i][lane], dptr + i * 32);
+            }
+            cp_async_commit();
+            dptr -= W * 64;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        }
+        uint32_t uH[W], uG[W], uM[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
+        if (p == 0) {
+            const int e = (t - 1) & 31;
+            const uint4 h = R.in[buf][0][e], g = R.in[buf][1][e], m = R.in[buf][2][e];
+            uH[0] = h.x; uH[1] = h.y; uH[2] = h.z; uH[3] = h.w;
+            uG[0] = g.x; uG[1] = g.y; uG[2] = g.z; uG[3] = g.w;
+            uM[0] = m.x; uM[1] = m.y; uM[2] = m.z; uM[3] = m.w;
+        }
+        auto columns = [&](auto sp) {
+            constexpr bool SPECIAL = decltype(sp)::value;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                if (FWD && live) {
+                    const uint32_t upMprev = w == 0 ? S.pM : uM[w - 1];
+                    stcg16(dptr + w * 64, upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
+                    stcg16(dptr + w * 64 + 32, S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
+                }
+                uint32_t S2[RPT];
+                const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
+                const uint32_t info = SPECIAL ? (xb.z >> (8 * w)) & 0xFFu : 0u;
+                if (SPECIAL && (info & 1u)) {
+                    const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
+                    const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) {
+                        const int yc = C.ycode[C.q0 + k];
+                        const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
+                        S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
+                }
+                uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
+                if (!FWD && live) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    const int k = FWD ? j : RPT - 1 - j;
+                    const uint32_t g  = __vmaxs2(S.Gl[k], vG);
+                    const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);
+                    const uint32_t tg = (s2 ^ C.flip) & 0x00010001u;
+                    const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
+                    const uint32_t Hc = s2 & 0xFFFEFFFEu;
+                    const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
+                    if (!FWD) {
+                        const uint4 dv = (k >> 2) ? dc1 : dc0;
+                        const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
+                        best = __vmaxu2(best, __vadd2(Mn, dk));
+                    }
+                    dg = S.Hl[k];
+                    S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
+                    vG = G2; vM = Mn;
+                }
+                constexpr int last = FWD ? RPT - 1 : 0;
+                S.oH[w] = S.Hl[last]; S.oG[w] = S.Gl[last]; S.oM[w] = S.Ml[last];
+            }
+        };
+        if (!special) columns(std::false_type{});
+        else                           columns(std::true_type{});
+        if (FWD) dptr += W * 64;
+        S.pH = uH[W - 1]; S.pM = uM[W - 1];
+        const int b = t - p;
+        if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
+        if (C.bout) {
+            if (p == 31) {
+                const int e = (b - 1) & 31;
+                R.out[0][e] = make_uint4(S.oH[0], S.oH[1], S.oH[2], S.oH[3]);
+                R.out[1][e] = make_uint4(S.oG[0], S.oG[1], S.oG[2], S.oG[3]);
+                R.out[2][e] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
+            }
+            const int b31 = t - 31;                      // block just finished by the last logical lane
+            if (b31 >= 1 && ((b31 & 31) == 0 || b31 == nb)) {
+                __syncwarp();
+                const int bb = ((b31 - 1) & ~31) + 1 + lane;
+                if (bb <= b31) {
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) C.bout[(size_t)pl * (nb + 1) + bb] = R.out[pl][lane];
+                }
+                if (C.prog_out) { __threadfence(); __syncwarp(); if (lane == 0) *C.prog_out = b31; }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 // dispatch on whether the window is steady (all lanes active in all of its steps)
 template <int DIR, int MODE>
 __device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win,
                                                  uint32_t &best, const TraceOut &TO)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
-    if (MODE == MODE_FAST && t0 >= 32 && t1 <= C.nb) sweep_window<DIR, MODE, false>(C, S, R, DS, win, t0, t1, best, TO);
+    if (MODE == MODE_FAST && t0 >= 32 && t1 <= C.nb) sweep_window_steady<DIR>(C, S, R, DS, win, t0, t1, best);
     else                        sweep_window<DIR, MODE, true>(C, S, R, DS, win, t0, t1, best, TO);
 }
 
