@@ -30,6 +30,14 @@ constexpr int CKS    = 32;         // steps per window
 constexpr int CKW    = 38;         // checkpoint words per lane: H,G,M of 8 rows + 3 x 4 outputs + 2 carried
 constexpr int MAX_BP = 100;        // AGEaligner.hh:94
 
+// Storage formats of the D plane (PairTask::dfmt).  RAW: 8 packed 16-bit pairs per (lane, block column) = 2 uint4.
+// OFF8: the forward maxima of consecutive rows differ by at most max(match, mismatch, 0) per row (every DP step adds at
+// most that, and prefix maxima inherit the bound), so the 8 entries of a (lane, block column) are stored as the first one
+// plus 8-bit offsets: per (lane, step) one uint4 with the 4 column bases and one uint4 of offset bytes per column,
+// 5 uint4 instead of 8.  Used when max(match, mismatch, 0) <= 15 (offsets <= 2*15*7 = 210).
+constexpr int DFMT_RAW = 0, DFMT_OFF8 = 1;
+__host__ __device__ inline int d_planes(int dfmt) { return dfmt == DFMT_OFF8 ? 5 : 2 * W; }     // uint4 per (lane, step)
+
 // trace codes, AGEaligner.hh:41-44
 enum { T_STOP = 0, T_DIAG = 1, T_HORI = 2, T_VERT = 3 };
 
@@ -59,8 +67,10 @@ struct PairTask {
     // Diagonal-major planes, [strip][step][...][lane]: what the 32 lanes touch in one step is contiguous, for the
     // forward and the reverse sweep alike (the anti-diagonal of one wavefront is the anti-diagonal of the other).
     uint32_t *D;                         // forward maxima shifted by one row and one column:
-                                         //   [s][t][w][h][lane][4]: k = 4h+j -> 2*Fmax[256s + 8l + k][W(t-l-1) + w]
+                                         //   RAW  [s][t][w][h][lane][4]: k = 4h+j -> 2*Fmax[256s + 8l + k][W(t-l-1) + w]
                                          //   = what the reverse cell (row+1, col+1) adds (K6, :545-550)
+                                         //   OFF8 [s][t][5][lane][4]: plane 0 = entry k = 0 of the 4 columns, plane 1+w = offsets of
+                                         //   column w, word j = bytes {A_2j, B_2j, A_2j+1, B_2j+1} (A / B = the halves of the pair)
     uint32_t *Dlast;                     // [P + 1]  2*Fmax[r][len1]
     uint32_t *Dtail;                     // [W*nb + 1] 2*Fmax[P][c] (only read when len2 == P)
     uint32_t *Rfirst;                    // [P + 2]  2*Rmax[r][1]
@@ -69,6 +79,7 @@ struct PairTask {
     // pass-2 trace planes of the aligner(s) of this pair that get breakpoints (one set when `select`, else one per half)
     char *p2set; uint32_t p2stride;
     int32_t k7;                          // a TDUP / inversion aligner is present: sets also hold the reverse maxima plane
+    int32_t dfmt;                        // DFMT_RAW / DFMT_OFF8
 };
 
 struct AlignerOut {

@@ -241,7 +241,7 @@ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi
 
 // Copy the raw sequences of pair `pi` into the pinned host blob at `h` (device address `d`) and fill its task record.
 // The column descriptors and row tables are derived from the raw strings on the device (age_pack_kernel).
-void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, PairTask &T)
+void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, PairTask &T, bool force_raw)
 {
     const HostPair &hp = B->pairs[pi];
     memset(&T, 0, sizeof(T));
@@ -275,6 +275,10 @@ void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, Pa
     // identical scoring
     T.c0x = pack2(c0x[0], c0x[1]); T.kabs = (uint32_t)kabs[0]; T.flip = pack2(flip[0], flip[1]); T.gborder = pack2(gb[0], gb[1]);
     T.m2 = pack2(2 * sc[0][0], 2 * sc[1][0]); T.mm2 = pack2(2 * sc[0][1], 2 * sc[1][1]);
+    // D as 8-bit row offsets when a DP step can add at most 15 (age_device.cuh); AGE_DFMT=raw forces the 16-bit planes (tests)
+    int smax = 0;
+    for (int k = 0; k < 2; ++k) smax = std::max(smax, std::max(sc[k][0], sc[k][1]));
+    T.dfmt = (!force_raw && smax <= 15) ? DFMT_OFF8 : DFMT_RAW;
 }
 
 void assign_scratch(const HostPair &hp, char *s, PairTask &T)
@@ -344,8 +348,10 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     if (!sl.outbuf.ensure(sl.out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
     if (!sl.hout.ensure(sl.out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
     if (!sl.aux.ensure(align_up(np * sizeof(PairHdr), 256) + (size_t)sl.queue_cap * sizeof(uint2))) { dev.err = "device allocation failed (work list)"; return false; }
+    const char *dfmt_env = getenv("AGE_DFMT");                      // test knob: "raw" keeps the 16-bit D planes
+    const bool force_raw = dfmt_env && strcmp(dfmt_env, "raw") == 0;
     parallel_for(ctx->host_threads, np, [&](size_t i) {
-        pack_pair(&B, jobs, pair_ids[i], sl.hin.ptr + task_bytes + in_off[i], sl.in.ptr + task_bytes + in_off[i], sl.tasks[i]);
+        pack_pair(&B, jobs, pair_ids[i], sl.hin.ptr + task_bytes + in_off[i], sl.in.ptr + task_bytes + in_off[i], sl.tasks[i], force_raw);
         assign_scratch(B.pairs[pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
     });
     memcpy(sl.hin.ptr, sl.tasks.data(), np * sizeof(PairTask));

@@ -54,6 +54,18 @@ __device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
     return t;
 }
 
+// OFF8 format of D (age_device.cuh): the entries of one (lane, block column) are `base` (row k = 0) and Ml[0..6] (k = 1..7)
+__device__ __forceinline__ uint4 d8_encode(uint32_t base, const uint32_t (&Ml)[RPT])
+{   // neither half can borrow: the maxima grow with the row
+    return make_uint4(prmt(0u, Ml[0] - base, 0x6420), prmt(Ml[1] - base, Ml[2] - base, 0x6420),
+                      prmt(Ml[3] - base, Ml[4] - base, 0x6420), prmt(Ml[5] - base, Ml[6] - base, 0x6420));
+}
+__device__ __forceinline__ uint32_t d8_offset(const uint4 &o, int k)       // packed offset of row k (0 in the upper bytes)
+{
+    const uint32_t wd = (k >> 1) == 0 ? o.x : (k >> 1) == 1 ? o.y : (k >> 1) == 2 ? o.z : o.w;
+    return prmt(wd, 0u, (k & 1) ? 0x4342 : 0x4140);
+}
+
 struct LaneState {
     uint32_t Hl[RPT], Gl[RPT], Ml[RPT];    // row state at the last finished column
     uint32_t oH[W], oG[W], oM[W];          // bottom-row outputs of the last finished block (shuffled to lane p+1)
@@ -92,6 +104,7 @@ template <int DIR> struct StripCtx {
     const uint8_t *ycode;
     const uint4 *bin; uint4 *bout;          // boundary planes in / out (nullptr at the first / last strip)
     uint4 *D4;                              // D as uint4
+    int dfmt, dstep;                        // storage format of D and its uint4 per step (32 lanes x d_planes)
     uint4 *Dtail4;                          // forward, last lane of the last strip only (else nullptr)
     uint32_t *tilemax;
     uint32_t *ckpt;
@@ -116,6 +129,7 @@ template <int DIR> struct StripCtx {
         bin = first ? nullptr : bnd + (size_t)(si - 1) * 3 * (nb + 1);
         bout = (si + 1 < T.nstrips) ? bnd + (size_t)si * 3 * (nb + 1) : nullptr;
         D4 = reinterpret_cast<uint4 *>(T.D);
+        dfmt = T.dfmt; dstep = 32 * d_planes(T.dfmt);
         Dtail4 = (FWD && p == 31 && si + 1 == T.nstrips) ? reinterpret_cast<uint4 *>(T.Dtail) : nullptr;
         tilemax = T.tilemax;
         ckpt = FWD ? T.ckpt_f : T.ckpt_r;
@@ -192,26 +206,32 @@ __device__ __forceinline__ void ring_fill_border(WarpRings &R, int lane, uint32_
     __syncwarp();
 }
 
-// One window (steps t0 .. t1) of one strip.  GUARD = false is the steady state in which every lane is active in
-// every step of the window.
+__device__ __forceinline__ void stcg16(uint4 *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{   // the D stream is written once and read once, much later: keep it out of L1
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // D slot of reverse step t (written by the forward sweep in step nb+32-t) -> shared memory, asynchronously
 template <int DIR>
 __device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS, int t)
 {
     if (t <= C.nsteps && C.live) {
-        const uint4 *src = C.D4 + ((C.sbase + (size_t)(C.nb + 31 - t)) * W) * 64 + C.lane;
+        const uint4 *src = C.D4 + (C.sbase + (size_t)(C.nb + 31 - t)) * C.dstep + C.lane;
 #pragma unroll
-        for (int i = 0; i < W * 2; ++i) cp_async16(&DS.d[t & 1][i][C.lane], src + i * 32);
+        for (int i = 0; i < W * 2; ++i) if (i < 5 || C.dfmt == DFMT_RAW) cp_async16(&DS.d[t & 1][i][C.lane], src + i * 32);
     }
     cp_async_commit();
 }
 
-template <int DIR, int MODE, bool GUARD>
-__device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
-                                             const int t0, const int t1, uint32_t &best, const TraceOut &TO)
+// One window (steps t0 .. t1) of one strip of the main sweep in which some lanes are idle in some steps: the first
+// window(s) of a strip (the wavefront fills up), the last ones (it drains, and the last block may hold padding columns).
+// The windows in between go through sweep_window_steady.
+template <int DIR, int DFMT>
+__device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
+                                                  const int t0, const int t1, uint32_t &best)
 {
     constexpr bool FWD = DIR > 0;
-    constexpr bool TRACE = false, TRACE_S = false, TRACE_M = false;   // the trace re-sweep is sweep_window_compact
+    constexpr int DSTEP = 32 * (DFMT == DFMT_OFF8 ? 5 : 2 * W);
     const int lane = C.lane, p = C.p, nb = C.nb;
     const int buf = win & 1;
     auto xload = [&](int b) { return __ldg(C.xblk + min(max(b, 0), nb + 1)); };
@@ -236,50 +256,53 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
             uM[0] = m.x; uM[1] = m.y; uM[2] = m.z; uM[3] = m.w;
         }
         const int b = t - p;
-        if (!GUARD || (b >= 1 && b <= nb)) {
-            const size_t slot = C.sbase + (size_t)(t - 1);
-            // reverse sweep: the shifted forward maxima of this block, written by the forward lane in step nb+32-t
-
+        if (b >= 1 && b <= nb) {
+            uint4 *dst = C.D4 + (C.sbase + (size_t)(t - 1)) * DSTEP + lane;      // forward: the D slot of this step
+            if (FWD && C.live && DFMT == DFMT_OFF8) stcg16(dst, S.pM, uM[0], uM[1], uM[2]);
+            uint4 dbase = make_uint4(0, 0, 0, 0);
+            if (!FWD && C.live && DFMT == DFMT_OFF8) dbase = DS.d[t & 1][0][lane];
             const bool special = (xb.z & 0x01010101u) != 0;
-            uint32_t tw[W];
-            uint32_t hotw = 0;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
-                // ---- forward: D[w] = maxima at the previous column, rows shifted by one (entry 0 = row above) ----
+                // ---- forward: D = maxima at the previous column, rows shifted by one (entry 0 = row above) ----------
                 const uint32_t upMprev = w == 0 ? S.pM : uM[w - 1];
-                if (FWD && !TRACE && C.live) {
-                    uint4 *dst = C.D4 + (slot * W + w) * 64 + lane;
-                    dst[0]  = make_uint4(upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
-                    dst[32] = make_uint4(S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
+                if (FWD && C.live) {
+                    if (DFMT == DFMT_RAW) {
+                        stcg16(dst + w * 64, upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
+                        stcg16(dst + w * 64 + 32, S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
+                    } else {
+                        const uint4 o = d8_encode(upMprev, S.Ml);
+                        stcg16(dst + (1 + w) * 32, o.x, o.y, o.z, o.w);
+                    }
                 }
                 // ---- substitution scores of this column ---------------------------------------------------------
                 uint32_t S2[RPT];
-                if (special) {
-                    const uint32_t info = (xb.z >> (8 * w)) & 0xFFu;
-                    if (info & 1u) {
-                        const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
-                        const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+                const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
+                const uint32_t info = (xb.z >> (8 * w)) & 0xFFu;
+                if (special && (info & 1u)) {
+                    const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
+                    const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
 #pragma unroll
-                        for (int k = 0; k < RPT; ++k) {
-                            const int yc = C.ycode[C.q0 + k];
-                            const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
-                            S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
-                        }
-                    } else {
-                        const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
-#pragma unroll
-                        for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
+                    for (int k = 0; k < RPT; ++k) {
+                        const int yc = C.ycode[C.q0 + k];
+                        const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
+                        S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
                     }
                 } else {
-                    const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
 #pragma unroll
                     for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
                 }
                 // ---- the column ---------------------------------------------------------------------------------
                 uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
-                if (!FWD && C.live) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                uint32_t colbase = 0, colbest = 0;
+                if (!FWD && C.live) {
+                    if (DFMT == DFMT_RAW) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                    else {
+                        dc0 = DS.d[t & 1][1 + (W - 1 - w)][lane];
+                        colbase = (W - 1 - w) == 0 ? dbase.x : (W - 1 - w) == 1 ? dbase.y : (W - 1 - w) == 2 ? dbase.z : dbase.w;
+                    }
+                }
                 uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
-                uint32_t nibw = 0;
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
                     const int k = FWD ? j : RPT - 1 - j;
@@ -289,44 +312,31 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
                     const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);         // 2*(s + (gap ? ge : go)) + 1
                     const uint32_t Hc = s2 & 0xFFFEFFFEu;
                     const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
-                    if (TRACE_S) nibw |= fs_code(half16(__vadd2(dg, S2[k]), TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) << (2 * k);
-                    if (TRACE_M) nibw |= fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << (2 * k);
-                    if (!FWD && !TRACE_S) {
-                        const uint4 dv = (k >> 2) ? dc1 : dc0;
-                        const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
-                        const uint32_t sum = __vadd2(Mn, dk);
-                        if (!TRACE) best = __vmaxu2(best, sum);
-                        else if ((int)((sum >> TO.sh) & 0xFFFFu) == TO.max2) hotw |= 1u << (8 * w + k);
+                    if (!FWD) {
+                        if (DFMT == DFMT_RAW) {
+                            const uint4 dv = (k >> 2) ? dc1 : dc0;
+                            const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
+                            best = __vmaxu2(best, __vadd2(Mn, dk));
+                        } else colbest = __vmaxu2(colbest, __vadd2(Mn, d8_offset(dc0, k)));
                     }
                     dg = S.Hl[k];
                     S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
                     vG = G2; vM = Mn;
                 }
+                if (!FWD && DFMT == DFMT_OFF8) best = __vmaxu2(best, __vadd2(colbest, colbase));
                 constexpr int last = FWD ? RPT - 1 : 0;
                 S.oH[w] = S.Hl[last]; S.oG[w] = S.Gl[last]; S.oM[w] = S.Ml[last];
-                tw[w] = nibw;
-                if (TRACE_M && !FWD && TO.Mp) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(TO.Mp) + (slot * W + w) * 64 + lane;
-                    dst[0]  = make_uint4(S.Ml[0], S.Ml[1], S.Ml[2], S.Ml[3]);
-                    dst[32] = make_uint4(S.Ml[4], S.Ml[5], S.Ml[6], S.Ml[7]);
-                }
             }
             S.pH = uH[W - 1]; S.pM = uM[W - 1];
-            if (TRACE) {
-                TO.P[slot * 32 + lane] = make_uint2(tw[0] | (tw[1] << 16), tw[2] | (tw[3] << 16));
-                if (!FWD && TRACE_M) TO.hot[slot * 32 + lane] = hotw;
-            }
-            if (!TRACE) {
-                if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
-                if (p == 31 && C.bout) {
-                    const int e = (b - 1) & 31;
-                    R.out[0][e] = make_uint4(S.oH[0], S.oH[1], S.oH[2], S.oH[3]);
-                    R.out[1][e] = make_uint4(S.oG[0], S.oG[1], S.oG[2], S.oG[3]);
-                    R.out[2][e] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
-                }
+            if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
+            if (p == 31 && C.bout) {
+                const int e = (b - 1) & 31;
+                R.out[0][e] = make_uint4(S.oH[0], S.oH[1], S.oH[2], S.oH[3]);
+                R.out[1][e] = make_uint4(S.oG[0], S.oG[1], S.oG[2], S.oG[3]);
+                R.out[2][e] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
             }
         }
-        if (!TRACE && C.bout) {
+        if (C.bout) {
             const int b31 = t - 31;                      // block just finished by the last logical lane
             if (b31 >= 1 && ((b31 & 31) == 0 || b31 == nb)) {
                 __syncwarp();
@@ -342,20 +352,16 @@ __device__ __forceinline__ void sweep_window(const StripCtx<DIR> &C, LaneState &
     }
 }
 
-__device__ __forceinline__ void stcg16(uint4 *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{   // the D stream is written once and read once, much later: keep it out of L1
-    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
 // The steady-state window of the main sweep (every lane active in every step, 32 <= t0, t1 <= nb): sweep_window with
 // GUARD = false, MODE_FAST, written for instruction count -- running pointers instead of per-step address arithmetic,
 // no clamps on the column descriptors (1 <= t - p <= nb throughout), and the N / IUPAC test hoisted out of the
 // column loop (one copy of the step body without it, one with it).
-template <int DIR>
+template <int DIR, int DFMT>
 __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
                                                     const int t0, const int t1, uint32_t &best)
 {
     constexpr bool FWD = DIR > 0;
+    constexpr int NPL = DFMT == DFMT_OFF8 ? 5 : 2 * W, DSTEP = 32 * NPL;     // uint4 of D per (lane, step) / per step
     const int lane = C.lane, p = C.p, nb = C.nb;
     const int buf = win & 1;
     // Column descriptors: only the selectors (.x, .y) are loaded per step, one step ahead.  The per-step "has an N / IUPAC
@@ -371,7 +377,7 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
     }
     uint2 xnext = __ldg(reinterpret_cast<const uint2 *>(xp));
     // forward: D slot of step t; reverse: D slot of the step fetched next (t + 1), i.e. forward step nb + 32 - (t + 1)
-    uint4 *dptr = C.D4 + ((C.sbase + (size_t)(FWD ? t0 - 1 : nb + 30 - t0)) * W) * 64 + lane;
+    uint4 *dptr = C.D4 + (C.sbase + (size_t)(FWD ? t0 - 1 : nb + 30 - t0)) * DSTEP + lane;
     const bool live = C.live;
 
     for (int t = t0; t <= t1; ++t) {
@@ -383,10 +389,10 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         if (!FWD) {
             if (live) {
 #pragma unroll
-                for (int i = 0; i < W * 2; ++i) cp_async16(&DS.d[(t + 1) & 1][i][lane], dptr + i * 32);
+                for (int i = 0; i < NPL; ++i) cp_async16(&DS.d[(t + 1) & 1][i][lane], dptr + i * 32);
             }
             cp_async_commit();
-            dptr -= W * 64;
+            dptr -= DSTEP;
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         }
         uint32_t uH[W], uG[W], uM[W];
@@ -399,14 +405,22 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
             uG[0] = g.x; uG[1] = g.y; uG[2] = g.z; uG[3] = g.w;
             uM[0] = m.x; uM[1] = m.y; uM[2] = m.z; uM[3] = m.w;
         }
+        if (FWD && live && DFMT == DFMT_OFF8) stcg16(dptr, S.pM, uM[0], uM[1], uM[2]);       // entry k = 0 of the four columns
+        uint4 dbase = make_uint4(0, 0, 0, 0);
+        if (!FWD && live && DFMT == DFMT_OFF8) dbase = DS.d[t & 1][0][lane];
         auto columns = [&](auto sp) {
             constexpr bool SPECIAL = decltype(sp)::value;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
                 if (FWD && live) {
                     const uint32_t upMprev = w == 0 ? S.pM : uM[w - 1];
-                    stcg16(dptr + w * 64, upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
-                    stcg16(dptr + w * 64 + 32, S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
+                    if (DFMT == DFMT_RAW) {
+                        stcg16(dptr + w * 64, upMprev, S.Ml[0], S.Ml[1], S.Ml[2]);
+                        stcg16(dptr + w * 64 + 32, S.Ml[3], S.Ml[4], S.Ml[5], S.Ml[6]);
+                    } else {
+                        const uint4 o = d8_encode(upMprev, S.Ml);
+                        stcg16(dptr + (1 + w) * 32, o.x, o.y, o.z, o.w);
+                    }
                 }
                 uint32_t S2[RPT];
                 const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
@@ -425,7 +439,14 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                     for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
                 }
                 uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
-                if (!FWD && live) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                uint32_t colbase = 0, colbest = 0;
+                if (!FWD && live) {
+                    if (DFMT == DFMT_RAW) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                    else {
+                        dc0 = DS.d[t & 1][1 + (W - 1 - w)][lane];
+                        colbase = (W - 1 - w) == 0 ? dbase.x : (W - 1 - w) == 1 ? dbase.y : (W - 1 - w) == 2 ? dbase.z : dbase.w;
+                    }
+                }
                 uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
@@ -437,21 +458,24 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                     const uint32_t Hc = s2 & 0xFFFEFFFEu;
                     const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
                     if (!FWD) {
-                        const uint4 dv = (k >> 2) ? dc1 : dc0;
-                        const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
-                        best = __vmaxu2(best, __vadd2(Mn, dk));
+                        if (DFMT == DFMT_RAW) {
+                            const uint4 dv = (k >> 2) ? dc1 : dc0;
+                            const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
+                            best = __vmaxu2(best, __vadd2(Mn, dk));
+                        } else colbest = __vmaxu2(colbest, __vadd2(Mn, d8_offset(dc0, k)));
                     }
                     dg = S.Hl[k];
                     S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
                     vG = G2; vM = Mn;
                 }
+                if (!FWD && DFMT == DFMT_OFF8) best = __vmaxu2(best, __vadd2(colbest, colbase));
                 constexpr int last = FWD ? RPT - 1 : 0;
                 S.oH[w] = S.Hl[last]; S.oG[w] = S.Gl[last]; S.oM[w] = S.Ml[last];
             }
         };
         if (!special) columns(std::false_type{});
         else                           columns(std::true_type{});
-        if (FWD) dptr += W * 64;
+        if (FWD) dptr += DSTEP;
         S.pH = uH[W - 1]; S.pM = uM[W - 1];
         const int b = t - p;
         if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
@@ -478,13 +502,12 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
 }
 
 // dispatch on whether the window is steady (all lanes active in all of its steps)
-template <int DIR, int MODE>
-__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win,
-                                                 uint32_t &best, const TraceOut &TO)
+template <int DIR, int DFMT>
+__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win, uint32_t &best)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
-    if (MODE == MODE_FAST && t0 >= 32 && t1 <= C.nb) sweep_window_steady<DIR>(C, S, R, DS, win, t0, t1, best);
-    else                        sweep_window<DIR, MODE, true>(C, S, R, DS, win, t0, t1, best, TO);
+    if (t0 >= 32 && t1 <= C.nb) sweep_window_steady<DIR, DFMT>(C, S, R, DS, win, t0, t1, best);
+    else                        sweep_window_edge<DIR, DFMT>(C, S, R, DS, win, t0, t1, best);
 }
 
 // The main sweep of one pair in one direction: checkpoints, tile maxima, all windows of the strips si0, si0 + stride, ...
@@ -496,7 +519,6 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
                                 const int si0 = 0, const int stride = 1, volatile int *prog = nullptr)
 {
     constexpr bool FWD = DIR > 0;
-    const TraceOut none{nullptr, nullptr, nullptr, 0, 0};
     for (int si = si0; si < T.nstrips; si += stride) {
         const int s = FWD ? si : T.nstrips - 1 - si;
         StripCtx<DIR> C;
@@ -520,7 +542,8 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
             __syncwarp();
             if (!C.first && win + 1 < C.nwin) { wait_blocks(win + 1); ring_prefetch(C, R, win + 1, (win + 1) & 1); }
             state_save(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
-            sweep_window_any<DIR, MODE_FAST>(C, S, R, DS, win, best, none);
+            if (C.dfmt == DFMT_OFF8) sweep_window_any<DIR, DFMT_OFF8>(C, S, R, DS, win, best);
+            else                     sweep_window_any<DIR, DFMT_RAW>(C, S, R, DS, win, best);
             if (!FWD) { C.tilemax[(size_t)(s * C.nwin + win) * 32 + lane] = best; best = 0; }
         }
         // the maxima at the last processed column: Fmax[.][len1] (forward) / Rmax[.][1] (reverse)
@@ -596,12 +619,19 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) S2[k] = prmt(C.Ta[k], C.Tb[k], sel);
             }
-            uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+            uint32_t dk[RPT] = {0, 0, 0, 0, 0, 0, 0, 0};
             if (!FWD && TRACE_M && C.live) {    // shifted forward maxima of this column (for the hot bits)
-                const uint4 *src = C.D4 + ((C.sbase + (size_t)(nb + 31 - t)) * W + (W - 1 - w)) * 64 + lane;
-                d0 = __ldcg(src); d1 = __ldcg(src + 32);
+                const uint4 *slot = C.D4 + (C.sbase + (size_t)(nb + 31 - t)) * C.dstep + lane;
+                if (C.dfmt == DFMT_RAW) {
+                    const uint4 d0 = __ldcg(slot + (W - 1 - w) * 64), d1 = __ldcg(slot + (W - 1 - w) * 64 + 32);
+                    dk[0] = d0.x; dk[1] = d0.y; dk[2] = d0.z; dk[3] = d0.w; dk[4] = d1.x; dk[5] = d1.y; dk[6] = d1.z; dk[7] = d1.w;
+                } else {
+                    const uint32_t base = __ldcg(reinterpret_cast<const uint32_t *>(slot) + (W - 1 - w));
+                    const uint4 o = __ldcg(slot + (1 + (W - 1 - w)) * 32);
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) dk[k] = base + d8_offset(o, k);
+                }
             }
-            const uint32_t dk[RPT] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
             uint32_t vG = upG, vM = upM, codes = 0;
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {

@@ -179,11 +179,13 @@ def test_two_devices_same_results(eng):
         assert not diff_summary(y, x)
 
 
-@pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_QUEUE_CAP": "4"}])
+@pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_QUEUE_CAP": "4"}, {"AGE_DFMT": "raw"},
+                                  {"AGE_DFMT": "raw", "AGE_LONG_NW": "1"}])
 def test_golden_records_other_kernel_paths(eng, knob, monkeypatch):
     """The same golden batch through the code paths a small batch does not take by itself: one warp per pair
-    (the kernel large batches use), 16 warps per pair (long alignments), and a work list too short for the
-    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand."""
+    (the kernel large batches use), 16 warps per pair (long alignments), a work list too short for the
+    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand, and the 16-bit storage format of the
+    forward-maxima plane (by default only scorings with match or mismatch above 15 use it)."""
     for k, v in knob.items():
         monkeypatch.setenv(k, v)
     jobs, owner = [], []
@@ -229,7 +231,10 @@ def test_scoring_corners(eng):
     """gap extension dearer than gap opening (the flipped tag branch), large match scores, equal open / extend"""
     rng = np.random.default_rng(5)
     jobs = []
-    for sc in [(1, -1, -1, -3), (5, -4, -3, -3), (63, -63, -40, -2), (2, -1, -2, -7), (1, -3, -100, -1), (7, -2, -1, -1)]:
+    # (15, ..) is the largest step the 8-bit row offsets of the forward-maxima plane hold, (16, ..) the first scoring on the
+    # 16-bit planes; (2, 9, ..) rewards mismatches more than matches (the offset bound is max(match, mismatch))
+    for sc in [(1, -1, -1, -3), (5, -4, -3, -3), (63, -63, -40, -2), (2, -1, -2, -7), (1, -3, -100, -1), (7, -2, -1, -1),
+               (15, -4, -3, -3), (16, -4, -3, -3), (2, 9, -3, -2), (15, -15, -1, -1)]:
         for flag in FLAGS:
             w, q = sv_pair(rng, int(rng.integers(120, 420)), int(rng.integers(20, 60)), ["del", "ins", "tdup", "inv"][flag % 4])
             jobs.append((w, q, flag, *sc))
