@@ -381,11 +381,10 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
     const bool live = C.live;
 
     for (int t = t0; t <= t1; ++t) {
-        uint4 xb = make_uint4(xnext.x, xnext.y, 0, 0);
+        const uint2 xb = xnext;
         xnext = __ldg(reinterpret_cast<const uint2 *>(++xp));
         const bool special = spec & 1u;
         spec >>= 1;
-        if (special) xb.z = __ldg(&xp[-1].z);
         if (!FWD) {
             if (live) {
 #pragma unroll
@@ -410,6 +409,9 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         if (!FWD && live && DFMT == DFMT_OFF8) dbase = DS.d[t & 1][0][lane];
         auto columns = [&](auto sp) {
             constexpr bool SPECIAL = decltype(sp)::value;
+            // the per-column N / IUPAC codes are only fetched on the rare path: even a predicated-off load in the common
+            // path costs a scoreboard wait on its destination register
+            const uint32_t xz = SPECIAL ? __ldg(&xp[-1].z) : 0u;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
                 if (FWD && live) {
@@ -424,7 +426,7 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                 }
                 uint32_t S2[RPT];
                 const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
-                const uint32_t info = SPECIAL ? (xb.z >> (8 * w)) & 0xFFu : 0u;
+                const uint32_t info = SPECIAL ? (xz >> (8 * w)) & 0xFFu : 0u;
                 if (SPECIAL && (info & 1u)) {
                     const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
                     const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
