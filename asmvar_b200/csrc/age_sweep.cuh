@@ -356,7 +356,7 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
 // GUARD = false, MODE_FAST, written for instruction count -- running pointers instead of per-step address arithmetic,
 // no clamps on the column descriptors (1 <= t - p <= nb throughout), and the N / IUPAC test hoisted out of the
 // column loop (one copy of the step body without it, one with it).
-template <int DIR, int DFMT>
+template <int DIR, int DFMT, bool FLIP>
 __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
                                                     const int t0, const int t1, uint32_t &best)
 {
@@ -455,9 +455,13 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                     const int k = FWD ? j : RPT - 1 - j;
                     const uint32_t g  = __vmaxs2(S.Gl[k], vG);
                     const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);
-                    const uint32_t tg = (s2 ^ C.flip) & 0x00010001u;
+                    const uint32_t tg = FLIP ? (~s2 & 0x00010001u) : (s2 & 0x00010001u);
                     const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
-                    const uint32_t Hc = s2 & 0xFFFEFFFEu;
+                    // clearing the tags: with FLIP = false tg IS the tag pair, and s2 - tg cannot borrow between the halves,
+                    // so the subtraction can run as a multiply-add on the FMA pipe (the ALU pipe is the busy one)
+                    uint32_t Hc;
+                    if (FLIP) Hc = s2 & 0xFFFEFFFEu;
+                    else asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, %2;" : "=r"(Hc) : "r"(tg), "r"(s2));
                     const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
                     if (!FWD) {
                         if (DFMT == DFMT_RAW) {
@@ -508,7 +512,10 @@ template <int DIR, int DFMT>
 __device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win, uint32_t &best)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
-    if (t0 >= 32 && t1 <= C.nb) sweep_window_steady<DIR, DFMT>(C, S, R, DS, win, t0, t1, best);
+    if (t0 >= 32 && t1 <= C.nb) {
+        if (C.flip == 0) sweep_window_steady<DIR, DFMT, false>(C, S, R, DS, win, t0, t1, best);
+        else             sweep_window_steady<DIR, DFMT, true>(C, S, R, DS, win, t0, t1, best);
+    }
     else                        sweep_window_edge<DIR, DFMT>(C, S, R, DS, win, t0, t1, best);
 }
 
