@@ -70,7 +70,7 @@ struct PairTask {
                                          //   RAW  [s][t][w][h][lane][4]: k = 4h+j -> 2*Fmax[256s + 8l + k][W(t-l-1) + w]
                                          //   = what the reverse cell (row+1, col+1) adds (K6, :545-550)
                                          //   OFF8 [s][t][5][lane][4]: plane 0 = entry k = 0 of the 4 columns, plane 1+w = offsets of
-                                         //   column w, word j = bytes {A_2j, B_2j, A_2j+1, B_2j+1} (A / B = the halves of the pair)
+                                         //   column w, word j = bytes {A_2j, A_2j+1, B_2j, B_2j+1} (A / B = the halves of the pair)
     uint32_t *Dlast;                     // [P + 1]  2*Fmax[r][len1]
     uint32_t *Dtail;                     // [W*nb + 1] 2*Fmax[P][c] (only read when len2 == P)
     uint32_t *Rfirst;                    // [P + 2]  2*Rmax[r][1]

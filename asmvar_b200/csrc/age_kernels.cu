@@ -262,8 +262,8 @@ struct View {
         const size_t slot = (size_t)(r >> 8) * nsteps + (t - 1);
         if (T->dfmt == DFMT_RAW) return T->D[(((slot * W + w) * 2 + (k >> 2)) * 32 + l) * 4 + (k & 3)];
         const uint32_t *q = T->D + (slot * 5 * 32 + l) * 4;                      // OFF8: entry 0 of the column + the row's offset bytes
-        const uint32_t wd = q[(size_t)(1 + w) * 128 + (k >> 1)] >> (16 * (k & 1));
-        return q[w] + ((wd & 0xFFu) | ((wd & 0xFF00u) << 8));
+        const uint32_t wd = q[(size_t)(1 + w) * 128 + (k >> 1)] >> (8 * (k & 1));       // bytes {A_2j, A_2j+1, B_2j, B_2j+1}
+        return q[w] + (wd & 0x00FF00FFu);
     }
     __device__ int F2(int r, int c) const { return (F2w(r, c) >> (16 * half)) & 0xFFFF; }
     __device__ int R2(int r, int c) const {              // 2 * Rmax[r][c]; needs ensure_rm(strip of r)

@@ -54,16 +54,18 @@ __device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
     return t;
 }
 
-// OFF8 format of D (age_device.cuh): the entries of one (lane, block column) are `base` (row k = 0) and Ml[0..6] (k = 1..7)
+// OFF8 format of D (age_device.cuh): the entries of one (lane, block column) are `base` (row k = 0) and Ml[0..6] (k = 1..7).
+// Word j holds rows 2j and 2j+1 as bytes {A_2j, A_2j+1, B_2j, B_2j+1} = offset(2j) + 256 * offset(2j+1) on the packed pairs:
+// one multiply-add per word on the FMA pipe (the ALU pipe is the one the recurrence saturates).
 __device__ __forceinline__ uint4 d8_encode(uint32_t base, const uint32_t (&Ml)[RPT])
 {   // neither half can borrow: the maxima grow with the row
-    return make_uint4(prmt(0u, Ml[0] - base, 0x6420), prmt(Ml[1] - base, Ml[2] - base, 0x6420),
-                      prmt(Ml[3] - base, Ml[4] - base, 0x6420), prmt(Ml[5] - base, Ml[6] - base, 0x6420));
+    return make_uint4((Ml[0] - base) * 256u, (Ml[2] - base) * 256u + (Ml[1] - base),
+                      (Ml[4] - base) * 256u + (Ml[3] - base), (Ml[6] - base) * 256u + (Ml[5] - base));
 }
 __device__ __forceinline__ uint32_t d8_offset(const uint4 &o, int k)       // packed offset of row k (0 in the upper bytes)
 {
     const uint32_t wd = (k >> 1) == 0 ? o.x : (k >> 1) == 1 ? o.y : (k >> 1) == 2 ? o.z : o.w;
-    return prmt(wd, 0u, (k & 1) ? 0x4342 : 0x4140);
+    return (k & 1) ? prmt(wd, 0u, 0x4341) : (wd & 0x00FF00FFu);
 }
 
 struct LaneState {
