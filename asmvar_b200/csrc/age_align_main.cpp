@@ -380,8 +380,8 @@ int mode_count(int flag)
     return n;
 }
 
-// candidates per age_align_batch call: 1.5 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
-const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 3552); }();
+// candidates per batch: 2.5 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
+const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 5920); }();
 
 // ---------------------------------------------------------------------------------------------------------
 // batch dialect (age_align.cpp)

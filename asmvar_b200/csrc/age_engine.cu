@@ -80,6 +80,7 @@ struct HostPair {
     int select;                  // 1: only the better half needs breakpoints (see PairTask::select)
     int len1, len2, nstrips, P, nb, nsteps, nwin;
     int k7;                      // holds a TDUP / INVL / INVR aligner (pass 2 then needs the reverse maxima plane)
+    int dfmt;                    // storage format of the D plane (DFMT_RAW / DFMT_OFF8, age_device.cuh)
     int nsets; size_t set_bytes;  // pass-2 trace plane sets (one per aligner that gets breakpoints)
     size_t in_bytes, scratch_bytes;
     double cells;
@@ -163,6 +164,8 @@ int check_range(const age_job &j)
 
 void build_plan(Batch *B, const age_job *jobs, size_t n)
 {
+    const char *dfmt_env = getenv("AGE_DFMT");                      // test knob: "raw" keeps the 16-bit D planes
+    const bool force_raw = dfmt_env && strcmp(dfmt_env, "raw") == 0;
     B->n_jobs = n;
     B->job_status.assign(n, AGE_OK);
     B->aligners.clear(); B->pairs.clear();
@@ -199,8 +202,10 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
         hp.nb = (j.len1 + W - 1) / W; hp.nsteps = hp.nb + 31; hp.nwin = (hp.nsteps + CKS - 1) / CKS;
         hp.k7 = (B->aligners[a0].flag != F_INDEL) || (a1 >= 0 && B->aligners[a1].flag != F_INDEL);
         const size_t slots = (size_t)hp.nstrips * hp.nsteps;                 // (strip, step) slots of the diagonal-major planes
+        // D as 8-bit row offsets when a DP step can add at most 15 (age_device.cuh)
+        hp.dfmt = (!force_raw && std::max((int)j.match, (int)j.mismatch) <= 15) ? DFMT_OFF8 : DFMT_RAW;
         hp.in_bytes = 2 * (align_up((size_t)j.len1, 16) + align_up((size_t)j.len2, 16));   // raw sequences of both halves
-        hp.scratch_bytes = align_up(slots * W * 2 * 32 * 16, 256) +
+        hp.scratch_bytes = align_up(slots * d_planes(hp.dfmt) * 32 * 16, 256) +
                            2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16, 256) +
                            2 * align_up(((size_t)hp.P + 2) * 4, 256) + align_up(((size_t)W * hp.nb + 4) * 4, 256) +
                            align_up((size_t)hp.nstrips * hp.nwin * 32 * 4, 256) +
@@ -241,7 +246,7 @@ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi
 
 // Copy the raw sequences of pair `pi` into the pinned host blob at `h` (device address `d`) and fill its task record.
 // The column descriptors and row tables are derived from the raw strings on the device (age_pack_kernel).
-void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, PairTask &T, bool force_raw)
+void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, PairTask &T)
 {
     const HostPair &hp = B->pairs[pi];
     memset(&T, 0, sizeof(T));
@@ -275,10 +280,7 @@ void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, Pa
     // identical scoring
     T.c0x = pack2(c0x[0], c0x[1]); T.kabs = (uint32_t)kabs[0]; T.flip = pack2(flip[0], flip[1]); T.gborder = pack2(gb[0], gb[1]);
     T.m2 = pack2(2 * sc[0][0], 2 * sc[1][0]); T.mm2 = pack2(2 * sc[0][1], 2 * sc[1][1]);
-    // D as 8-bit row offsets when a DP step can add at most 15 (age_device.cuh); AGE_DFMT=raw forces the 16-bit planes (tests)
-    int smax = 0;
-    for (int k = 0; k < 2; ++k) smax = std::max(smax, std::max(sc[k][0], sc[k][1]));
-    T.dfmt = (!force_raw && smax <= 15) ? DFMT_OFF8 : DFMT_RAW;
+    T.dfmt = hp.dfmt;
 }
 
 void assign_scratch(const HostPair &hp, char *s, PairTask &T)
@@ -286,7 +288,7 @@ void assign_scratch(const HostPair &hp, char *s, PairTask &T)
     const size_t slots = (size_t)hp.nstrips * hp.nsteps;
     const size_t bsz = align_up((size_t)std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16, 256);
     const size_t csz = align_up((size_t)hp.nstrips * hp.nwin * CKW * 32 * 4, 256);
-    T.D = (uint32_t *)s; s += align_up(slots * W * 2 * 32 * 16, 256);
+    T.D = (uint32_t *)s; s += align_up(slots * d_planes(hp.dfmt) * 32 * 16, 256);
     T.bnd_f = (uint4 *)s; s += bsz;
     T.bnd_r = (uint4 *)s; s += bsz;
     T.Dlast = (uint32_t *)s; s += align_up(((size_t)hp.P + 2) * 4, 256);
@@ -348,10 +350,8 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     if (!sl.outbuf.ensure(sl.out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
     if (!sl.hout.ensure(sl.out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
     if (!sl.aux.ensure(align_up(np * sizeof(PairHdr), 256) + (size_t)sl.queue_cap * sizeof(uint2))) { dev.err = "device allocation failed (work list)"; return false; }
-    const char *dfmt_env = getenv("AGE_DFMT");                      // test knob: "raw" keeps the 16-bit D planes
-    const bool force_raw = dfmt_env && strcmp(dfmt_env, "raw") == 0;
     parallel_for(ctx->host_threads, np, [&](size_t i) {
-        pack_pair(&B, jobs, pair_ids[i], sl.hin.ptr + task_bytes + in_off[i], sl.in.ptr + task_bytes + in_off[i], sl.tasks[i], force_raw);
+        pack_pair(&B, jobs, pair_ids[i], sl.hin.ptr + task_bytes + in_off[i], sl.in.ptr + task_bytes + in_off[i], sl.tasks[i]);
         assign_scratch(B.pairs[pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
     });
     memcpy(sl.hin.ptr, sl.tasks.data(), np * sizeof(PairTask));

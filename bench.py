@@ -167,11 +167,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=3552, help="candidates per step per GPU (3552 = 1.5 pairs per resident warp: 148 SMs x 16 warps; the longest-first deal needs more pairs than warps to balance)")
+    ap.add_argument("--batch", type=int, default=5920, help="candidates per step per GPU (5920 = 2.5 pairs per resident warp: 148 SMs x 16 warps; about 137 GB of scratch; the longest-first deal needs more pairs than warps to balance)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cli", action="store_true", help="skip the age_align process leg (FASTA in -> .age out)")
-    ap.add_argument("--cli-candidates", type=int, default=99456, help="candidates of the age_align process leg (C2 asks for N = 100 000; 28 chunks of 3552)")
+    ap.add_argument("--cli-candidates", type=int, default=100640, help="candidates of the age_align process leg (C2 asks for N = 100 000; 17 chunks of 5920)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 (default, the configuration the metric is quoted on); c4 = -inv 20 kb x 4 kb; c5 = 50 kb x 10 kb -indel -both "
                          "(extra measurements, not the headline)")
