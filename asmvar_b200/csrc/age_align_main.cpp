@@ -488,24 +488,44 @@ int batch_main(int argc, char **argv)
     prof("variant table parsed");
     if (regs.empty()) cerr << "[WARNING] The variant list is empty!\n";
 
+    // The windows of one chunk are cut out of the FASTA records on all host cores (the reference copies the whole record per
+    // candidate, age_align.cpp:244-245); look-ups and error checks stay in table order.
+    const string usel = upper(sel);
+    const bool all = usel == "ALL";
+    struct Pick { const Reg *r; const string *t, *q; };
+    vector<Pick> picks;
     vector<Candidate> cands;
+    auto cut = [&]() {
+        cands.resize(picks.size());
+        parallel_for(picks.size(), [&](size_t i) {
+            const Reg &r = *picks[i].r;
+            Candidate &c = cands[i];
+            c.header = "# " + r.info + "\n";
+            c.ok = substr(*picks[i].t, r.tid, (int)r.ts, (int)r.te, c.s1) && substr(*picks[i].q, r.qid, (int)r.qs, (int)r.qe, c.s2);
+            if (c.ok) {
+                if (o.revcom1) c.s1.revcom();
+                if (o.revcom2) c.s2.revcom();
+                if (o.both) { c.s3 = c.s2; c.s3.revcom(); }
+            }
+        });
+        for (size_t i = 0; i < picks.size(); ++i)
+            if (!cands[i].ok) {
+                const Reg &r = *picks[i].r;
+                cerr << "# [ERROR] bad region " << r.tid << ":" << r.ts << "-" << r.te << " / " << r.qid << ":" << r.qs << "-" << r.qe << "\n";
+            }
+        picks.clear();
+        flush_candidates(cands, o, true);
+    };
     for (const Reg &r : regs) {
-        if (upper(sel) != "ALL" && upper(sel) != upper(r.tid)) continue;
-        if (!tfa.count(r.tid)) { flush_candidates(cands, o, true); drain_candidates(); cerr << "# [ERROR] " << r.tid << " is not in " << tfile << "\n"; die(1); }
-        if (!qfa.count(r.qid)) { flush_candidates(cands, o, true); drain_candidates(); cerr << "# [ERROR] " << r.qid << " is not in " << qfile << "\n"; die(1); }
-        Candidate c;
-        c.header = "# " + r.info + "\n";
-        c.ok = substr(tfa[r.tid], r.tid, (int)r.ts, (int)r.te, c.s1) && substr(qfa[r.qid], r.qid, (int)r.qs, (int)r.qe, c.s2);
-        if (!c.ok) cerr << "# [ERROR] bad region " << r.tid << ":" << r.ts << "-" << r.te << " / " << r.qid << ":" << r.qs << "-" << r.qe << "\n";
-        else {
-            if (o.revcom1) c.s1.revcom();
-            if (o.revcom2) c.s2.revcom();
-            if (o.both) { c.s3 = c.s2; c.s3.revcom(); }
-        }
-        cands.push_back(std::move(c));
-        if (cands.size() >= CHUNK) flush_candidates(cands, o, true);
+        if (!all && usel != upper(r.tid)) continue;
+        const auto ti = tfa.find(r.tid);
+        if (ti == tfa.end()) { cut(); drain_candidates(); cerr << "# [ERROR] " << r.tid << " is not in " << tfile << "\n"; die(1); }
+        const auto qi = qfa.find(r.qid);
+        if (qi == qfa.end()) { cut(); drain_candidates(); cerr << "# [ERROR] " << r.qid << " is not in " << qfile << "\n"; die(1); }
+        picks.push_back(Pick{&r, &ti->second, &qi->second});
+        if (picks.size() >= CHUNK) cut();
     }
-    flush_candidates(cands, o, true);
+    cut();
     prof("all windows cut");
     drain_candidates();
     cerr << "\n******************** AGE ALL DONE ********************\n";

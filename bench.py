@@ -37,13 +37,13 @@ sys.path.insert(0, str(ROOT))
 
 SCORING = (1, -1, -10, -1)          # AgeOption.h:25-28 (AsmvarDetect defaults) = Test2/Run.sh
 ALG_BYTES_PER_CELL_UPDATE = 2.5     # indel = 5 B per matrix cell = 2.5 B per cell update
-# DRAM traffic of age_sweep_kernel from the committed `ncu --set full` capture (profiles/r1_sweep_kernel_ncu_key_metrics.txt):
-# dram__bytes_read.sum 93.39 GB + dram__bytes_write.sum 96.79 GB for one launch over 81.94 G cell updates
-NCU_DRAM_BYTES_PER_CELL_UPDATE = (93.392639e9 + 96.789729e9) / 81.94e9
+# DRAM traffic of age_sweep_kernel from the committed `ncu --set full` capture (profiles/r1b_sweep_kernel_ncu_key_metrics.txt):
+# dram__bytes_read.sum 96.09 GB + dram__bytes_write.sum 101.08 GB for one launch over 137.24 G cell updates (5920 candidates)
+NCU_DRAM_BYTES_PER_CELL_UPDATE = (96.086718e9 + 101.077318e9) / 137.23574e9
 KERNELS_PER_STEP = 8                # age_pack, age_sweep, age_select, age_presweep x2, age_enum, age_blocks (+ the pack of the stage call)
 # s16x2 / logic instructions of the recurrence per cell pair: VIMNMX, PRMT, VIADDMNMX, LOP3, VIADD,
-# LOP3, VIMNMX3 in both sweeps, + VIADD, VIMNMX.U16x2 for the split sum in the reverse sweep  => (7 + 9) / 2 per pair-cell
-# visit, and a pair-cell visit is two cell updates
+# tag clearing, VIMNMX3 in both sweeps, + offset decode and VIADDMNMX.U16x2 for the split sum in the reverse sweep
+# => (7 + 9) / 2 per pair-cell visit, and a pair-cell visit is two cell updates
 SIMD_INSTR_PER_CELL_UPDATE = (7 + 9) / 2 / 2
 WORKLOAD = "C2 synthetic indel candidates: 5 kb windows, 2x500 bp flanks, -indel -both, 1/-1/-10/-1"
 
@@ -279,6 +279,8 @@ def main():
         value = total_c / (k_ms / 1e3)
         hbm, which = measured_peaks()
         ach = ALG_BYTES_PER_CELL_UPDATE * cu * args.steps / (fill_ms / 1e3) / 1e9
+        traffic = NCU_DRAM_BYTES_PER_CELL_UPDATE * cu / 1e9 if args.workload == "c2" else None
+        dram_ach = None if traffic is None else traffic * args.steps / (fill_ms / 1e3)
         out = {
             "metric": "AGE realignments/sec", "value": value, "unit": "realignments/s", "gcups": total_cu / (k_ms / 1e3) / 1e9,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": k_ms / args.steps,
@@ -293,10 +295,14 @@ def main():
             "gpu_launches": launches,
             "kernel_wall_ms_per_step": wall_ms / args.steps,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         "traffic": NCU_DRAM_BYTES_PER_CELL_UPDATE * cu / 1e9 if args.workload == "c2" else None, "traffic_unit": "GB per launch",
+                         "traffic": traffic, "traffic_unit": "GB per launch",
+                         "dram_achieved": dram_ach, "dram_frac": None if dram_ach is None else dram_ach / hbm,
                          "kernel": "age_sweep_kernel", "peak_source": which,
-                         "note": "achieved = 2.5 algorithmic B per cell update (SURVEY 8d) x cell updates of one launch / its CUDA-event time, per GPU; "
-                                 "traffic = ncu dram read+write of the committed capture (2.32 B per cell update) scaled to this launch"},
+                         "note": "achieved = 2.5 algorithmic B per cell update (SURVEY 8d: 16-bit Fmax written + read, 1 trace byte per cell) x cell "
+                                 "updates of one launch / its CUDA-event time, per GPU.  frac can exceed 1: this design moves fewer bytes than that "
+                                 "model (no trace in the main sweep, Fmax as 8-bit row offsets): traffic = ncu dram read+write of the committed "
+                                 "capture (1.44 B per cell update) scaled to this launch, dram_achieved = traffic / the same time.  The kernel is "
+                                 "bound by integer SIMD issue (int_roofline, ALU pipe 72 % active in the capture)"},
         }
         peak = C.c_double(0.0)
         if capi.load().age_int16_peak(local, C.byref(peak)) == 0 and peak.value > 0:
