@@ -746,8 +746,11 @@ age_select_kernel(Pass2Params prm)
 
 // ---- pre-sweep: one warp per queued window, at full occupancy ------------------------------------------------------
 constexpr int PRE_WARPS = 4;
+#ifndef PRE_OCC
+#define PRE_OCC 4
+#endif
 
-__global__ void __launch_bounds__(PRE_WARPS * 32)
+__global__ void __launch_bounds__(PRE_WARPS * 32, PRE_OCC)
 age_presweep_kernel(Pass2Params prm, int round)
 {
     __shared__ WarpRings rings[PRE_WARPS];
@@ -934,10 +937,10 @@ void launch_pass2(const Pass2Params &p, cudaStream_t st)
     cudaMemsetAsync(p.queue_n, 0, sizeof(int32_t), st);
     const int nb = (p.n_pairs + 3) / 4;
     age_select_kernel<<<std::min(nb, sms * 8), SEL_WARPS * 32, 0, st>>>(p);
-    age_presweep_kernel<<<sms * 4, PRE_WARPS * 32, 0, st>>>(p, 0);      // windows along the split row / column (maxima trace)
+    age_presweep_kernel<<<sms * PRE_OCC, PRE_WARPS * 32, 0, st>>>(p, 0);      // windows along the split row / column (maxima trace)
     cudaMemsetAsync(p.queue_n, 0, sizeof(int32_t), st);
     age_enum_kernel<<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
-    age_presweep_kernel<<<sms * 4, PRE_WARPS * 32, 0, st>>>(p, 1);      // windows along the traceback paths (scores trace)
+    age_presweep_kernel<<<sms * PRE_OCC, PRE_WARPS * 32, 0, st>>>(p, 1);      // windows along the traceback paths (scores trace)
     age_blocks_kernel<<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
     if (prof) {
         unsigned long long z[8];

@@ -587,6 +587,8 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
     const int lane = C.lane, p = C.p, nb = C.nb, buf = win & 1;
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
     const int prev_lane = FWD ? (lane + 31) & 31 : (lane + 1) & 31;
+    const uint32_t hbit = 1u << TO.sh, hmask = 0xFFFFu << TO.sh, hsign = 0x8000u << TO.sh;   // the wanted half of a packed word
+    const uint32_t maxw = (uint32_t)TO.max2 << TO.sh;
 #pragma unroll
     for (int w = 0; w < W; ++w) { X.oH[w][lane] = S.oH[w]; X.oG[w][lane] = S.oG[w]; X.oM[w][lane] = S.oM[w]; }
 
@@ -653,10 +655,22 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
                 const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
                 const uint32_t Hc = s2 & 0xFFFEFFFEu;
                 const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
-                if (TRACE_S) codes |= fs_code(half16(__vadd2(dg, S2[k]), TO.sh), half16(S.Gl[k], TO.sh), half16(vG, TO.sh)) << (2 * k);
-                if (TRACE_M) codes |= fm_code(half16(Hc, TO.sh), half16(S.Ml[k], TO.sh), half16(vM, TO.sh)) << (2 * k);
+                // Trace codes of the wanted half, read off the packed words the recurrence has anyway (fs_code / fm_code
+                // state the rules on plain integers):
+                //   FS: the cell's tag says gap (H / V) or not; among the gaps V wins iff the vertical candidate is the
+                //       larger-or-equal one (g == vG); without a gap the cell is D unless even the diagonal was negative.
+                //   FM: H iff the left maximum beats max(own, up), else V iff up beats own.
+                if (TRACE_S) {
+                    const bool gap = (s2 & hbit) != 0, vwin = ((g ^ vG) & hmask) == 0, dneg = (__vadd2(dg, S2[k]) & hsign) != 0;
+                    codes |= (gap ? (vwin ? T_VERT : T_HORI) : (dneg ? T_STOP : T_DIAG)) << (2 * k);
+                }
+                if (TRACE_M) {
+                    const uint32_t m1 = __vmaxs2(Hc, vM);
+                    const bool isH = ((Mn ^ m1) & hmask) != 0, isV = ((m1 ^ Hc) & hmask) != 0;
+                    codes |= (isH ? T_HORI : (isV ? T_VERT : T_STOP)) << (2 * k);
+                }
                 if (!FWD && TRACE_M) {
-                    if ((int)((__vadd2(Mn, dk[k]) >> TO.sh) & 0xFFFFu) == TO.max2) hotw |= 1u << (8 * w + k);
+                    if (((__vadd2(Mn, dk[k]) ^ maxw) & hmask) == 0) hotw |= 1u << (8 * w + k);
                 }
                 dg = S.Hl[k];
                 S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
