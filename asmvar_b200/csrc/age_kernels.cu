@@ -380,9 +380,33 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
     const int len2 = V.len2;
     int n_add = 0;
     bool stop = false;
-    for (int r = 0; r <= len2 && !stop; ++r) {                           // forward scan (:552-573)
+    // Most rows hold no candidate: the per-row column ranges are inspected 32 rows at a time (one per lane) and only the
+    // non-empty rows are visited, in the reference's order.
+    for (int rb = 0; rb <= len2 && !stop; rb += 32) {                     // forward scan (:552-573)
+      const int myr = min(rb + lane, len2), mylo = rlo[myr], myhi = rhi[myr];
+      const bool mine = rb + lane <= len2 && myhi >= mylo;
+      unsigned rows = __ballot_sync(0xFFFFFFFFu, mine);
+      if (rows && __all_sync(0xFFFFFFFFu, !mine || mylo == myhi)) {
+        // one candidate column per row (the split runs along a column: insertions): the 32 rows are tested side by side,
+        // hits are taken in row order
+        V.ensure_lanes(3, mine ? myr + 1 : -1, mylo + 1);
+        const bool tie = mine && V.tie_nc(myr, mylo);
+        V.ensure_lanes(1, tie ? myr : -1, mylo);
+        unsigned m = __ballot_sync(0xFFFFFFFFu, tie && V.code_nc(1, myr, mylo) == T_STOP);
+        while (m && !stop) {
+            const int b = __ffs(m) - 1; m &= m - 1;
+            const int c = __shfl_sync(0xFFFFFFFFu, mylo, b);
+            int lg1 = c, lg2 = rb + b, rg1 = c + 1, rg2 = rb + b + 1;
+            walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
+            const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+            if (res > 0) ++n_add;
+            if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+        }
+        continue;
+      }
+      while (rows && !stop) {
+        const int r = rb + __ffs(rows) - 1; rows &= rows - 1;
         const int lo = rlo[r], hi = rhi[r];
-        if (hi < lo) continue;
         for (int cb = lo & ~31; cb <= hi && !stop; cb += 32) {
             const int c = cb + lane;
             const bool in = c >= lo && c <= hi;
@@ -400,11 +424,30 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
                 if (n_add >= MAX_BP / 2 || res < 0) stop = true;
             }
         }
+      }
     }
     n_add = 0; stop = false;
-    for (int r = len2; r >= 0 && !stop; --r) {                            // reverse scan (:586-610)
+    for (int rb = len2 & ~31; rb >= 0 && !stop; rb -= 32) {               // reverse scan (:586-610)
+      const int myr = min(rb + lane, len2), mylo = rlo[myr], myhi = rhi[myr];
+      const bool mine = rb + lane <= len2 && myhi >= mylo;
+      unsigned rows = __ballot_sync(0xFFFFFFFFu, mine);
+      if (rows && __all_sync(0xFFFFFFFFu, !mine || mylo == myhi)) {
+        V.ensure_lanes(3, mine ? myr + 1 : -1, mylo + 1);
+        unsigned m = __ballot_sync(0xFFFFFFFFu, mine && V.tie_nc(myr, mylo) && V.code_nc(3, myr + 1, mylo + 1) == T_STOP);
+        while (m && !stop) {
+            const int b = 31 - __clz(m); m &= ~(1u << b);
+            const int c = __shfl_sync(0xFFFFFFFFu, mylo, b);
+            int lg1 = c, lg2 = rb + b, rg1 = c + 1, rg2 = rb + b + 1;
+            walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
+            const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+            if (res > 0) ++n_add;
+            if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+        }
+        continue;
+      }
+      while (rows && !stop) {
+        const int r = rb + 31 - __clz(rows); rows &= ~(1u << (r - rb));
         const int lo = rlo[r], hi = rhi[r];
-        if (hi < lo) continue;
         for (int cb = hi & ~31; cb >= (lo & ~31) && !stop; cb -= 32) {
             const int c = cb + lane;
             const bool in = c >= lo && c <= hi;
@@ -420,6 +463,7 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
                 if (n_add >= MAX_BP / 2 || res < 0) stop = true;
             }
         }
+      }
     }
 }
 
