@@ -438,7 +438,7 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
         OutLayout H = out_layout(sl, sl.hout.ptr);
         if (H.counters[2] > sl.pool_cap) {
             if (!rerun_with_pool(B, dev, sl, H.counters[2] + 4096)) return false;
-            st.launches += 9; st.fill_launches += 1;
+            st.launches += 7; st.fill_launches += 1;      // pack, sweep, select, 2 pre-sweeps, enumerate, blocks
             continue;
         }
         for (size_t i = 0; i < sl.pair_ids.size(); ++i) {
@@ -463,7 +463,7 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) st.fill_ms += ms;
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) st.kernel_ms += ms;
         if (cudaEventElapsedTime(&ms, sl.ev[5], sl.ev[6]) == cudaSuccess) st.d2h_ms += ms;
-        st.launches += 8; st.fill_launches += 1;
+        st.launches += 7; st.fill_launches += 1;          // pack, sweep, select, 2 pre-sweeps, enumerate, blocks
         return true;
     }
     dev.err = "block pool overflow";
@@ -785,7 +785,7 @@ extern "C" int age_run_staged(age_ctx *ctx)
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
     }
-    ctx->stats.launches += 8; ctx->stats.fill_launches += 1;
+    ctx->stats.launches += 6; ctx->stats.fill_launches += 1;       // sweep, select, 2 pre-sweeps, enumerate, blocks (packed at stage time)
     return 0;
 }
 

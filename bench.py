@@ -40,7 +40,8 @@ ALG_BYTES_PER_CELL_UPDATE = 2.5     # indel = 5 B per matrix cel
 # DRAM traffic of age_sweep_kernel from the committed `ncu --set full` capture (profiles/r1b_sweep_kernel_ncu_key_metrics.txt):
 # dram__bytes_read.sum 96.09 GB + dram__bytes_write.sum 101.08 GB for one launch over 137.24 G cell updates (5920 candidates)
 NCU_DRAM_BYTES_PER_CELL_UPDATE = (96.086718e9 + 101.077318e9) / 137.23574e9
-KERNELS_PER_STEP = 8                # age_pack, age_sweep, age_select, age_presweep x2, age_enum, age_blocks (+ the pack of the stage call)
+KERNELS_PER_STEP = 6                # per age_run_staged: age_sweep, age_select, age_presweep x2, age_enum, age_blocks (age_pack runs at stage time;
+                                    # an end-to-end step launches 7)
 # s16x2 / logic instructions of the recurrence per cell pair: VIMNMX, PRMT, VIADDMNMX, LOP3, VIADD,
 # tag clearing, VIMNMX3 in both sweeps, + offset decode and VIADDMNMX.U16x2 for the split sum in the reverse sweep
 # => (7 + 9) / 2 per pair-cell visit, and a pair-cell visit is two cell updates
