@@ -1,5 +1,5 @@
-// age_sweep.cuh -- the wavefront sweep shared by the main sweep kernel (MODE_FAST) and by the on-demand trace
-// recomputation of pass 2 (MODE_TRACE).
+// age_sweep.cuh -- the wavefront sweep: the main sweep kernels (sweep_window_steady / sweep_window_edge) and the trace
+// recomputation of pass 2 (sweep_window_compact).
 //
 // Reference semantics (src/AsmvarAGE/src/AGEaligner.cpp): K1/K2 calcScores :978-1083 and K3/K4 calcMaxima :862-976.
 // One warp sweeps one strip (32 lanes x 8 rows) of one pair along the reference window; lane p works on block
@@ -10,7 +10,7 @@
 
 namespace age {
 
-enum { MODE_FAST = 0, MODE_TRACE_S = 1, MODE_TRACE_M = 2 };   // S: FS / RS (scores trace), M: FM / RM (maxima trace) + hot bits
+enum { MODE_TRACE_S = 1, MODE_TRACE_M = 2 };   // trace re-sweeps: S = FS / RS (scores trace), M = FM / RM (maxima trace) + hot bits
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 {
@@ -20,7 +20,6 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s)
 }
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
-__device__ __forceinline__ int half16(uint32_t v, int sh) { return (int)(short)((v >> sh) & 0xFFFFu); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -36,24 +35,6 @@ __device__ __forceinline__ int subst2(int xc, int yc, int m2, int mm2)
     if (xc >= 5 || yc >= 5) return 0;
     return xc == yc ? m2 : mm2;
 }
-// FS code of one cell from its three (2x+tag) candidates -- the tie order of :1015-1017
-__device__ __forceinline__ uint32_t fs_code(int d, int h, int v)
-{
-    int s = d; uint32_t t = T_DIAG;
-    if (h >= s) { s = h; t = T_HORI; }
-    if (v >= s) { s = v; t = T_VERT; }
-    if (s < 0) t = T_STOP;
-    return t;
-}
-// FM code (:899-915 / :952-968): VERTICAL is tested first, HORIZONTAL overrides when strictly greater
-__device__ __forceinline__ uint32_t fm_code(int own, int left, int up)
-{
-    int cur = own; uint32_t t = T_STOP;
-    if (up > cur)   { cur = up; t = T_VERT; }
-    if (left > cur) { t = T_HORI; }
-    return t;
-}
-
 // OFF8 format of D (age_device.cuh): the entries of one (lane, block column) are `base` (row k = 0) and Ml[0..6] (k = 1..7).
 // Word j holds rows 2j and 2j+1 as bytes {A_2j, A_2j+1, B_2j, B_2j+1} = offset(2j) + 256 * offset(2j+1) on the packed pairs:
 // one multiply-add per word on the FMA pipe (the ALU pipe is the one the recurrence saturates).
@@ -354,8 +335,8 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
     }
 }
 
-// The steady-state window of the main sweep (every lane active in every step, 32 <= t0, t1 <= nb): sweep_window with
-// GUARD = false, MODE_FAST, written for instruction count -- running pointers instead of per-step address arithmetic,
+// The steady-state window of the main sweep (every lane active in every step, 32 <= t0, t1 <= nb), written for
+// instruction count -- running pointers instead of per-step address arithmetic,
 // no clamps on the column descriptors (1 <= t - p <= nb throughout), and the N / IUPAC test hoisted out of the
 // column loop (one copy of the step body without it, one with it).
 template <int DIR, int DFMT, bool FLIP>
@@ -655,11 +636,12 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
                 const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
                 const uint32_t Hc = s2 & 0xFFFEFFFEu;
                 const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
-                // Trace codes of the wanted half, read off the packed words the recurrence has anyway (fs_code / fm_code
-                // state the rules on plain integers):
-                //   FS: the cell's tag says gap (H / V) or not; among the gaps V wins iff the vertical candidate is the
-                //       larger-or-equal one (g == vG); without a gap the cell is D unless even the diagonal was negative.
-                //   FM: H iff the left maximum beats max(own, up), else V iff up beats own.
+                // Trace codes of the wanted half, read off the packed words the recurrence has anyway.
+                //   FS (:1015-1017: s = d, t = D; if h >= s: H; if v >= s: V; if s < 0: stop): the cell's tag says gap (H / V)
+                //       or not; among the gaps V wins iff the vertical candidate is the larger-or-equal one (g == vG);
+                //       without a gap the cell is D unless even the diagonal candidate was negative.
+                //   FM (:899-915 / :952-968: V if up > own, then H if left > the larger of the two): H iff the left maximum
+                //       beats max(own, up), else V iff up beats own.
                 if (TRACE_S) {
                     const bool gap = (s2 & hbit) != 0, vwin = ((g ^ vG) & hmask) == 0, dneg = (__vadd2(dg, S2[k]) & hsign) != 0;
                     codes |= (gap ? (vwin ? T_VERT : T_HORI) : (dneg ? T_STOP : T_DIAG)) << (2 * k);
