@@ -386,21 +386,28 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
       const int myr = min(rb + lane, len2), mylo = rlo[myr], myhi = rhi[myr];
       const bool mine = rb + lane <= len2 && myhi >= mylo;
       unsigned rows = __ballot_sync(0xFFFFFFFFu, mine);
-      if (rows && __all_sync(0xFFFFFFFFu, !mine || mylo == myhi)) {
-        // one candidate column per row (the split runs along a column: insertions): the 32 rows are tested side by side,
-        // hits are taken in row order
-        V.ensure_lanes(3, mine ? myr + 1 : -1, mylo + 1);
-        const bool tie = mine && V.tie_nc(myr, mylo);
-        V.ensure_lanes(1, tie ? myr : -1, mylo);
-        unsigned m = __ballot_sync(0xFFFFFFFFu, tie && V.code_nc(1, myr, mylo) == T_STOP);
-        while (m && !stop) {
-            const int b = __ffs(m) - 1; m &= m - 1;
-            const int c = __shfl_sync(0xFFFFFFFFu, mylo, b);
-            int lg1 = c, lg2 = rb + b, rg1 = c + 1, rg2 = rb + b + 1;
-            walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
-            const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-            if (res > 0) ++n_add;
-            if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+      if (rows && __all_sync(0xFFFFFFFFu, !mine || myhi - mylo < 4)) {
+        // at most four candidate columns per row (the split runs along a column: insertions): 8 rows x 4 columns are tested
+        // side by side, lane order = row-major order, hits are taken in that order
+        for (int sub = 0; sub < 32 && !stop; sub += 8) {
+            if (!((rows >> sub) & 0xFFu)) continue;
+            const int src = sub + (lane >> 2);
+            const int r = rb + src, lo = __shfl_sync(0xFFFFFFFFu, mylo, src), hi = __shfl_sync(0xFFFFFFFFu, myhi, src);
+            const int c = lo + (lane & 3);
+            const bool in = ((rows >> src) & 1u) && c <= hi;
+            V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
+            const bool tie = in && V.tie_nc(r, c);
+            V.ensure_lanes(1, tie ? r : -1, c);
+            unsigned m = __ballot_sync(0xFFFFFFFFu, tie && V.code_nc(1, r, c) == T_STOP);
+            while (m && !stop) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int cc = __shfl_sync(0xFFFFFFFFu, c, b), rr = rb + sub + (b >> 2);
+                int lg1 = cc, lg2 = rr, rg1 = cc + 1, rg2 = rr + 1;
+                walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
+                const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+                if (res > 0) ++n_add;
+                if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+            }
         }
         continue;
       }
@@ -431,17 +438,24 @@ __device__ void indel_enumerate(const View &V, BpList &L, const int *rlo, const 
       const int myr = min(rb + lane, len2), mylo = rlo[myr], myhi = rhi[myr];
       const bool mine = rb + lane <= len2 && myhi >= mylo;
       unsigned rows = __ballot_sync(0xFFFFFFFFu, mine);
-      if (rows && __all_sync(0xFFFFFFFFu, !mine || mylo == myhi)) {
-        V.ensure_lanes(3, mine ? myr + 1 : -1, mylo + 1);
-        unsigned m = __ballot_sync(0xFFFFFFFFu, mine && V.tie_nc(myr, mylo) && V.code_nc(3, myr + 1, mylo + 1) == T_STOP);
-        while (m && !stop) {
-            const int b = 31 - __clz(m); m &= ~(1u << b);
-            const int c = __shfl_sync(0xFFFFFFFFu, mylo, b);
-            int lg1 = c, lg2 = rb + b, rg1 = c + 1, rg2 = rb + b + 1;
-            walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
-            const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-            if (res > 0) ++n_add;
-            if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+      if (rows && __all_sync(0xFFFFFFFFu, !mine || myhi - mylo < 4)) {
+        for (int sub = 24; sub >= 0 && !stop; sub -= 8) {
+            if (!((rows >> sub) & 0xFFu)) continue;
+            const int src = sub + (lane >> 2);
+            const int r = rb + src, lo = __shfl_sync(0xFFFFFFFFu, mylo, src), hi = __shfl_sync(0xFFFFFFFFu, myhi, src);
+            const int c = lo + (lane & 3);
+            const bool in = ((rows >> src) & 1u) && c <= hi;
+            V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
+            unsigned m = __ballot_sync(0xFFFFFFFFu, in && V.tie_nc(r, c) && V.code_nc(3, r + 1, c + 1) == T_STOP);
+            while (m && !stop) {
+                const int b = 31 - __clz(m); m &= ~(1u << b);
+                const int cc = __shfl_sync(0xFFFFFFFFu, c, b), rr = rb + sub + (b >> 2);
+                int lg1 = cc, lg2 = rr, rg1 = cc + 1, rg2 = rr + 1;
+                walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
+                const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+                if (res > 0) ++n_add;
+                if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+            }
         }
         continue;
       }
