@@ -499,14 +499,16 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx, const B
         }
         for (auto &v : per_dev) std::sort(v.begin(), v.end());
     }
+    const char *cap_env = getenv("AGE_MEM_BUDGET_MB");               // test knob: a small budget forces several sub-batches
     for (int d = 0; d < nd; ++d) {
         size_t sc = 256, in = align_up(per_dev[d].size() * sizeof(PairTask), 256);
         for (int pi : per_dev[d]) { sc += B.pairs[pi].scratch_bytes; in += B.pairs[pi].in_bytes; }
-        if (sc <= ctx->devs[d].scratch.cap && in <= ctx->devs[d].slot[slot].in.cap) {        // fits what is already allocated
+        if (!cap_env && sc <= ctx->devs[d].scratch.cap && in <= ctx->devs[d].slot[slot].in.cap) {        // fits what is already allocated
             if (!per_dev[d].empty()) res[d].push_back(per_dev[d]);
             continue;
         }
         query_budget(d);
+        if (cap_env) budget[d] = (size_t)std::max(1L, atol(cap_env)) << 20;
         std::vector<int> cur; size_t used = 0;
         for (int pi : per_dev[d]) {
             const size_t need = B.pairs[pi].scratch_bytes + B.pairs[pi].in_bytes + 4096;

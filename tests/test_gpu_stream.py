@@ -105,3 +105,26 @@ def test_stream_two_devices():
     for g, w in zip(got, want):
         for x, y in zip(g, w):
             assert not diff_summary(x, y)
+
+
+def test_batches_larger_than_the_memory_budget(monkeypatch):
+    """AGE_MEM_BUDGET_MB=4: every batch is cut into several sub-batches that run one after the other (the path a batch
+    larger than the device memory takes), alone and with a normal batch in flight before it"""
+    bs = batches()
+    with engine.Engine([0]) as e1:
+        want = [e1.align(b) for b in bs]
+    with engine.Engine([0]) as e2:
+        first = e2.make_jobs(bs[0])
+        e2.submit(first[0], first[2])                      # in flight, one piece
+        monkeypatch.setenv("AGE_MEM_BUDGET_MB", "4")
+        second = e2.make_jobs(bs[1])
+        e2.submit(second[0], second[2])                    # several pieces: runs synchronously behind the first
+        r0 = [r.summary() for r in e2.collect(first[2])[:first[2]]]
+        r1 = [r.summary() for r in e2.collect(second[2])[:second[2]]]
+        got = [r0, r1] + [e2.align(b) for b in bs[2:]]
+        with pytest.raises(engine.AgeError):
+            e2.stage(second[0], second[2])                 # the split form needs the batch in one piece
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for x, y in zip(g, w):
+            assert not diff_summary(x, y)
