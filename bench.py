@@ -143,7 +143,7 @@ def reference_arm(args, rank: int):
         return
     from asmvar_b200 import synth
     cores = os.cpu_count() or 1
-    per_step = max(cores, 8) * 2
+    per_step = max(cores, 8) * 4          # ~10 s of CPU work per step on the box's 16 cores
     total = None
     cands = synth.indel_candidates(per_step, seed=1002)
     cu = cell_updates(cands)
@@ -329,7 +329,7 @@ def main():
         if world == 1 and not args.no_cpu and args.workload == "c2":
             try:
                 cores = os.cpu_count() or 1
-                sample = cands[: min(len(cands), max(cores, 8) * 2)]
+                sample = cands[: min(len(cands), max(cores, 8) * 8)]      # ~20 s of CPU work, a bit over a second of wall time
                 with tempfile.TemporaryDirectory() as d:
                     sec = run_reference(sample, cores, Path(d))
                 out["cpu_baseline"] = {"value": len(sample) / sec, "unit": "realignments/s", "gcups": cell_updates(sample) / sec / 1e9,
