@@ -98,15 +98,15 @@ class AgeStats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("fill_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("cell_updates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("launches", C.c_uint64), ("fill_launches", C.c_uint64), ("n_aligners", C.c_uint64),
+        ("launches", C.c_uint64), ("fill_launches", C.c_uint64), ("n_aligners", C.c_uint64), ("sweep_bytes", C.c_uint64),
     ]
 
 
 # every symbol include/age_b200.h declares; tests check the library exports all of them
 EXPORTED_SYMBOLS = [
-    "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged",
+    "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged", "age_run_staged_many",
     "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version", "age_int16_peak",
-    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment",
+    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment", "age_plan",
 ]
 
 _lib = None
@@ -141,10 +141,14 @@ def load() -> C.CDLL:
     lib.age_stage.argtypes = [vp, C.POINTER(AgeJob), C.c_size_t]
     lib.age_run_staged.restype = C.c_int
     lib.age_run_staged.argtypes = [vp]
+    lib.age_run_staged_many.restype = C.c_int
+    lib.age_run_staged_many.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.age_fetch.restype = C.c_int
     lib.age_fetch.argtypes = [vp, C.POINTER(AgeResult), C.c_size_t]
     lib.age_get_stats.restype = C.c_int
     lib.age_get_stats.argtypes = [vp, C.POINTER(AgeStats)]
+    lib.age_plan.restype = C.c_int
+    lib.age_plan.argtypes = [C.POINTER(AgeJob), C.c_size_t, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.age_format_alignment.restype = C.c_size_t
     lib.age_format_alignment.argtypes = [C.POINTER(AgeSeqView), C.POINTER(AgeSeqView), C.POINTER(AgeJob),
                                          C.POINTER(AgeResult), C.c_char_p, C.c_size_t]

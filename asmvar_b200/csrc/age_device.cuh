@@ -77,9 +77,11 @@ struct PairTask {
     uint32_t *tilemax;                   // [nstrips][nwin][32] max over (lane's 8 rows x one window) of Fmax + Rmax
     uint32_t *ckpt_f, *ckpt_r;           // [nstrips][nwin][CKW][32] lane state at the start of every window
     // pass-2 trace planes of the aligner(s) of this pair that get breakpoints (one set when `select`, else one per half)
-    char *p2set; uint32_t p2stride;
+    char *p2set; uint64_t p2stride;
     int32_t k7;                          // a TDUP / inversion aligner is present: sets also hold the reverse maxima plane
     int32_t dfmt;                        // DFMT_RAW / DFMT_OFF8
+    int32_t wide;                        // 1: one aligner (half 0) in 32-bit words with the reference's u16 storage made explicit
+                                         //    (Ar<true>, age_sweep.cuh): every scoring / length the 16-bit halves cannot hold
 };
 
 struct AlignerOut {
@@ -124,9 +126,22 @@ __host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t 
            p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4) + p2_up((nwt + 1) * 4);
 }
 
+// One chunk of a sub-batch on one device: pairs [0, n_wide) run in the 32-bit kernels, the rest in the packed 16-bit ones.
+// counters: 32 ints, zeroed by launch_chunk_sweeps (0 / 16: pair counters of the packed / wide long-sweep kernel, 1: blocks
+// used in the pool, the rest: work counters of the pass-2 kernels).
+struct BatchLaunch {
+    const PairTask *pairs; int32_t n_pairs, n_wide;
+    int32_t nw, nw_wide;                                // warps per pair in the sweep of the packed / wide pairs (sweep_warps_per_pair)
+    AlignerOut *outs; Block *pool; int32_t pool_cap;
+    int32_t *counters;
+    PairHdr *hdr; uint2 *queue; int32_t queue_cap;
+};
+
 // launchers (age_kernels.cu)
 void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st);
-void launch_sweeps(const PairTask *d_pairs, int n_pairs, int max_strips, int32_t *d_counter, cudaStream_t st);
-void launch_pass2(const Pass2Params &p, cudaStream_t st);
+int  sweep_warps_per_pair(int n_pairs, int max_strips);
+void launch_chunk_sweeps(const BatchLaunch &b, cudaStream_t st);
+void launch_chunk_pass2(const BatchLaunch &b, cudaStream_t st);
+int  launches_per_chunk(const BatchLaunch &b);          // kernels the two calls above start
 
 } // namespace age

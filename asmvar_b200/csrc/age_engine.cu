@@ -81,30 +81,50 @@ struct HostPair {
     int len1, len2, nstrips, P, nb, nsteps, nwin;
     int k7;                      // holds a TDUP / INVL / INVR aligner (pass 2 then needs the reverse maxima plane)
     int dfmt;                    // storage format of the D plane (DFMT_RAW / DFMT_OFF8, age_device.cuh)
+    int wide;                    // one aligner in 32-bit words (PairTask::wide)
     int nsets; size_t set_bytes;  // pass-2 trace plane sets (one per aligner that gets breakpoints)
     size_t in_bytes, scratch_bytes;
     double cells;
 };
 
-// What one batch in flight owns on one device.  The big scratch arena (D planes, checkpoints, trace planes) is
-// shared by both slots of a device: kernels of consecutive batches run back to back on one stream.
+constexpr int MAX_CHUNKS = 4;
+
+// A chunk: a quarter of a sub-batch with its own kernels, counters, share of the block pool and of the work list, and its
+// own region of the scratch arena.  The sweeps of consecutive chunks alternate between two streams, pass 2 runs on a third
+// (high-priority) one: pass 2 of chunk c and the end of its sweep overlap the sweep of chunk c+1.
+struct Chunk {
+    int p0 = 0, n_pairs = 0, n_wide = 0;         // pairs [p0, p0 + n_pairs) of the slot's task array, wide ones first
+    int nw = 1, nw_wide = 1;                     // warps per pair in the sweep (sweep_warps_per_pair)
+    int pool0 = 0, pool_cap = 0, queue0 = 0, queue_cap = 0;
+    size_t sc_begin = 0, sc_end = 0;             // range of the scratch arena its pairs use
+    cudaEvent_t ev_sw = nullptr, ev_p2 = nullptr;
+};
+
+// What one batch in flight owns on one device.  The big scratch arena (D planes, checkpoints, trace planes) is shared by
+// both slots of a device, chunk by chunk: a chunk starts when the chunks that used its range before are through pass 2.
 struct Slot {
     Arena in, outbuf, aux;
     PinnedBuf hin, hout;
-    cudaEvent_t ev[7] = {};      // 0/1 H2D begin/end (cp), 2 kernels begin, 3 sweeps end, 4 kernels end (st), 5/6 D2H begin/end (rb)
-    std::vector<int> pair_ids;   // the sub-batch resident in this slot
+    cudaEvent_t ev[7] = {};      // 0/1 H2D begin/end (cp), 2 kernels begin, 3 last sweep end, 4 kernels end, 5/6 D2H begin/end (rb)
+    std::vector<int> pair_ids;   // the sub-batch resident in this slot, chunk by chunk
     std::vector<PairTask> tasks;
     std::vector<size_t> sc_off;
-    int n_outs = 0, pool_cap = 0, queue_cap = 0;
-    size_t in_bytes = 0, out_bytes = 0;
+    Chunk chunk[MAX_CHUNKS];
+    int n_chunks = 0;
+    int n_outs = 0, pool_cap = 0, queue_cap = 0, launches = 0;
+    size_t in_bytes = 0, out_bytes = 0, sc_bytes = 0;
 };
+
+struct Occupant { size_t begin, end; cudaEvent_t done; };   // a range of the scratch arena and the event behind its last user
 
 struct Device {
     int id = 0;
-    cudaStream_t st = nullptr;   // kernels
+    cudaStream_t sw[2] = {nullptr, nullptr};   // sweeps (and the pack kernel) of even / odd chunks
+    cudaStream_t p2 = nullptr;   // pass 2, high priority: its short-lived CTAs take the SM slots that retiring sweep CTAs free
     cudaStream_t cp = nullptr;   // host -> device copies of the next batch
     cudaStream_t rb = nullptr;   // device -> host read-back of the previous one
     Arena scratch;
+    std::vector<Occupant> occ;
     Slot slot[2];
     std::string err;
 };
@@ -117,6 +137,7 @@ struct Batch {
     std::vector<HostPair> pairs;
     std::vector<AlignerOut> outs;                 // per aligner (global index)
     std::vector<std::vector<age_block>> blocks;   // per aligner: left | right | alt_left | alt_right
+    std::vector<int> partner_of;                  // mutual -both partner of every job (or -1)
     std::vector<char> on_dev;                     // devices that hold an asynchronous sub-batch of this batch
     age_stats stats{};
     int state = 0;                                // 0 free, 1 in flight on the devices, 2 results gathered (oversize batch, run synchronously)
@@ -149,17 +170,22 @@ template <class F> void parallel_for(int nthreads, size_t n, F f)
 
 bool single_mode(int flag) { return flag == F_INDEL || flag == F_TDUP || flag == F_INVL || flag == F_INVR; }
 
-// 16-bit range of the packed (2*score + tag) representation; see DESIGN.md "score range"
-int check_range(const age_job &j)
+// Which arithmetic a job runs in (DESIGN.md "Arithmetic and its limits").  PACKED: 2*score + tag fits a signed 16-bit half
+// for every cell, two aligners share a word.  WIDE: 32-bit words with the reference's unsigned-short storage made explicit
+// (AGEaligner.hh:86): any gap costs, any length, scores beyond 32767 and the wrap beyond 65535 included.
+enum { RANGE_PACKED = 0, RANGE_WIDE = 1, RANGE_ERR = 2 };
+int classify_range(const age_job &j, bool force_wide)
 {
     const int m = j.match, mm = j.mismatch, go = j.gap_open, ge = j.gap_extend;
-    if (m > 63 || m < -63 || mm > 63 || mm < -63) return AGE_ERR_RANGE;
-    if (go >= 0 || ge >= 0 || go < -4000 || ge < -4000) return AGE_ERR_RANGE;
+    if (m > 16383 || m < -16383 || mm > 16383 || mm < -16383) return RANGE_ERR;  // 2*S must fit the 16-bit table entries of the wide path
+    if (force_wide) return RANGE_WIDE;
+    if (m > 63 || m < -63 || mm > 63 || mm < -63) return RANGE_WIDE;
+    if (go >= 0 || ge >= 0 || go < -4000 || ge < -4000) return RANGE_WIDE;
     const long k = 2L * (ge - go) - 1;
     const long kabs = k < 0 ? -k : k;
-    const long top = 2L * std::max(m, 0) * std::min(j.len1, j.len2);
-    if (top + kabs + 2L * (-go) + 2L * (-ge) + 8 > 32767) return AGE_ERR_RANGE;
-    return AGE_OK;
+    const long top = 2L * std::max(std::max(m, mm), 0) * std::min(j.len1, j.len2);   // a DP step adds at most max(match, mismatch, 0)
+    if (top + kabs + 2L * (-go) + 2L * (-ge) + 8 > 32767) return RANGE_WIDE;
+    return RANGE_PACKED;
 }
 
 void build_plan(Batch *B, const age_job *jobs, size_t n)
@@ -169,13 +195,21 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
     B->n_jobs = n;
     B->job_status.assign(n, AGE_OK);
     B->aligners.clear(); B->pairs.clear();
+    std::vector<char> wide_job(n, 0);
+    const bool force_wide = getenv("AGE_FORCE_WIDE") != nullptr;    // test knob: everything through the 32-bit kernels
     for (size_t i = 0; i < n; ++i) {
         const age_job &j = jobs[i];
         int st = AGE_OK;
-        const bool inv = j.flag == F_INV;
+        // AGEaligner.cpp:72-77: the INVERSION bit wins over whatever else is set (main aligner INVL, auxiliary INVR)
+        const bool inv = (j.flag & F_INV) != 0;
         if (!j.seq1 || !j.seq2 || j.len1 <= 0 || j.len2 <= 0) st = AGE_NOT_ALIGNED;        // AGEaligner.cpp:68
-        else if (!inv && !single_mode(j.flag)) st = AGE_NOT_ALIGNED;                         // AGEaligner.cpp:69
-        else st = check_range(j);
+        else if (!(j.flag & (F_INDEL | F_TDUP | F_INV | F_INVR | F_INVL))) st = AGE_NOT_ALIGNED;   // AGEaligner.cpp:69
+        else if (!inv && !single_mode(j.flag)) st = AGE_ERR_ARG;        // several mode bits without INVERSION: see age_b200.h
+        else {
+            const int rg = classify_range(j, force_wide);
+            if (rg == RANGE_ERR) st = AGE_ERR_RANGE;
+            wide_job[i] = rg == RANGE_WIDE;
+        }
         B->job_status[i] = st;
         if (st != AGE_OK) continue;
         if (inv) {
@@ -203,8 +237,9 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
         hp.k7 = (B->aligners[a0].flag != F_INDEL) || (a1 >= 0 && B->aligners[a1].flag != F_INDEL);
         const size_t slots = (size_t)hp.nstrips * hp.nsteps;                 // (strip, step) slots of the diagonal-major planes
         // D as 8-bit row offsets when a DP step can add at most 15 (age_device.cuh)
-        hp.dfmt = (!force_raw && std::max((int)j.match, (int)j.mismatch) <= 15) ? DFMT_OFF8 : DFMT_RAW;
-        hp.in_bytes = 2 * (align_up((size_t)j.len1, 16) + align_up((size_t)j.len2, 16));   // raw sequences of both halves
+        hp.wide = wide_job[B->aligners[a0].job];
+        hp.dfmt = (!hp.wide && !force_raw && std::max((int)j.match, (int)j.mismatch) <= 15) ? DFMT_OFF8 : DFMT_RAW;
+        hp.in_bytes = (hp.wide ? 1 : 2) * (align_up((size_t)j.len1, 16) + align_up((size_t)j.len2, 16));   // raw sequences of the halves
         hp.scratch_bytes = align_up(slots * d_planes(hp.dfmt) * 32 * 16, 256) +
                            2 * align_up((size_t)std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16, 256) +
                            2 * align_up(((size_t)hp.P + 2) * 4, 256) + align_up(((size_t)W * hp.nb + 4) * 4, 256) +
@@ -220,14 +255,17 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
     std::vector<int> first_of(n, -1);
     for (size_t a = 0; a < B->aligners.size(); ++a) if (B->aligners[a].role == 0) first_of[B->aligners[a].job] = (int)a;
     std::vector<char> used(B->aligners.size(), 0);
+    // wide aligners run one per warp: the selection between partners / INVL and INVR is made on the host (assemble)
+    for (size_t a = 0; a < B->aligners.size(); ++a)
+        if (wide_job[B->aligners[a].job]) { add_pair((int)a, -1, 0); used[a] = 1; }
     for (size_t a = 0; a < B->aligners.size(); ++a) {
         const Aligner &al = B->aligners[a];
         if (used[a] || al.role != 0) continue;
         const age_job &j = jobs[al.job];
-        if (j.flag == F_INV) { add_pair((int)a, (int)a + 1, 1); used[a] = used[a + 1] = 1; continue; }
+        if (j.flag & F_INV) { add_pair((int)a, (int)a + 1, 1); used[a] = used[a + 1] = 1; continue; }
         const int pj = j.partner;
-        if (pj > al.job && (size_t)pj < n && jobs[pj].partner == al.job && B->job_status[pj] == AGE_OK &&
-            jobs[pj].flag != F_INV && same((int)a, first_of[pj])) {
+        if (pj > al.job && (size_t)pj < n && jobs[pj].partner == al.job && B->job_status[pj] == AGE_OK && !wide_job[pj] &&
+            !(jobs[pj].flag & F_INV) && same((int)a, first_of[pj])) {
             add_pair((int)a, first_of[pj], 1); used[a] = used[first_of[pj]] = 1;
         }
     }
@@ -237,6 +275,11 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
     for (size_t i = 0; i < order.size();) {
         if (i + 1 < order.size() && same(order[i + 1], order[i])) { add_pair(order[i], order[i + 1], 0); i += 2; }
         else { add_pair(order[i], -1, 0); i += 1; }
+    }
+    B->partner_of.assign(n, -1);
+    for (size_t i = 0; i < n; ++i) {
+        const int pj = jobs[i].partner;
+        if (pj >= 0 && (size_t)pj < n && (size_t)pj != i && jobs[pj].partner == (int)i) B->partner_of[i] = pj;
     }
     B->outs.assign(B->aligners.size(), AlignerOut{});
     B->blocks.assign(B->aligners.size(), {});
@@ -280,7 +323,11 @@ void pack_pair(const Batch *B, const age_job *jobs, int pi, char *h, char *d, Pa
     // identical scoring
     T.c0x = pack2(c0x[0], c0x[1]); T.kabs = (uint32_t)kabs[0]; T.flip = pack2(flip[0], flip[1]); T.gborder = pack2(gb[0], gb[1]);
     T.m2 = pack2(2 * sc[0][0], 2 * sc[1][0]); T.mm2 = pack2(2 * sc[0][1], 2 * sc[1][1]);
-    T.dfmt = hp.dfmt;
+    if (hp.wide) {                   // one aligner, plain 32-bit words
+        T.c0x = (uint32_t)c0x[0]; T.flip = (uint32_t)flip[0]; T.gborder = (uint32_t)gb[0];
+        T.m2 = (uint32_t)(2 * sc[0][0]); T.mm2 = (uint32_t)(2 * sc[0][1]);
+    }
+    T.dfmt = hp.dfmt; T.wide = hp.wide;
 }
 
 void assign_scratch(const HostPair &hp, char *s, PairTask &T)
@@ -302,23 +349,61 @@ void assign_scratch(const HostPair &hp, char *s, PairTask &T)
     T.xblk_r = (uint4 *)s; s += xs;
     T.ytab = (uint2 *)s; s += align_up((size_t)hp.P * 8, 256);
     T.ycode = (uint8_t *)s; s += align_up((size_t)hp.P, 256);
-    T.p2set = s; T.p2stride = (uint32_t)hp.set_bytes; T.k7 = hp.k7;
+    T.p2set = s; T.p2stride = hp.set_bytes; T.k7 = hp.k7;
 }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { dev.err = std::string(#call) + ": " + cudaGetErrorString(e_); return false; } } while (0)
 
 size_t out_bytes_of(int n_outs, int pool_cap)
 {
-    return align_up((size_t)n_outs * sizeof(AlignerOut), 256) + align_up((size_t)pool_cap * sizeof(Block), 256) + 256;
+    return align_up((size_t)n_outs * sizeof(AlignerOut), 256) + align_up((size_t)pool_cap * sizeof(Block), 256) + 1024;
 }
 
-// stage one sub-batch (pair ids) in a slot of a device: pack, copy inputs (copy stream), lay out scratch
+bool sync_device(Device &dev)
+{
+    CK(cudaSetDevice(dev.id));
+    for (cudaStream_t st : {dev.sw[0], dev.sw[1], dev.p2, dev.cp, dev.rb}) if (st) CK(cudaStreamSynchronize(st));
+    dev.occ.clear();
+    return true;
+}
+
+// Deal the (wide first, longest first) ordered pairs of a sub-batch to its chunks.  Small sub-batches and those whose pairs
+// are shared by several warps (long alignments) stay in one piece.
+int plan_chunks(const Batch &B, const std::vector<int> &sorted, std::vector<int> &chunk_major, int *count, int *nw, int *nw_wide)
+{
+    int n_wide = 0, ms = 1, ms_wide = 1;
+    for (int pi : sorted) {
+        const HostPair &hp = B.pairs[pi];
+        n_wide += hp.wide;
+        (hp.wide ? ms_wide : ms) = std::max(hp.wide ? ms_wide : ms, hp.nstrips);
+    }
+    const int n_packed = (int)sorted.size() - n_wide;
+    *nw = sweep_warps_per_pair(n_packed, ms);
+    *nw_wide = sweep_warps_per_pair(n_wide, ms_wide);
+    int C = 1;
+    if (*nw == 1 && (n_wide == 0 || *nw_wide == 1)) C = std::max(1, std::min(MAX_CHUNKS, (int)sorted.size() / 1024));
+    if (const char *e = getenv("AGE_CHUNKS")) C = std::max(1, std::min(MAX_CHUNKS, atoi(e)));   // knob: 1 = one chunk, nothing overlaps
+    C = std::min<int>(C, std::max<size_t>(1, sorted.size()));
+    chunk_major.clear();
+    for (int c = 0; c < C; ++c) {
+        count[c] = 0;
+        for (size_t i = c; i < sorted.size(); i += C) { chunk_major.push_back(sorted[i]); ++count[c]; }
+    }
+    return C;
+}
+
+// stage one sub-batch (pair ids) in a slot of a device: plan its chunks, pack, copy inputs (copy stream), lay out scratch
 bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, Slot &sl, const std::vector<int> &pair_ids_in)
 {
     CK(cudaSetDevice(dev.id));
-    // longest pairs first: the persistent sweep kernel hands out pairs in this order, so its tail is made of short ones
-    sl.pair_ids = pair_ids_in;
-    std::stable_sort(sl.pair_ids.begin(), sl.pair_ids.end(), [&](int a, int b) { return B.pairs[a].cells * B.pairs[a].nstrips > B.pairs[b].cells * B.pairs[b].nstrips; });
+    // wide pairs first (they run in their own kernels), then the longest pairs first: the sweep grid is dispatched in this
+    // order, so its tail is made of short pairs
+    std::vector<int> sorted = pair_ids_in;
+    std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) {
+        if (B.pairs[a].wide != B.pairs[b].wide) return B.pairs[a].wide > B.pairs[b].wide;
+        return B.pairs[a].cells * B.pairs[a].nstrips > B.pairs[b].cells * B.pairs[b].nstrips; });
+    int count[MAX_CHUNKS], nw = 1, nw_wide = 1;
+    sl.n_chunks = plan_chunks(B, sorted, sl.pair_ids, count, &nw, &nw_wide);
     const std::vector<int> &pair_ids = sl.pair_ids;
     const size_t np = pair_ids.size();
     sl.tasks.assign(np, PairTask{});
@@ -326,26 +411,34 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     sl.sc_off.assign(np + 1, 0);
     int n_outs = 0;
     size_t nwt_total = 0;
-    for (size_t i = 0; i < np; ++i) {
-        HostPair &hp = B.pairs[pair_ids[i]];
-        in_off[i + 1] = in_off[i] + hp.in_bytes;
-        sl.sc_off[i + 1] = sl.sc_off[i] + hp.scratch_bytes;
-        nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets;
-        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.aligners[hp.a[k]].out = n_outs++;
+    for (int c = 0, p0 = 0; c < sl.n_chunks; p0 += count[c], ++c) {
+        Chunk &ch = sl.chunk[c];
+        ch.p0 = p0; ch.n_pairs = count[c]; ch.n_wide = 0; ch.nw = nw; ch.nw_wide = nw_wide;
+        ch.sc_begin = sl.sc_off[p0];
+        for (int i = p0; i < p0 + count[c]; ++i) {
+            HostPair &hp = B.pairs[pair_ids[i]];
+            ch.n_wide += hp.wide;
+            in_off[i + 1] = in_off[i] + hp.in_bytes;
+            sl.sc_off[i + 1] = sl.sc_off[i] + hp.scratch_bytes;
+            nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets;
+            for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.aligners[hp.a[k]].out = n_outs++;
+        }
+        ch.sc_end = sl.sc_off[p0 + count[c]];
     }
     sl.n_outs = n_outs;
-    sl.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
-    if (const char *e = getenv("AGE_QUEUE_CAP")) sl.queue_cap = std::max(1, atoi(e));   // test knob: a short work list forces on-demand re-sweeps
+    sl.sc_bytes = sl.sc_off[np];
+    sl.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64 * sl.n_chunks, (size_t)1 << 24);
+    if (const char *e = getenv("AGE_QUEUE_CAP")) sl.queue_cap = std::max(1, atoi(e)) * sl.n_chunks;   // test knob: a short work list forces on-demand re-sweeps
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
     sl.in_bytes = task_bytes + in_off[np];
     if (!sl.hin.ensure(sl.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
     if (!sl.in.ensure(sl.in_bytes)) { dev.err = "device allocation failed (inputs)"; return false; }
-    if (sl.sc_off[np] + 256 > dev.scratch.cap) {
-        CK(cudaStreamSynchronize(dev.st));               // the batch in flight still works in the arena that is about to move
-        if (!dev.scratch.ensure(sl.sc_off[np] + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
+    if (sl.sc_bytes + 256 > dev.scratch.cap) {
+        if (!sync_device(dev)) return false;             // the batch in flight still works in the arena that is about to move
+        if (!dev.scratch.ensure(sl.sc_bytes + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
     }
-    sl.pool_cap = n_outs * 96 + 4096;
-    if (const char *e = getenv("AGE_POOL_CAP")) sl.pool_cap = std::max(1, atoi(e));     // test knob: a small block pool forces the overflow re-run
+    sl.pool_cap = n_outs * 96 + 4096 * sl.n_chunks;
+    if (const char *e = getenv("AGE_POOL_CAP")) sl.pool_cap = std::max(1, atoi(e)) * sl.n_chunks;     // test knob: a small block pool forces the overflow re-run
     sl.out_bytes = out_bytes_of(n_outs, sl.pool_cap);
     if (!sl.outbuf.ensure(sl.out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
     if (!sl.hout.ensure(sl.out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
@@ -358,8 +451,6 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     CK(cudaEventRecord(sl.ev[0], dev.cp));
     CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.in_bytes, cudaMemcpyHostToDevice, dev.cp));
     CK(cudaEventRecord(sl.ev[1], dev.cp));
-    CK(cudaStreamWaitEvent(dev.st, sl.ev[1], 0));
-    launch_pack((const PairTask *)sl.in.ptr, (int)np, dev.st);
     return true;
 }
 
@@ -369,34 +460,55 @@ OutLayout out_layout(const Slot &sl, char *base)
     OutLayout L;
     L.outs = (AlignerOut *)base;
     L.pool = (Block *)(base + align_up((size_t)sl.n_outs * sizeof(AlignerOut), 256));
-    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)sl.pool_cap * sizeof(Block), 256));
+    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)sl.pool_cap * sizeof(Block), 256));   // 32 ints per chunk
     return L;
 }
 
-Pass2Params pass2_params(Slot &sl, const OutLayout &L)
-{
-    Pass2Params p{};
-    p.pairs = (const PairTask *)sl.in.ptr; p.n_pairs = (int)sl.tasks.size(); p.outs = L.outs;
-    p.hdr = (PairHdr *)sl.aux.ptr;
-    p.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)); p.queue_cap = sl.queue_cap; p.queue_n = L.counters + 12;
-    p.pool = L.pool; p.pool_cap = sl.pool_cap; p.pool_used = L.counters + 2; p.next = L.counters + 4;   // next: 8 ints
-    return p;
-}
-
-// all kernels of the slot's sub-batch on the compute stream
+// All kernels of the slot's sub-batch.  Per chunk: [wait for the earlier users of its scratch range] pack + sweeps on the
+// sweep stream of its parity, then pass 2 on the high-priority stream.
 bool run_on_device(Device &dev, Slot &sl)
 {
     CK(cudaSetDevice(dev.id));
-    const int np = (int)sl.tasks.size();
     OutLayout L = out_layout(sl, sl.outbuf.ptr);
-    CK(cudaMemsetAsync(L.counters, 0, 64, dev.st));
-    CK(cudaEventRecord(sl.ev[2], dev.st));
-    int max_strips = 1;
-    for (const PairTask &t : sl.tasks) max_strips = std::max(max_strips, (int)t.nstrips);
-    launch_sweeps((const PairTask *)sl.in.ptr, np, max_strips, L.counters + 0, dev.st);
-    CK(cudaEventRecord(sl.ev[3], dev.st));
-    launch_pass2(pass2_params(sl, L), dev.st);
-    CK(cudaEventRecord(sl.ev[4], dev.st));
+    const int C = sl.n_chunks;
+    // shares of the block pool and of the work list
+    for (int c = 0; c < C; ++c) {
+        Chunk &ch = sl.chunk[c];
+        ch.pool0 = (int)((long long)sl.pool_cap * c / C); ch.pool_cap = (int)((long long)sl.pool_cap * (c + 1) / C) - ch.pool0;
+        ch.queue0 = (int)((long long)sl.queue_cap * c / C); ch.queue_cap = (int)((long long)sl.queue_cap * (c + 1) / C) - ch.queue0;
+    }
+    sl.launches = 0;
+    for (int c = 0; c < C; ++c) {
+        Chunk &ch = sl.chunk[c];
+        cudaStream_t st = dev.sw[c & 1];
+        CK(cudaStreamWaitEvent(st, sl.ev[1], 0));                    // inputs on the device
+        if (c == 0) CK(cudaEventRecord(sl.ev[2], st));
+        std::vector<Occupant> keep;                                  // earlier users of this chunk's scratch range
+        for (const Occupant &o : dev.occ) {
+            const bool overlap = o.begin < ch.sc_end && ch.sc_begin < o.end;
+            if (overlap) CK(cudaStreamWaitEvent(st, o.done, 0));
+            if (overlap && o.begin >= ch.sc_begin && o.end <= ch.sc_end) continue;          // superseded by this chunk
+            if (dev.occ.size() > 16 && cudaEventQuery(o.done) == cudaSuccess) continue;     // long finished
+            keep.push_back(o);
+        }
+        cudaGetLastError();                                          // (cudaErrorNotReady of the queries)
+        dev.occ.swap(keep);
+        BatchLaunch b{};
+        b.pairs = (const PairTask *)sl.in.ptr + ch.p0; b.n_pairs = ch.n_pairs; b.n_wide = ch.n_wide; b.nw = ch.nw; b.nw_wide = ch.nw_wide;
+        b.outs = L.outs; b.pool = L.pool + ch.pool0; b.pool_cap = ch.pool_cap; b.counters = L.counters + 32 * c;
+        b.hdr = (PairHdr *)sl.aux.ptr + ch.p0;
+        b.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)) + ch.queue0; b.queue_cap = ch.queue_cap;
+        launch_pack(b.pairs, b.n_pairs, st);
+        launch_chunk_sweeps(b, st);
+        CK(cudaEventRecord(ch.ev_sw, st));
+        if (c == C - 1) CK(cudaEventRecord(sl.ev[3], st));
+        CK(cudaStreamWaitEvent(dev.p2, ch.ev_sw, 0));
+        launch_chunk_pass2(b, dev.p2);
+        CK(cudaEventRecord(ch.ev_p2, dev.p2));
+        dev.occ.push_back(Occupant{ch.sc_begin, ch.sc_end, ch.ev_p2});
+        sl.launches += 1 + launches_per_chunk(b);
+    }
+    CK(cudaEventRecord(sl.ev[4], dev.p2));                           // the pass-2 stream runs the chunks in order: this is the end of the batch
     CK(cudaGetLastError());
     return true;
 }
@@ -416,16 +528,15 @@ bool enqueue_fetch(Device &dev, Slot &sl)
 // (or moved) the scratch arena in the meantime, so the sweeps are repeated as well; the packed inputs are still resident.
 bool rerun_with_pool(Batch &B, Device &dev, Slot &sl, int pool_cap)
 {
-    CK(cudaStreamSynchronize(dev.st));
-    CK(cudaStreamSynchronize(dev.rb));
+    if (!sync_device(dev)) return false;
     sl.pool_cap = pool_cap;
     sl.out_bytes = out_bytes_of(sl.n_outs, sl.pool_cap);
     if (!sl.outbuf.ensure(sl.out_bytes) || !sl.hout.ensure(sl.out_bytes)) { dev.err = "allocation failed (block pool)"; return false; }
-    if (sl.sc_off.back() + 256 > dev.scratch.cap && !dev.scratch.ensure(sl.sc_off.back() + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
+    if (sl.sc_bytes + 256 > dev.scratch.cap && !dev.scratch.ensure(sl.sc_bytes + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
     for (size_t i = 0; i < sl.tasks.size(); ++i) assign_scratch(B.pairs[sl.pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
     memcpy(sl.hin.ptr, sl.tasks.data(), sl.tasks.size() * sizeof(PairTask));
-    CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, dev.st));
-    launch_pack((const PairTask *)sl.in.ptr, (int)sl.tasks.size(), dev.st);
+    CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, dev.cp));
+    CK(cudaEventRecord(sl.ev[1], dev.cp));
     return run_on_device(dev, sl) && enqueue_fetch(dev, sl);
 }
 
@@ -436,25 +547,31 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaEventSynchronize(sl.ev[6]));
         OutLayout H = out_layout(sl, sl.hout.ptr);
-        if (H.counters[2] > sl.pool_cap) {
-            if (!rerun_with_pool(B, dev, sl, H.counters[2] + 4096)) return false;
-            st.launches += 7; st.fill_launches += 1;      // pack, sweep, select, 2 pre-sweeps, enumerate, blocks
+        long long want = 0;                               // a chunk ran out of its share of the block pool: run again with a larger pool
+        for (int c = 0; c < sl.n_chunks; ++c)
+            if (H.counters[32 * c + 1] > sl.chunk[c].pool_cap) want = std::max(want, (long long)H.counters[32 * c + 1] * sl.n_chunks);
+        if (want) {
+            if (!rerun_with_pool(B, dev, sl, (int)std::min<long long>(want + 4096 * sl.n_chunks, 1LL << 30))) return false;
+            st.launches += sl.launches; st.fill_launches += sl.n_chunks;
             continue;
         }
-        for (size_t i = 0; i < sl.pair_ids.size(); ++i) {
-            const HostPair &hp = B.pairs[sl.pair_ids[i]];
-            for (int k = 0; k < 2; ++k) {
-                if (hp.a[k] < 0) continue;
-                const Aligner &al = B.aligners[hp.a[k]];
-                const AlignerOut &o = H.outs[al.out];
-                memcpy(&B.outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
-                std::vector<age_block> &b = B.blocks[hp.a[k]];
-                b.clear();
-                for (int q = 0; q < 4; ++q)
-                    for (int x = 0; x < o.n_blk[q]; ++x) {
-                        const Block &s = H.pool[o.blk_off[q] + x];
-                        b.push_back(age_block{s.start1, s.start2, s.length});
-                    }
+        for (int c = 0; c < sl.n_chunks; ++c) {
+            const Chunk &ch = sl.chunk[c];
+            for (int i = ch.p0; i < ch.p0 + ch.n_pairs; ++i) {
+                const HostPair &hp = B.pairs[sl.pair_ids[i]];
+                for (int k = 0; k < 2; ++k) {
+                    if (hp.a[k] < 0) continue;
+                    const Aligner &al = B.aligners[hp.a[k]];
+                    const AlignerOut &o = H.outs[al.out];
+                    memcpy(&B.outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
+                    std::vector<age_block> &b = B.blocks[hp.a[k]];
+                    b.clear();
+                    for (int q = 0; q < 4; ++q)
+                        for (int x = 0; x < o.n_blk[q]; ++x) {
+                            const Block &s = H.pool[ch.pool0 + o.blk_off[q] + x];
+                            b.push_back(age_block{s.start1, s.start2, s.length});
+                        }
+                }
             }
         }
         float ms = 0;
@@ -463,11 +580,30 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) st.fill_ms += ms;
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) st.kernel_ms += ms;
         if (cudaEventElapsedTime(&ms, sl.ev[5], sl.ev[6]) == cudaSuccess) st.d2h_ms += ms;
-        st.launches += 7; st.fill_launches += 1;          // pack, sweep, select, 2 pre-sweeps, enumerate, blocks
+        st.launches += sl.launches; st.fill_launches += sl.n_chunks;
         return true;
     }
     dev.err = "block pool overflow";
     return false;
+}
+
+// Longest-processing-time-first deal of the pairs of a plan across nd devices (cost = DP area; a wide pair costs about
+// as much as a packed one per area: one aligner at ~2.2x the instructions instead of two).  Each device keeps plan order.
+std::vector<std::vector<int>> deal_pairs(const Batch &B, int nd)
+{
+    std::vector<int> order(B.pairs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::vector<std::vector<int>> per_dev(nd);
+    if (nd == 1) { per_dev[0] = order; return per_dev; }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return B.pairs[a].cells > B.pairs[b].cells; });
+    std::vector<double> load(nd, 0.0);
+    for (int pi : order) {
+        int best = 0;
+        for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
+        per_dev[best].push_back(pi); load[best] += B.pairs[pi].cells;
+    }
+    for (auto &v : per_dev) std::sort(v.begin(), v.end());
+    return per_dev;
 }
 
 // split the pairs of the plan into per-device sub-batches that fit the scratch budget
@@ -484,21 +620,7 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx, const B
         fr += dev.scratch.cap + dev.slot[slot].in.cap + dev.slot[slot].outbuf.cap + dev.slot[slot].aux.cap;
         budget[d] = (size_t)(0.85 * (double)fr);
     };
-    // longest-processing-time-first deal across devices
-    std::vector<int> order(B.pairs.size());
-    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::vector<std::vector<int>> per_dev(nd);
-    if (nd == 1) per_dev[0] = order;
-    else {
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return B.pairs[a].cells > B.pairs[b].cells; });
-        std::vector<double> load(nd, 0.0);
-        for (int pi : order) {
-            int best = 0;
-            for (int d = 1; d < nd; ++d) if (load[d] < load[best]) best = d;
-            per_dev[best].push_back(pi); load[best] += B.pairs[pi].cells;
-        }
-        for (auto &v : per_dev) std::sort(v.begin(), v.end());
-    }
+    std::vector<std::vector<int>> per_dev = deal_pairs(B, nd);
     const char *cap_env = getenv("AGE_MEM_BUDGET_MB");               // test knob: a small budget forces several sub-batches
     for (int d = 0; d < nd; ++d) {
         size_t sc = 256, in = align_up(per_dev[d].size() * sizeof(PairTask), 256);
@@ -523,9 +645,16 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx, const B
 void account(Batch &B)
 {
     B.stats.n_aligners = B.aligners.size();
-    B.stats.cell_updates = 0;
-    for (const HostPair &hp : B.pairs)
+    B.stats.cell_updates = 0; B.stats.sweep_bytes = 0;
+    for (const HostPair &hp : B.pairs) {
         for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.stats.cell_updates += (uint64_t)(2.0 * hp.cells);
+        // D written by the forward and read by the reverse sweep (lanes whose rows lie beyond the contig skip it), a
+        // checkpoint per window and direction, boundary rows written and read per direction, one tile maximum per lane and window
+        const double live = std::min(1.0, (hp.len2 / 8 + 1) / (32.0 * hp.nstrips));
+        B.stats.sweep_bytes += (uint64_t)(2.0 * live * hp.nstrips * hp.nsteps * d_planes(hp.dfmt) * 512.0) +
+                               2ull * hp.nstrips * hp.nwin * CKW * 128 + 4ull * std::max(hp.nstrips - 1, 0) * 3 * (hp.nb + 1) * 16 +
+                               (uint64_t)hp.nstrips * hp.nwin * 128;
+    }
 }
 
 void assemble(const Batch &B, age_result *out, size_t n)
@@ -562,6 +691,19 @@ void assemble(const Batch &B, age_result *out, size_t n)
         r.n_left = o.n_blk[0]; r.n_right = o.n_blk[1]; r.n_alt_left = o.n_blk[2]; r.n_alt_right = o.n_blk[3];
         const age_block *b = B.blocks[pick].data();
         r.left = b; r.right = b + r.n_left; r.alt_left = r.right + r.n_right; r.alt_right = r.alt_left + r.n_alt_left;
+    }
+    // Mutual -both partners that did not share a warp (wide jobs) both come back complete: keep the details of the one
+    // age_align prints only (the lower index unless the other scores strictly higher, age_align.cpp:273), as the
+    // on-device selection does.
+    for (size_t i = 0; i < n; ++i) {
+        const int pj = B.partner_of[i];
+        if (pj <= (int)i) continue;
+        age_result &a = out[i], &b = out[pj];
+        if (a.status != AGE_OK || b.status != AGE_OK || !a.detail || !b.detail) continue;
+        age_result &lose = b.score > a.score ? a : b;
+        lose.detail = 0; lose.n_bp = 0; lose.alt_index = -1; lose.used_aux = 0;
+        lose.n_left = lose.n_right = lose.n_alt_left = lose.n_alt_right = 0;
+        lose.left = lose.right = lose.alt_left = lose.alt_right = nullptr;
     }
 }
 
@@ -625,7 +767,11 @@ int submit(age_ctx *ctx, const age_job *jobs, size_t n)
         merge_stats(B.stats, dstat);
         B.state = 2;
     }
-    if (!ok) { B.state = 0; return AGE_ERR_CUDA; }
+    if (!ok) {                    // other devices may already have copies or kernels of this batch in flight: drain them before the slot is reused
+        for (Device &dev : ctx->devs) sync_device(dev);
+        B.state = 0;
+        return AGE_ERR_CUDA;
+    }
     ctx->head ^= 1; ctx->in_flight += 1;
     if (g_hprof) fprintf(stderr, "[host prof] submit: plan %.2f ms, sub-batching + stage + launch %.2f ms\n", t1 - t0, wall_ms() - t1);
     return 0;
@@ -647,7 +793,7 @@ int collect(age_ctx *ctx, age_result *out, size_t n)
         merge_stats(B.stats, dstat);
     }
     B.state = 0; ctx->in_flight -= 1;
-    if (!ok) return AGE_ERR_CUDA;
+    if (!ok) { for (Device &dev : ctx->devs) sync_device(dev); return AGE_ERR_CUDA; }
     const double t1 = wall_ms();
     account(B);
     assemble(B, out, n);
@@ -680,11 +826,20 @@ extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
         ctx->devs.push_back(d);
     }
     for (Device &d : ctx->devs) {
-        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&d.rb, cudaStreamNonBlocking) == cudaSuccess;
-        for (Slot &sl : d.slot)
+        bool ok = cudaSetDevice(d.id) == cudaSuccess;
+        int prio_lo = 0, prio_hi = 0;
+        if (ok) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        ok = ok && cudaStreamCreateWithPriority(&d.sw[0], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&d.sw[1], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&d.p2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&d.rb, cudaStreamNonBlocking) == cudaSuccess;
+        for (Slot &sl : d.slot) {
             for (int e = 0; ok && e < 7; ++e) ok = cudaEventCreate(&sl.ev[e]) == cudaSuccess;
+            for (Chunk &ch : sl.chunk)
+                ok = ok && cudaEventCreateWithFlags(&ch.ev_sw, cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ch.ev_p2, cudaEventDisableTiming) == cudaSuccess;
+        }
         if (!ok) { g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); age_destroy(ctx); return nullptr; }
     }
     if (g_hprof) fprintf(stderr, "[host prof] age_create %.1f ms\n", wall_ms() - t_create);
@@ -696,17 +851,14 @@ extern "C" void age_destroy(age_ctx *ctx)
     if (!ctx) return;
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
-        if (d.st) cudaStreamSynchronize(d.st);
-        if (d.cp) cudaStreamSynchronize(d.cp);
-        if (d.rb) cudaStreamSynchronize(d.rb);
+        for (cudaStream_t st : {d.sw[0], d.sw[1], d.p2, d.cp, d.rb}) if (st) cudaStreamSynchronize(st);
         d.scratch.release();
         for (Slot &sl : d.slot) {
             sl.in.release(); sl.outbuf.release(); sl.aux.release(); sl.hin.release(); sl.hout.release();
             for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
+            for (Chunk &ch : sl.chunk) { if (ch.ev_sw) cudaEventDestroy(ch.ev_sw); if (ch.ev_p2) cudaEventDestroy(ch.ev_p2); }
         }
-        if (d.st) cudaStreamDestroy(d.st);
-        if (d.cp) cudaStreamDestroy(d.cp);
-        if (d.rb) cudaStreamDestroy(d.rb);
+        for (cudaStream_t st : {d.sw[0], d.sw[1], d.p2, d.cp, d.rb}) if (st) cudaStreamDestroy(st);
     }
     delete ctx;
 }
@@ -761,7 +913,7 @@ extern "C" int age_stage(age_ctx *ctx, const age_job *jobs, size_t n)
         B.on_dev[d] = 1;
         B.stats.h2d_bytes += sl.in_bytes;
     }
-    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.cp); cudaStreamSynchronize(dev.st); }
+    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.cp); }
     ctx->stats = B.stats;
     ctx->staged = true;
     return 0;
@@ -782,13 +934,47 @@ extern "C" int age_run_staged(age_ctx *ctx)
         if (!B.on_dev[d]) continue;
         Slot &sl = dev.slot[0];
         cudaSetDevice(dev.id);
-        if (cudaStreamSynchronize(dev.st) != cudaSuccess) { ctx->err = cudaGetErrorString(cudaGetLastError()); return AGE_ERR_CUDA; }
+        if (cudaEventSynchronize(sl.ev[4]) != cudaSuccess) { ctx->err = cudaGetErrorString(cudaGetLastError()); return AGE_ERR_CUDA; }
         float ms = 0;
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) ctx->stats.kernel_ms = std::max(ctx->stats.kernel_ms, (double)ms);
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) ctx->stats.fill_ms = std::max(ctx->stats.fill_ms, (double)ms);
     }
-    ctx->stats.launches += 6; ctx->stats.fill_launches += 1;       // sweep, select, 2 pre-sweeps, enumerate, blocks (packed at stage time)
+    for (size_t d = 0; d < ctx->devs.size(); ++d) if (B.on_dev[d]) ctx->stats.launches += ctx->devs[d].slot[0].launches;   // packed at stage time
+    ctx->stats.fill_launches += 1;
     return 0;
+}
+
+extern "C" int age_run_staged_many(age_ctx *ctx, int reps, double *total_ms)
+{
+    if (!ctx || !ctx->staged || reps < 1) return AGE_ERR_ARG;
+    Batch &B = ctx->batch[0];
+    const size_t nd = ctx->devs.size();
+    std::vector<cudaEvent_t> e0(nd, nullptr);
+    for (size_t d = 0; d < nd; ++d) {
+        Device &dev = ctx->devs[d];
+        if (!B.on_dev[d]) continue;
+        cudaSetDevice(dev.id);
+        cudaEventCreate(&e0[d]);
+        cudaEventRecord(e0[d], dev.sw[0]);
+    }
+    int rc = 0;
+    for (int r = 0; r < reps && rc == 0; ++r)            // repeats are queued back to back: chunk c of repeat r+1 follows pass 2 of chunk c of repeat r
+        for (size_t d = 0; d < nd; ++d)
+            if (B.on_dev[d] && !run_on_device(ctx->devs[d], ctx->devs[d].slot[0])) { ctx->err = ctx->devs[d].err; rc = AGE_ERR_CUDA; break; }
+    double worst = 0;
+    for (size_t d = 0; d < nd; ++d) {
+        Device &dev = ctx->devs[d];
+        if (!B.on_dev[d]) continue;
+        cudaSetDevice(dev.id);
+        float ms = 0;
+        if (cudaEventSynchronize(dev.slot[0].ev[4]) != cudaSuccess) { ctx->err = cudaGetErrorString(cudaGetLastError()); rc = AGE_ERR_CUDA; }
+        else if (cudaEventElapsedTime(&ms, e0[d], dev.slot[0].ev[4]) == cudaSuccess) worst = std::max(worst, (double)ms);
+        cudaEventDestroy(e0[d]);
+        if (rc == 0) ctx->stats.launches += (uint64_t)reps * dev.slot[0].launches;
+    }
+    if (total_ms) *total_ms = worst;
+    ctx->stats.kernel_ms = worst / reps;
+    return rc;
 }
 
 extern "C" int age_fetch(age_ctx *ctx, age_result *out, size_t n)
@@ -803,8 +989,26 @@ extern "C" int age_fetch(age_ctx *ctx, age_result *out, size_t n)
     }
     ctx->stats.d2h_bytes = scratch_stats.d2h_bytes;
     account(B);
-    ctx->stats.n_aligners = B.stats.n_aligners; ctx->stats.cell_updates = B.stats.cell_updates;
+    ctx->stats.n_aligners = B.stats.n_aligners; ctx->stats.cell_updates = B.stats.cell_updates; ctx->stats.sweep_bytes = B.stats.sweep_bytes;
     assemble(B, out, n);
+    return 0;
+}
+
+extern "C" int age_plan(const age_job *jobs, size_t n, int n_dev, int32_t *device_of_job, int32_t *arith_of_job)
+{
+    if ((!jobs && n) || n_dev < 1 || !device_of_job) return AGE_ERR_ARG;
+    Batch B;
+    build_plan(&B, jobs, n);
+    for (size_t i = 0; i < n; ++i) { device_of_job[i] = -1; if (arith_of_job) arith_of_job[i] = B.job_status[i] == AGE_OK ? 16 : B.job_status[i]; }
+    const auto per_dev = deal_pairs(B, n_dev);
+    for (int d = 0; d < n_dev; ++d)
+        for (int pi : per_dev[d])
+            for (int k = 0; k < 2; ++k) {
+                if (B.pairs[pi].a[k] < 0) continue;
+                const Aligner &al = B.aligners[B.pairs[pi].a[k]];
+                if (al.role == 0) device_of_job[al.job] = d;
+                if (arith_of_job && B.pairs[pi].wide) arith_of_job[al.job] = 32;
+            }
     return 0;
 }
 

@@ -29,6 +29,39 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// Lane arithmetic of the recurrence.  Ar<false>: two aligners per word, 2*score + tag in signed 16-bit halves (the fast
+// path).  Ar<true> ("wide"): one aligner per word in 32 bits, with the reference's storage type made explicit -- every
+// score is stored as `unsigned short` (AGEaligner.hh:86, AGEaligner.cpp:1019,1073), so the doubled value is reduced
+// modulo 2^17 after the trace decision (`wrap`), and the split sum `unsigned short val = *maxf + *maxr` (:479,548)
+// modulo 2^17 as well (`sum`); the equality tests of findBPs (:493,565) compare plain ints and are not wrapped.
+template <bool WIDE> struct Ar;
+template <> struct Ar<false> {
+    static constexpr uint32_t TAG = 0x00010001u, NTAG = 0xFFFEFFFEu;
+    static __device__ __forceinline__ uint32_t maxs(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+    static __device__ __forceinline__ uint32_t maxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+    static __device__ __forceinline__ uint32_t wrap(uint32_t x) { return x; }
+    static __device__ __forceinline__ uint32_t sum(uint32_t x) { return x; }
+    static __device__ __forceinline__ uint32_t pack(int a, int b) { return (uint32_t)(a & 0xFFFF) | ((uint32_t)b << 16); }
+    static __device__ __forceinline__ int lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+    static __device__ __forceinline__ int hi(uint32_t v) { return (int)(short)(v >> 16); }
+};
+template <> struct Ar<true> {
+    static constexpr uint32_t TAG = 1u, NTAG = 0xFFFFFFFEu;
+    static __device__ __forceinline__ uint32_t maxs(uint32_t a, uint32_t b) { return (uint32_t)max((int)a, (int)b); }
+    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__viaddmax_s32_relu((int)a, (int)b, (int)c); }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+    static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__vimax3_s32((int)a, (int)b, (int)c); }
+    static __device__ __forceinline__ uint32_t maxu(uint32_t a, uint32_t b) { return max(a, b); }
+    static __device__ __forceinline__ uint32_t wrap(uint32_t x) { return x & 0x1FFFFu; }
+    static __device__ __forceinline__ uint32_t sum(uint32_t x) { return x & 0x1FFFEu; }
+    static __device__ __forceinline__ uint32_t pack(int a, int) { return (uint32_t)a; }
+    static __device__ __forceinline__ int lo(uint32_t v) { return (int)v; }
+    static __device__ __forceinline__ int hi(uint32_t v) { return (int)v; }
+};
+
 // substitution score (x2) of one half for a special column (Scorer.hh:24-39): codes >= 5 score 0
 __device__ __forceinline__ int subst2(int xc, int yc, int m2, int mm2)
 {
@@ -209,10 +242,11 @@ __device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS,
 // One window (steps t0 .. t1) of one strip of the main sweep in which some lanes are idle in some steps: the first
 // window(s) of a strip (the wavefront fills up), the last ones (it drains, and the last block may hold padding columns).
 // The windows in between go through sweep_window_steady.
-template <int DIR, int DFMT>
+template <int DIR, int DFMT, bool WIDE>
 __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
                                                   const int t0, const int t1, uint32_t &best)
 {
+    using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
     constexpr int DSTEP = 32 * (DFMT == DFMT_OFF8 ? 5 : 2 * W);
     const int lane = C.lane, p = C.p, nb = C.nb;
@@ -264,12 +298,12 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
                 const uint32_t info = (xb.z >> (8 * w)) & 0xFFu;
                 if (special && (info & 1u)) {
                     const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
-                    const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+                    const int m2a = A::lo(C.m2), m2b = A::hi(C.m2), mm2a = A::lo(C.mm2), mm2b = A::hi(C.mm2);
 #pragma unroll
                     for (int k = 0; k < RPT; ++k) {
                         const int yc = C.ycode[C.q0 + k];
                         const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
-                        S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
+                        S2[k] = A::pack(sa, sb);
                     }
                 } else {
 #pragma unroll
@@ -289,17 +323,17 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
                     const int k = FWD ? j : RPT - 1 - j;
-                    const uint32_t g  = __vmaxs2(S.Gl[k], vG);
-                    const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);      // max(2d, 2h+1, 2v+1, 0)
-                    const uint32_t tg = (s2 ^ C.flip) & 0x00010001u;
-                    const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);         // 2*(s + (gap ? ge : go)) + 1
-                    const uint32_t Hc = s2 & 0xFFFEFFFEu;
-                    const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
+                    const uint32_t g  = A::maxs(S.Gl[k], vG);
+                    const uint32_t s2 = A::wrap(A::addmax_relu(dg, S2[k], g));    // max(2d, 2h+1, 2v+1, 0)
+                    const uint32_t tg = (s2 ^ C.flip) & A::TAG;
+                    const uint32_t G2 = A::add(tg * C.kabs + s2, C.c0x);          // 2*(s + (gap ? ge : go)) + 1
+                    const uint32_t Hc = s2 & A::NTAG;
+                    const uint32_t Mn = A::max3(Hc, S.Ml[k], vM);
                     if (!FWD) {
                         if (DFMT == DFMT_RAW) {
                             const uint4 dv = (k >> 2) ? dc1 : dc0;
                             const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
-                            best = __vmaxu2(best, __vadd2(Mn, dk));
+                            best = A::maxu(best, A::sum(A::add(Mn, dk)));
                         } else colbest = __vmaxu2(colbest, __vadd2(Mn, d8_offset(dc0, k)));
                     }
                     dg = S.Hl[k];
@@ -339,10 +373,11 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
 // instruction count -- running pointers instead of per-step address arithmetic,
 // no clamps on the column descriptors (1 <= t - p <= nb throughout), and the N / IUPAC test hoisted out of the
 // column loop (one copy of the step body without it, one with it).
-template <int DIR, int DFMT, bool FLIP>
+template <int DIR, int DFMT, bool FLIP, bool WIDE>
 __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
                                                     const int t0, const int t1, uint32_t &best)
 {
+    using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
     constexpr int NPL = DFMT == DFMT_OFF8 ? 5 : 2 * W, DSTEP = 32 * NPL;     // uint4 of D per (lane, step) / per step
     const int lane = C.lane, p = C.p, nb = C.nb;
@@ -412,12 +447,12 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                 const uint32_t info = SPECIAL ? (xz >> (8 * w)) & 0xFFu : 0u;
                 if (SPECIAL && (info & 1u)) {
                     const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
-                    const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+                    const int m2a = A::lo(C.m2), m2b = A::hi(C.m2), mm2a = A::lo(C.mm2), mm2b = A::hi(C.mm2);
 #pragma unroll
                     for (int k = 0; k < RPT; ++k) {
                         const int yc = C.ycode[C.q0 + k];
                         const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
-                        S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
+                        S2[k] = A::pack(sa, sb);
                     }
                 } else {
 #pragma unroll
@@ -436,21 +471,21 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
                     const int k = FWD ? j : RPT - 1 - j;
-                    const uint32_t g  = __vmaxs2(S.Gl[k], vG);
-                    const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);
-                    const uint32_t tg = FLIP ? (~s2 & 0x00010001u) : (s2 & 0x00010001u);
-                    const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
+                    const uint32_t g  = A::maxs(S.Gl[k], vG);
+                    const uint32_t s2 = A::wrap(A::addmax_relu(dg, S2[k], g));
+                    const uint32_t tg = FLIP ? (~s2 & A::TAG) : (s2 & A::TAG);
+                    const uint32_t G2 = A::add(tg * C.kabs + s2, C.c0x);
                     // clearing the tags: with FLIP = false tg IS the tag pair, and s2 - tg cannot borrow between the halves,
                     // so the subtraction can run as a multiply-add on the FMA pipe (the ALU pipe is the busy one)
                     uint32_t Hc;
-                    if (FLIP) Hc = s2 & 0xFFFEFFFEu;
+                    if (FLIP) Hc = s2 & A::NTAG;
                     else asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, %2;" : "=r"(Hc) : "r"(tg), "r"(s2));
-                    const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
+                    const uint32_t Mn = A::max3(Hc, S.Ml[k], vM);
                     if (!FWD) {
                         if (DFMT == DFMT_RAW) {
                             const uint4 dv = (k >> 2) ? dc1 : dc0;
                             const uint32_t dk = (k & 3) == 0 ? dv.x : (k & 3) == 1 ? dv.y : (k & 3) == 2 ? dv.z : dv.w;
-                            best = __vmaxu2(best, __vadd2(Mn, dk));
+                            best = A::maxu(best, A::sum(A::add(Mn, dk)));
                         } else colbest = __vmaxu2(colbest, __vadd2(Mn, d8_offset(dc0, k)));
                     }
                     dg = S.Hl[k];
@@ -491,22 +526,22 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
 }
 
 // dispatch on whether the window is steady (all lanes active in all of its steps)
-template <int DIR, int DFMT>
+template <int DIR, int DFMT, bool WIDE>
 __device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win, uint32_t &best)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
     if (t0 >= 32 && t1 <= C.nb) {
-        if (C.flip == 0) sweep_window_steady<DIR, DFMT, false>(C, S, R, DS, win, t0, t1, best);
-        else             sweep_window_steady<DIR, DFMT, true>(C, S, R, DS, win, t0, t1, best);
+        if (C.flip == 0) sweep_window_steady<DIR, DFMT, false, WIDE>(C, S, R, DS, win, t0, t1, best);
+        else             sweep_window_steady<DIR, DFMT, true, WIDE>(C, S, R, DS, win, t0, t1, best);
     }
-    else                        sweep_window_edge<DIR, DFMT>(C, S, R, DS, win, t0, t1, best);
+    else                        sweep_window_edge<DIR, DFMT, WIDE>(C, S, R, DS, win, t0, t1, best);
 }
 
 // The main sweep of one pair in one direction: checkpoints, tile maxima, all windows of the strips si0, si0 + stride, ...
 // (in sweep order).  With stride > 1 several warps of one CTA share the pair (long alignments): strip si starts as soon
 // as the warp of strip si-1 has flushed the first boundary blocks and then runs 32+ steps behind it; `prog` (shared
 // memory, one counter per strip, zeroed by the caller) carries the number of flushed blocks.
-template <int DIR>
+template <int DIR, bool WIDE>
 __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, const int lane,
                                 const int si0 = 0, const int stride = 1, volatile int *prog = nullptr)
 {
@@ -534,8 +569,8 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
             __syncwarp();
             if (!C.first && win + 1 < C.nwin) { wait_blocks(win + 1); ring_prefetch(C, R, win + 1, (win + 1) & 1); }
             state_save(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
-            if (C.dfmt == DFMT_OFF8) sweep_window_any<DIR, DFMT_OFF8>(C, S, R, DS, win, best);
-            else                     sweep_window_any<DIR, DFMT_RAW>(C, S, R, DS, win, best);
+            if (!WIDE && C.dfmt == DFMT_OFF8) sweep_window_any<DIR, DFMT_OFF8, false>(C, S, R, DS, win, best);
+            else                              sweep_window_any<DIR, DFMT_RAW, WIDE>(C, S, R, DS, win, best);
             if (!FWD) { C.tilemax[(size_t)(s * C.nwin + win) * 32 + lane] = best; best = 0; }
         }
         // the maxima at the last processed column: Fmax[.][len1] (forward) / Rmax[.][1] (reverse)
@@ -559,16 +594,18 @@ struct TraceSmem {
 // columns of a block is NOT unrolled (its per-column values live in shared memory), so the whole step body is a few
 // hundred instructions.  Pass 2 is latency- and instruction-fetch-bound: a fully unrolled 32-cell body with the
 // trace code inlined overflows the instruction cache and runs several times slower.
-template <int DIR, int MODE>
+template <int DIR, int MODE, bool WIDE>
 __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, TraceSmem &X,
                                                   const int win, const TraceOut &TO)
 {
+    using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
     constexpr bool TRACE_S = MODE == MODE_TRACE_S, TRACE_M = MODE == MODE_TRACE_M;
     const int lane = C.lane, p = C.p, nb = C.nb, buf = win & 1;
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
     const int prev_lane = FWD ? (lane + 31) & 31 : (lane + 1) & 31;
-    const uint32_t hbit = 1u << TO.sh, hmask = 0xFFFFu << TO.sh, hsign = 0x8000u << TO.sh;   // the wanted half of a packed word
+    // the wanted half of a packed word (wide: the whole word)
+    const uint32_t hbit = 1u << TO.sh, hmask = WIDE ? 0xFFFFFFFFu : 0xFFFFu << TO.sh, hsign = WIDE ? 0x80000000u : 0x8000u << TO.sh;
     const uint32_t maxw = (uint32_t)TO.max2 << TO.sh;
 #pragma unroll
     for (int w = 0; w < W; ++w) { X.oH[w][lane] = S.oH[w]; X.oG[w][lane] = S.oG[w]; X.oM[w][lane] = S.oM[w]; }
@@ -601,12 +638,12 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
             const uint32_t info = (xb.z >> (8 * w)) & 0xFFu;
             if (info & 1u) {
                 const int xa = (info >> 1) & 7, xc = (info >> 4) & 7;
-                const int m2a = lo16(C.m2), m2b = hi16(C.m2), mm2a = lo16(C.mm2), mm2b = hi16(C.mm2);
+                const int m2a = A::lo(C.m2), m2b = A::hi(C.m2), mm2a = A::lo(C.mm2), mm2b = A::hi(C.mm2);
 #pragma unroll
                 for (int k = 0; k < RPT; ++k) {
                     const int yc = C.ycode[C.q0 + k];
                     const int sa = subst2(xa, yc & 15, m2a, mm2a), sb = subst2(xc, yc >> 4, m2b, mm2b);
-                    S2[k] = (uint32_t)(sa & 0xFFFF) | ((uint32_t)sb << 16);
+                    S2[k] = A::pack(sa, sb);
                 }
             } else {
                 const uint32_t sel = ((w < 2 ? xb.x : xb.y) >> (16 * (w & 1))) & 0xFFFFu;
@@ -630,12 +667,12 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 const int k = FWD ? j : RPT - 1 - j;
-                const uint32_t g  = __vmaxs2(S.Gl[k], vG);
-                const uint32_t s2 = __viaddmax_s16x2_relu(dg, S2[k], g);
-                const uint32_t tg = (s2 ^ C.flip) & 0x00010001u;
-                const uint32_t G2 = __vadd2(tg * C.kabs + s2, C.c0x);
-                const uint32_t Hc = s2 & 0xFFFEFFFEu;
-                const uint32_t Mn = __vimax3_s16x2(Hc, S.Ml[k], vM);
+                const uint32_t g  = A::maxs(S.Gl[k], vG);
+                const uint32_t s2 = A::wrap(A::addmax_relu(dg, S2[k], g));
+                const uint32_t tg = (s2 ^ C.flip) & A::TAG;
+                const uint32_t G2 = A::add(tg * C.kabs + s2, C.c0x);
+                const uint32_t Hc = s2 & A::NTAG;
+                const uint32_t Mn = A::max3(Hc, S.Ml[k], vM);
                 // Trace codes of the wanted half, read off the packed words the recurrence has anyway.
                 //   FS (:1015-1017: s = d, t = D; if h >= s: H; if v >= s: V; if s < 0: stop): the cell's tag says gap (H / V)
                 //       or not; among the gaps V wins iff the vertical candidate is the larger-or-equal one (g == vG);
@@ -643,16 +680,16 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
                 //   FM (:899-915 / :952-968: V if up > own, then H if left > the larger of the two): H iff the left maximum
                 //       beats max(own, up), else V iff up beats own.
                 if (TRACE_S) {
-                    const bool gap = (s2 & hbit) != 0, vwin = ((g ^ vG) & hmask) == 0, dneg = (__vadd2(dg, S2[k]) & hsign) != 0;
+                    const bool gap = (s2 & hbit) != 0, vwin = ((g ^ vG) & hmask) == 0, dneg = (A::add(dg, S2[k]) & hsign) != 0;
                     codes |= (gap ? (vwin ? T_VERT : T_HORI) : (dneg ? T_STOP : T_DIAG)) << (2 * k);
                 }
                 if (TRACE_M) {
-                    const uint32_t m1 = __vmaxs2(Hc, vM);
+                    const uint32_t m1 = A::maxs(Hc, vM);
                     const bool isH = ((Mn ^ m1) & hmask) != 0, isV = ((m1 ^ Hc) & hmask) != 0;
                     codes |= (isH ? T_HORI : (isV ? T_VERT : T_STOP)) << (2 * k);
                 }
                 if (!FWD && TRACE_M) {
-                    if (((__vadd2(Mn, dk[k]) ^ maxw) & hmask) == 0) hotw |= 1u << (8 * w + k);
+                    if (((A::add(Mn, dk[k]) ^ maxw) & hmask) == 0) hotw |= 1u << (8 * w + k);    // plain int compare (:565), no wrap
                 }
                 dg = S.Hl[k];
                 S.Hl[k] = Hc; S.Gl[k] = G2; S.Ml[k] = Mn;
@@ -676,7 +713,7 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
 }
 
 // Recompute one window of one strip from its checkpoint, emitting the trace (pass 2).
-template <int DIR, int MODE>
+template <int DIR, int MODE, bool WIDE>
 __device__ __forceinline__ void sweep_window_trace(const PairTask &T, WarpRings &R, TraceSmem &X, const int lane, int s, int win, const TraceOut &TO)
 {
     constexpr bool FWD = DIR > 0;
@@ -688,7 +725,7 @@ __device__ __forceinline__ void sweep_window_trace(const PairTask &T, WarpRings 
     __syncwarp();
     if (C.first) ring_fill_border(R, lane, C.gborder);
     else { ring_prefetch(C, R, win, win & 1); cp_async_wait_all(); __syncwarp(); }
-    sweep_window_compact<DIR, MODE>(C, S, R, X, win, TO);
+    sweep_window_compact<DIR, MODE, WIDE>(C, S, R, X, win, TO);
     __syncwarp();
 }
 

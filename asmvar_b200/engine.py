@@ -117,6 +117,12 @@ class Engine:
     def run_staged(self):
         self._check(self.lib.age_run_staged(self.ctx), "age_run_staged")
 
+    def run_staged_many(self, reps: int) -> float:
+        """`reps` runs of the staged batch queued back to back; returns the CUDA-event time of all of them in ms"""
+        ms = C.c_double(0.0)
+        self._check(self.lib.age_run_staged_many(self.ctx, reps, C.byref(ms)), "age_run_staged_many")
+        return ms.value
+
     def fetch(self, n: int):
         res = (capi.AgeResult * max(1, n))()
         self._check(self.lib.age_fetch(self.ctx, res, n), "age_fetch")

@@ -29,16 +29,13 @@ def _mutate(rng, a: np.ndarray, sub=0.01, indel=0.001) -> np.ndarray:
     m = rng.random(n) < sub
     a[m] = _ACGT[rng.integers(0, 4, int(m.sum()))]
     dele = rng.random(n) < indel / 2
-    ins = rng.random(n) < indel / 2
+    ins = (rng.random(n) < indel / 2) & ~dele
     if dele.any() or ins.any():
-        out = []
-        for i in range(n):
-            if dele[i]:
-                continue
-            out.append(a[i])
-            if ins[i]:
-                out.append(_ACGT[rng.integers(0, 4)])
-        a = np.array(out, dtype=np.uint8)
+        reps = (~dele).astype(np.int64) + ins            # deleted bases vanish, a random base follows the inserted-after ones
+        out = np.repeat(a, reps)
+        at = np.cumsum(reps)[ins] - 1
+        out[at] = _ACGT[rng.integers(0, 4, at.size)]
+        a = out
     return a
 
 
@@ -85,6 +82,32 @@ def tdup_candidates(n: int, seed: int = 1003, window: int = 4000, flank: int = 5
     return out
 
 
+C3_WINDOWS = (1000, 2000, 4000, 8000)
+C3_CONTIGS = (500, 1000, 2000)
+
+
+def mixed_candidates(n: int, seed: int = 1003, p_indel: float = 0.7):
+    """C3: len1 in {1, 2, 4, 8} kb x len2 in {0.5, 1, 2} kb, uniform over the 12 bins; 70 % indel candidates as in C2,
+    30 % tandem duplications.  Returns (kind, window, contig) with kind "indel" / "tdup": the reference runs one mode
+    per invocation (age_align.cpp:207-221), so the two kinds go to two invocations (-i -b / -d -b)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        window = C3_WINDOWS[int(rng.integers(0, 4))]
+        len2 = C3_CONTIGS[int(rng.integers(0, 3))]
+        sub_seed = int(rng.integers(0, 2**31 - 1))
+        if rng.random() < p_indel:
+            flank = min(len2 // 2, (window - 100) // 2)
+            w, q = indel_candidates(1, seed=sub_seed, window=window, flank=flank, max_del=max(60, window - 2 * flank),
+                                    max_ins=max(60, min(1000, len2)))[0]
+            out.append(("indel", w, q))
+        else:
+            flank = min(len2 // 2, window // 2 - 120)
+            w, q = tdup_candidates(1, seed=sub_seed, window=window, flank=flank)[0]
+            out.append(("tdup", w, q))
+    return out
+
+
 def inversion_candidates(n: int, seed: int = 1004, window: int = 20000, flank: int = 2000):
     """C4: inversion of W[a:b]; the contig holds `flank` bases outside and `flank` inside one breakpoint."""
     rng = np.random.default_rng(seed)
@@ -109,13 +132,15 @@ def long_sv_candidates(n: int, seed: int = 1005, window: int = 50000, flank: int
     return indel_candidates(n, seed=seed, window=window, flank=flank, max_del=35000, p_del=1.0, min_sv=5000)
 
 
-def write_files(cands, outdir: Path, prefix: str = "c"):
-    """FASTA pair + variant table for the batch CLI: one target record and one query record per candidate."""
+def write_files(cands, outdir: Path, prefix: str = "c", ids=None):
+    """FASTA pair + variant table for the batch CLI: one target record and one query record per candidate, named after
+    `ids` (default 0..n-1) so that shards of one candidate list keep the names of the whole list."""
     outdir = Path(outdir)
     outdir.mkdir(parents=True, exist_ok=True)
     t, q, v = outdir / f"{prefix}.target.fa", outdir / f"{prefix}.query.fa", outdir / f"{prefix}.var.txt"
     with open(t, "wb") as ft, open(q, "wb") as fq, open(v, "w") as fv:
-        for i, (w, c) in enumerate(cands):
+        for k, (w, c) in enumerate(cands):
+            i = k if ids is None else ids[k]
             ft.write(b">t%d\n%s\n" % (i, w))
             fq.write(b">q%d\n%s\n" % (i, c))
             fv.write(f"t{i}\t1\t{len(w)}\tq{i}\t1\t{len(c)}\tcand{i}\n")

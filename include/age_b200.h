@@ -31,9 +31,12 @@ extern "C" {
 /* Status codes of age_result.status */
 #define AGE_OK              0
 #define AGE_NOT_ALIGNED     1   /* AGEaligner::align() would return false (AGEaligner.cpp:68-69) */
-#define AGE_ERR_RANGE      -1   /* scores do not fit the 16-bit DP range */
+#define AGE_ERR_RANGE      -1   /* |match| or |mismatch| > 16383: 2*S does not fit the 16-bit score tables */
 #define AGE_ERR_CUDA       -2
-#define AGE_ERR_ARG        -3
+#define AGE_ERR_ARG        -3   /* also: several mode bits set without AGE_INVERSION_FLAG.  The reference accepts such flags
+                                 * (AGEaligner.cpp:69 only tests `flag & ALL_FLAGS`) and then mixes the modes' code paths; neither of
+                                 * its command lines can produce them.  With AGE_INVERSION_FLAG set the other bits are ignored, as in
+                                 * AGEaligner.cpp:72-77.  Deliberate difference. */
 
 typedef struct age_ctx age_ctx;
 
@@ -44,7 +47,7 @@ typedef struct age_ctx age_ctx;
 typedef struct {
     const char *seq1; int32_t len1;     /* first sequence  = target / reference window */
     const char *seq2; int32_t len2;     /* second sequence = query / assembly contig    */
-    int32_t flag;                       /* exactly one AGE_*_FLAG                       */
+    int32_t flag;                       /* one AGE_*_FLAG (see AGE_ERR_ARG)             */
     int16_t match, mismatch, gap_open, gap_extend;
     int32_t partner;                    /* -both (age_align.cpp:264-278): index in the same batch of the job that aligns the
                                          * reverse-complemented contig against the same seq1, or -1.  When two jobs name each other,
@@ -89,6 +92,8 @@ typedef struct {
     uint64_t launches;         /* kernels launched */
     uint64_t fill_launches;
     uint64_t n_aligners;       /* single-mode aligner runs executed (a -inv job is two) */
+    uint64_t sweep_bytes;      /* bytes the sweep kernels of the batch move to and from HBM by construction: the D planes in the
+                                * batch's storage format written and read back, checkpoints, strip boundary rows, tile maxima */
 } age_stats;
 
 /* Replaces: process start-up of age_align (age_align.cpp:194-229).  device_ids may be NULL
@@ -116,9 +121,19 @@ int age_in_flight(const age_ctx *ctx);
  * stage = host packing + host->device copy; run = kernels only (repeatable); fetch = device->host + result assembly. */
 int age_stage(age_ctx *ctx, const age_job *jobs, size_t n);
 int age_run_staged(age_ctx *ctx);
+/* `reps` runs of the staged batch queued back to back without a host synchronisation in between (the chunks of consecutive
+ * runs overlap exactly as the chunks of consecutive age_submit batches do); *total_ms = CUDA-event time of all of them. */
+int age_run_staged_many(age_ctx *ctx, int reps, double *total_ms);
 int age_fetch(age_ctx *ctx, age_result *out, size_t n);
 
 int age_get_stats(const age_ctx *ctx, age_stats *st);
+
+/* Host-only planning, no CUDA device needed (replaces nothing in the reference; its sharding hook is --selectId,
+ * age_align.cpp:233): what age_create(ids, n_dev) + age_submit would do with these jobs.  device_of_job[i] = index of the
+ * device the job's main aligner runs on (pairs are dealt longest-processing-time-first by DP area; mutual -both partners and
+ * the INVL / INVR aligners of an -inv job share a warp, hence a device), -1 if the job is not aligned.
+ * arith_of_job[i] (may be NULL) = 16: packed 16-bit halves, 32: wide 32-bit words, otherwise the AGE_* status (<= 1) the job would get. */
+int age_plan(const age_job *jobs, size_t n, int n_dev, int32_t *device_of_job, int32_t *arith_of_job);
 
 /* Replaces: AGEaligner::printAlignment() (AGEaligner.cpp:179-380) incl. AliFragment::printAlignment
  * (AGEaligner.hh:230-272).  Writes the record (starting with the blank line before "MATCH = ...") into

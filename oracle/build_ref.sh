@@ -14,7 +14,9 @@
 # Outputs:
 #   oracle/_ref/age_align_ref        batch CLI (src/AsmvarAGE/src/age_align.cpp),  -O2, no OpenMP
 #   oracle/_ref/age_align_ref_orig   original CLI (src/AsmvarAGE/src/Trash/age_align.cpp), -O2, no OpenMP
-#   oracle/_ref/age_align_ref_omp    batch CLI with -fopenmp -DOMP (2 threads / alignment, as shipped)
+#   oracle/_ref/age_align_ref_omp    batch CLI with -O2 -fopenmp -DOMP (2 threads / alignment)
+#   oracle/_ref/age_align_ref_shipped  batch CLI exactly as the reference's Makefile builds it (src/AsmvarAGE/src/Makefile:1-3:
+#                                    no optimisation flag, -fopenmp -DOMP): the "as shipped" flavour of bench.py's cpu_baseline
 #   oracle/_ref/age_detect_dump      oracle/detect_dump.cpp (ours) around the AsmvarDetect flavour of the aligner
 #                                    (src/AsmvarDetect/AGEaligner.{h,cpp}): dumps AlignResult for golden vectors
 #   oracle/_ref/age_recall_dump      oracle/recall_dump.cpp (ours) around src/AsmvarDetect/VarUnit.cpp:
@@ -52,6 +54,7 @@ patch_tbm "$STAGE/orig/AGEaligner.cpp"
 FLAGS='-DAGE_VERSION="v0.8" -DAGE_TIME -w -O2'
 ( cd "$STAGE/batch" && g++ $FLAGS AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref" )
 ( cd "$STAGE/batch" && g++ $FLAGS -fopenmp -DOMP AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref_omp" )
+( cd "$STAGE/batch" && g++ -DAGE_VERSION="v0.8" -DAGE_TIME -w -fopenmp -DOMP AGEaligner.cpp age_align.cpp Join.cpp gzstream.cpp -lz -o "$OUT/age_align_ref_shipped" )
 ( cd "$STAGE/orig"  && g++ $FLAGS AGEaligner.cpp age_align.cpp -o "$OUT/age_align_ref_orig" )
 DET="$REF/src/AsmvarDetect"
 if [ -f "$DET/AGEaligner.cpp" ]; then

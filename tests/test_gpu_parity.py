@@ -151,7 +151,7 @@ def test_homopolymer_and_degenerate(eng):
 
 def test_not_aligned_and_range(eng):
     res = eng.align([(b"", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1), (b"ACGT", b"ACGT", 0, 1, -1, -10, -1),
-                     (b"ACGT", b"ACGT", capi.INDEL_FLAG, 100, -1, -10, -1), (b"ACGT", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1)])
+                     (b"ACGT", b"ACGT", capi.INDEL_FLAG, 20000, -1, -10, -1), (b"ACGT", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1)])
     assert [r["status"] for r in res] == [capi.AGE_NOT_ALIGNED, capi.AGE_NOT_ALIGNED, capi.AGE_ERR_RANGE, capi.AGE_OK]
 
 
@@ -179,13 +179,14 @@ def test_two_devices_same_results(eng):
         assert not diff_summary(y, x)
 
 
-@pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_QUEUE_CAP": "4"}, {"AGE_DFMT": "raw"},
-                                  {"AGE_DFMT": "raw", "AGE_LONG_NW": "1"}])
+@pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_DFMT": "raw"}, {"AGE_DFMT": "raw", "AGE_LONG_NW": "1"},
+                                  {"AGE_QUEUE_CAP": "4"}, {"AGE_CHUNKS": "4", "AGE_LONG_NW": "1"}, {"AGE_CHUNKS": "3", "AGE_QUEUE_CAP": "4"}])
 def test_golden_records_other_kernel_paths(eng, knob, monkeypatch):
     """The same golden batch through the code paths a small batch does not take by itself: one warp per pair
     (the kernel large batches use), 16 warps per pair (long alignments), a work list too short for the
-    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand, and the 16-bit storage format of the
-    forward-maxima plane (by default only scorings with match or mismatch above 15 use it)."""
+    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand, the 16-bit storage format of the
+    forward-maxima plane (by default only scorings with match or mismatch above 15 use it), and a batch cut into
+    chunks whose kernels overlap on several streams (by default only batches of thousands of pairs are)."""
     for k, v in knob.items():
         monkeypatch.setenv(k, v)
     jobs, owner = [], []
