@@ -126,9 +126,9 @@ __host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t 
            p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4) + p2_up((nwt + 1) * 4);
 }
 
-// One chunk of a sub-batch on one device: pairs [0, n_wide) run in the 32-bit kernels, the rest in the packed 16-bit ones.
-// counters: 32 ints, zeroed by launch_chunk_sweeps (0 / 16: pair counters of the packed / wide long-sweep kernel, 1: blocks
-// used in the pool, the rest: work counters of the pass-2 kernels).
+// One sub-batch on one device: pairs [0, n_wide) run in the 32-bit kernels, the rest in the packed 16-bit ones.
+// counters: 32 ints, zeroed by launch_sweeps (0 / 16: pair counters of the packed / wide sweep kernel, 1: blocks used in
+// the pool, the rest: work counters of the pass-2 kernels).
 struct BatchLaunch {
     const PairTask *pairs; int32_t n_pairs, n_wide;
     int32_t nw, nw_wide;                                // warps per pair in the sweep of the packed / wide pairs (sweep_warps_per_pair)
@@ -140,8 +140,8 @@ struct BatchLaunch {
 // launchers (age_kernels.cu)
 void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st);
 int  sweep_warps_per_pair(int n_pairs, int max_strips);
-void launch_chunk_sweeps(const BatchLaunch &b, cudaStream_t st);
-void launch_chunk_pass2(const BatchLaunch &b, cudaStream_t st);
-int  launches_per_chunk(const BatchLaunch &b);          // kernels the two calls above start
+void launch_sweeps(const BatchLaunch &b, cudaStream_t st);
+void launch_pass2(const BatchLaunch &b, cudaStream_t st);
+int  launches_per_batch(const BatchLaunch &b);          // kernels the two calls above start
 
 } // namespace age

@@ -87,44 +87,25 @@ struct HostPair {
     double cells;
 };
 
-constexpr int MAX_CHUNKS = 4;
-
-// A chunk: a quarter of a sub-batch with its own kernels, counters, share of the block pool and of the work list, and its
-// own region of the scratch arena.  The sweeps of consecutive chunks alternate between two streams, pass 2 runs on a third
-// (high-priority) one: pass 2 of chunk c and the end of its sweep overlap the sweep of chunk c+1.
-struct Chunk {
-    int p0 = 0, n_pairs = 0, n_wide = 0;         // pairs [p0, p0 + n_pairs) of the slot's task array, wide ones first
-    int nw = 1, nw_wide = 1;                     // warps per pair in the sweep (sweep_warps_per_pair)
-    int pool0 = 0, pool_cap = 0, queue0 = 0, queue_cap = 0;
-    size_t sc_begin = 0, sc_end = 0;             // range of the scratch arena its pairs use
-    cudaEvent_t ev_sw = nullptr, ev_p2 = nullptr;
-};
-
-// What one batch in flight owns on one device.  The big scratch arena (D planes, checkpoints, trace planes) is shared by
-// both slots of a device, chunk by chunk: a chunk starts when the chunks that used its range before are through pass 2.
+// What one batch in flight owns on one device.  The big scratch arena (D planes, checkpoints, trace planes) is
+// shared by both slots of a device: kernels of consecutive batches run back to back on one stream.
 struct Slot {
     Arena in, outbuf, aux;
     PinnedBuf hin, hout;
-    cudaEvent_t ev[7] = {};      // 0/1 H2D begin/end (cp), 2 kernels begin, 3 last sweep end, 4 kernels end, 5/6 D2H begin/end (rb)
-    std::vector<int> pair_ids;   // the sub-batch resident in this slot, chunk by chunk
+    cudaEvent_t ev[7] = {};      // 0/1 H2D begin/end (cp), 2 kernels begin, 3 sweeps end, 4 kernels end (st), 5/6 D2H begin/end (rb)
+    std::vector<int> pair_ids;   // the sub-batch resident in this slot: wide pairs first, then longest first
     std::vector<PairTask> tasks;
     std::vector<size_t> sc_off;
-    Chunk chunk[MAX_CHUNKS];
-    int n_chunks = 0;
-    int n_outs = 0, pool_cap = 0, queue_cap = 0, launches = 0;
+    int n_outs = 0, pool_cap = 0, queue_cap = 0, n_wide = 0, nw = 1, nw_wide = 1, launches = 0;
     size_t in_bytes = 0, out_bytes = 0, sc_bytes = 0;
 };
 
-struct Occupant { size_t begin, end; cudaEvent_t done; };   // a range of the scratch arena and the event behind its last user
-
 struct Device {
     int id = 0;
-    cudaStream_t sw[2] = {nullptr, nullptr};   // sweeps (and the pack kernel) of even / odd chunks
-    cudaStream_t p2 = nullptr;   // pass 2, high priority: its short-lived CTAs take the SM slots that retiring sweep CTAs free
+    cudaStream_t st = nullptr;   // kernels
     cudaStream_t cp = nullptr;   // host -> device copies of the next batch
     cudaStream_t rb = nullptr;   // device -> host read-back of the previous one
     Arena scratch;
-    std::vector<Occupant> occ;
     Slot slot[2];
     std::string err;
 };
@@ -362,83 +343,53 @@ size_t out_bytes_of(int n_outs, int pool_cap)
 bool sync_device(Device &dev)
 {
     CK(cudaSetDevice(dev.id));
-    for (cudaStream_t st : {dev.sw[0], dev.sw[1], dev.p2, dev.cp, dev.rb}) if (st) CK(cudaStreamSynchronize(st));
-    dev.occ.clear();
+    for (cudaStream_t st : {dev.st, dev.cp, dev.rb}) if (st) CK(cudaStreamSynchronize(st));
     return true;
 }
 
-// Deal the (wide first, longest first) ordered pairs of a sub-batch to its chunks.  Small sub-batches and those whose pairs
-// are shared by several warps (long alignments) stay in one piece.
-int plan_chunks(const Batch &B, const std::vector<int> &sorted, std::vector<int> &chunk_major, int *count, int *nw, int *nw_wide)
-{
-    int n_wide = 0, ms = 1, ms_wide = 1;
-    for (int pi : sorted) {
-        const HostPair &hp = B.pairs[pi];
-        n_wide += hp.wide;
-        (hp.wide ? ms_wide : ms) = std::max(hp.wide ? ms_wide : ms, hp.nstrips);
-    }
-    const int n_packed = (int)sorted.size() - n_wide;
-    *nw = sweep_warps_per_pair(n_packed, ms);
-    *nw_wide = sweep_warps_per_pair(n_wide, ms_wide);
-    int C = 1;
-    if (*nw == 1 && (n_wide == 0 || *nw_wide == 1)) C = std::max(1, std::min(MAX_CHUNKS, (int)sorted.size() / 1024));
-    if (const char *e = getenv("AGE_CHUNKS")) C = std::max(1, std::min(MAX_CHUNKS, atoi(e)));   // knob: 1 = one chunk, nothing overlaps
-    C = std::min<int>(C, std::max<size_t>(1, sorted.size()));
-    chunk_major.clear();
-    for (int c = 0; c < C; ++c) {
-        count[c] = 0;
-        for (size_t i = c; i < sorted.size(); i += C) { chunk_major.push_back(sorted[i]); ++count[c]; }
-    }
-    return C;
-}
-
-// stage one sub-batch (pair ids) in a slot of a device: plan its chunks, pack, copy inputs (copy stream), lay out scratch
+// stage one sub-batch (pair ids) in a slot of a device: pack, copy inputs (copy stream), lay out scratch
 bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, Slot &sl, const std::vector<int> &pair_ids_in)
 {
     CK(cudaSetDevice(dev.id));
-    // wide pairs first (they run in their own kernels), then the longest pairs first: the sweep grid is dispatched in this
-    // order, so its tail is made of short pairs
-    std::vector<int> sorted = pair_ids_in;
-    std::stable_sort(sorted.begin(), sorted.end(), [&](int a, int b) {
+    // wide pairs first (they run in their own kernels), then the longest pairs first: the persistent sweep kernel hands out
+    // pairs in this order, so its tail is made of short ones
+    sl.pair_ids = pair_ids_in;
+    std::stable_sort(sl.pair_ids.begin(), sl.pair_ids.end(), [&](int a, int b) {
         if (B.pairs[a].wide != B.pairs[b].wide) return B.pairs[a].wide > B.pairs[b].wide;
         return B.pairs[a].cells * B.pairs[a].nstrips > B.pairs[b].cells * B.pairs[b].nstrips; });
-    int count[MAX_CHUNKS], nw = 1, nw_wide = 1;
-    sl.n_chunks = plan_chunks(B, sorted, sl.pair_ids, count, &nw, &nw_wide);
     const std::vector<int> &pair_ids = sl.pair_ids;
     const size_t np = pair_ids.size();
     sl.tasks.assign(np, PairTask{});
     std::vector<size_t> in_off(np + 1, 0);
     sl.sc_off.assign(np + 1, 0);
-    int n_outs = 0;
+    int n_outs = 0, ms = 1, ms_wide = 1;
     size_t nwt_total = 0;
-    for (int c = 0, p0 = 0; c < sl.n_chunks; p0 += count[c], ++c) {
-        Chunk &ch = sl.chunk[c];
-        ch.p0 = p0; ch.n_pairs = count[c]; ch.n_wide = 0; ch.nw = nw; ch.nw_wide = nw_wide;
-        ch.sc_begin = sl.sc_off[p0];
-        for (int i = p0; i < p0 + count[c]; ++i) {
-            HostPair &hp = B.pairs[pair_ids[i]];
-            ch.n_wide += hp.wide;
-            in_off[i + 1] = in_off[i] + hp.in_bytes;
-            sl.sc_off[i + 1] = sl.sc_off[i] + hp.scratch_bytes;
-            nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets;
-            for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.aligners[hp.a[k]].out = n_outs++;
-        }
-        ch.sc_end = sl.sc_off[p0 + count[c]];
+    sl.n_wide = 0;
+    for (size_t i = 0; i < np; ++i) {
+        HostPair &hp = B.pairs[pair_ids[i]];
+        sl.n_wide += hp.wide;
+        (hp.wide ? ms_wide : ms) = std::max(hp.wide ? ms_wide : ms, hp.nstrips);
+        in_off[i + 1] = in_off[i] + hp.in_bytes;
+        sl.sc_off[i + 1] = sl.sc_off[i] + hp.scratch_bytes;
+        nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets;
+        for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.aligners[hp.a[k]].out = n_outs++;
     }
+    sl.nw = sweep_warps_per_pair((int)np - sl.n_wide, ms);
+    sl.nw_wide = sweep_warps_per_pair(sl.n_wide, ms_wide);
     sl.n_outs = n_outs;
     sl.sc_bytes = sl.sc_off[np];
-    sl.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64 * sl.n_chunks, (size_t)1 << 24);
-    if (const char *e = getenv("AGE_QUEUE_CAP")) sl.queue_cap = std::max(1, atoi(e)) * sl.n_chunks;   // test knob: a short work list forces on-demand re-sweeps
+    sl.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
+    if (const char *e = getenv("AGE_QUEUE_CAP")) sl.queue_cap = std::max(1, atoi(e));   // test knob: a short work list forces on-demand re-sweeps
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
     sl.in_bytes = task_bytes + in_off[np];
     if (!sl.hin.ensure(sl.in_bytes)) { dev.err = "pinned host allocation failed"; return false; }
     if (!sl.in.ensure(sl.in_bytes)) { dev.err = "device allocation failed (inputs)"; return false; }
     if (sl.sc_bytes + 256 > dev.scratch.cap) {
-        if (!sync_device(dev)) return false;             // the batch in flight still works in the arena that is about to move
+        CK(cudaStreamSynchronize(dev.st));               // the batch in flight still works in the arena that is about to move
         if (!dev.scratch.ensure(sl.sc_bytes + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
     }
-    sl.pool_cap = n_outs * 96 + 4096 * sl.n_chunks;
-    if (const char *e = getenv("AGE_POOL_CAP")) sl.pool_cap = std::max(1, atoi(e)) * sl.n_chunks;     // test knob: a small block pool forces the overflow re-run
+    sl.pool_cap = n_outs * 96 + 4096;
+    if (const char *e = getenv("AGE_POOL_CAP")) sl.pool_cap = std::max(1, atoi(e));     // test knob: a small block pool forces the overflow re-run
     sl.out_bytes = out_bytes_of(n_outs, sl.pool_cap);
     if (!sl.outbuf.ensure(sl.out_bytes)) { dev.err = "device allocation failed (outputs)"; return false; }
     if (!sl.hout.ensure(sl.out_bytes)) { dev.err = "pinned host allocation failed"; return false; }
@@ -451,6 +402,8 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     CK(cudaEventRecord(sl.ev[0], dev.cp));
     CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.in_bytes, cudaMemcpyHostToDevice, dev.cp));
     CK(cudaEventRecord(sl.ev[1], dev.cp));
+    CK(cudaStreamWaitEvent(dev.st, sl.ev[1], 0));
+    launch_pack((const PairTask *)sl.in.ptr, (int)np, dev.st);
     return true;
 }
 
@@ -460,55 +413,26 @@ OutLayout out_layout(const Slot &sl, char *base)
     OutLayout L;
     L.outs = (AlignerOut *)base;
     L.pool = (Block *)(base + align_up((size_t)sl.n_outs * sizeof(AlignerOut), 256));
-    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)sl.pool_cap * sizeof(Block), 256));   // 32 ints per chunk
+    L.counters = (int32_t *)((char *)L.pool + align_up((size_t)sl.pool_cap * sizeof(Block), 256));   // 32 ints
     return L;
 }
 
-// All kernels of the slot's sub-batch.  Per chunk: [wait for the earlier users of its scratch range] pack + sweeps on the
-// sweep stream of its parity, then pass 2 on the high-priority stream.
+// all kernels of the slot's sub-batch on the compute stream
 bool run_on_device(Device &dev, Slot &sl)
 {
     CK(cudaSetDevice(dev.id));
     OutLayout L = out_layout(sl, sl.outbuf.ptr);
-    const int C = sl.n_chunks;
-    // shares of the block pool and of the work list
-    for (int c = 0; c < C; ++c) {
-        Chunk &ch = sl.chunk[c];
-        ch.pool0 = (int)((long long)sl.pool_cap * c / C); ch.pool_cap = (int)((long long)sl.pool_cap * (c + 1) / C) - ch.pool0;
-        ch.queue0 = (int)((long long)sl.queue_cap * c / C); ch.queue_cap = (int)((long long)sl.queue_cap * (c + 1) / C) - ch.queue0;
-    }
-    sl.launches = 0;
-    for (int c = 0; c < C; ++c) {
-        Chunk &ch = sl.chunk[c];
-        cudaStream_t st = dev.sw[c & 1];
-        CK(cudaStreamWaitEvent(st, sl.ev[1], 0));                    // inputs on the device
-        if (c == 0) CK(cudaEventRecord(sl.ev[2], st));
-        std::vector<Occupant> keep;                                  // earlier users of this chunk's scratch range
-        for (const Occupant &o : dev.occ) {
-            const bool overlap = o.begin < ch.sc_end && ch.sc_begin < o.end;
-            if (overlap) CK(cudaStreamWaitEvent(st, o.done, 0));
-            if (overlap && o.begin >= ch.sc_begin && o.end <= ch.sc_end) continue;          // superseded by this chunk
-            if (dev.occ.size() > 16 && cudaEventQuery(o.done) == cudaSuccess) continue;     // long finished
-            keep.push_back(o);
-        }
-        cudaGetLastError();                                          // (cudaErrorNotReady of the queries)
-        dev.occ.swap(keep);
-        BatchLaunch b{};
-        b.pairs = (const PairTask *)sl.in.ptr + ch.p0; b.n_pairs = ch.n_pairs; b.n_wide = ch.n_wide; b.nw = ch.nw; b.nw_wide = ch.nw_wide;
-        b.outs = L.outs; b.pool = L.pool + ch.pool0; b.pool_cap = ch.pool_cap; b.counters = L.counters + 32 * c;
-        b.hdr = (PairHdr *)sl.aux.ptr + ch.p0;
-        b.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)) + ch.queue0; b.queue_cap = ch.queue_cap;
-        launch_pack(b.pairs, b.n_pairs, st);
-        launch_chunk_sweeps(b, st);
-        CK(cudaEventRecord(ch.ev_sw, st));
-        if (c == C - 1) CK(cudaEventRecord(sl.ev[3], st));
-        CK(cudaStreamWaitEvent(dev.p2, ch.ev_sw, 0));
-        launch_chunk_pass2(b, dev.p2);
-        CK(cudaEventRecord(ch.ev_p2, dev.p2));
-        dev.occ.push_back(Occupant{ch.sc_begin, ch.sc_end, ch.ev_p2});
-        sl.launches += 1 + launches_per_chunk(b);
-    }
-    CK(cudaEventRecord(sl.ev[4], dev.p2));                           // the pass-2 stream runs the chunks in order: this is the end of the batch
+    CK(cudaEventRecord(sl.ev[2], dev.st));
+    BatchLaunch b{};
+    b.pairs = (const PairTask *)sl.in.ptr; b.n_pairs = (int)sl.tasks.size(); b.n_wide = sl.n_wide; b.nw = sl.nw; b.nw_wide = sl.nw_wide;
+    b.outs = L.outs; b.pool = L.pool; b.pool_cap = sl.pool_cap; b.counters = L.counters;
+    b.hdr = (PairHdr *)sl.aux.ptr;
+    b.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)); b.queue_cap = sl.queue_cap;
+    launch_sweeps(b, dev.st);
+    CK(cudaEventRecord(sl.ev[3], dev.st));
+    launch_pass2(b, dev.st);
+    CK(cudaEventRecord(sl.ev[4], dev.st));
+    sl.launches = launches_per_batch(b);
     CK(cudaGetLastError());
     return true;
 }
@@ -535,8 +459,8 @@ bool rerun_with_pool(Batch &B, Device &dev, Slot &sl, int pool_cap)
     if (sl.sc_bytes + 256 > dev.scratch.cap && !dev.scratch.ensure(sl.sc_bytes + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
     for (size_t i = 0; i < sl.tasks.size(); ++i) assign_scratch(B.pairs[sl.pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
     memcpy(sl.hin.ptr, sl.tasks.data(), sl.tasks.size() * sizeof(PairTask));
-    CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, dev.cp));
-    CK(cudaEventRecord(sl.ev[1], dev.cp));
+    CK(cudaMemcpyAsync(sl.in.ptr, sl.hin.ptr, sl.tasks.size() * sizeof(PairTask), cudaMemcpyHostToDevice, dev.st));
+    launch_pack((const PairTask *)sl.in.ptr, (int)sl.tasks.size(), dev.st);
     return run_on_device(dev, sl) && enqueue_fetch(dev, sl);
 }
 
@@ -547,31 +471,25 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
     for (int attempt = 0; attempt < 4; ++attempt) {
         CK(cudaEventSynchronize(sl.ev[6]));
         OutLayout H = out_layout(sl, sl.hout.ptr);
-        long long want = 0;                               // a chunk ran out of its share of the block pool: run again with a larger pool
-        for (int c = 0; c < sl.n_chunks; ++c)
-            if (H.counters[32 * c + 1] > sl.chunk[c].pool_cap) want = std::max(want, (long long)H.counters[32 * c + 1] * sl.n_chunks);
-        if (want) {
-            if (!rerun_with_pool(B, dev, sl, (int)std::min<long long>(want + 4096 * sl.n_chunks, 1LL << 30))) return false;
-            st.launches += sl.launches; st.fill_launches += sl.n_chunks;
+        if (H.counters[1] > sl.pool_cap) {                // the block pool was too small: run again with a larger one
+            if (!rerun_with_pool(B, dev, sl, H.counters[1] + 4096)) return false;
+            st.launches += 1 + sl.launches; st.fill_launches += 1;
             continue;
         }
-        for (int c = 0; c < sl.n_chunks; ++c) {
-            const Chunk &ch = sl.chunk[c];
-            for (int i = ch.p0; i < ch.p0 + ch.n_pairs; ++i) {
-                const HostPair &hp = B.pairs[sl.pair_ids[i]];
-                for (int k = 0; k < 2; ++k) {
-                    if (hp.a[k] < 0) continue;
-                    const Aligner &al = B.aligners[hp.a[k]];
-                    const AlignerOut &o = H.outs[al.out];
-                    memcpy(&B.outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
-                    std::vector<age_block> &b = B.blocks[hp.a[k]];
-                    b.clear();
-                    for (int q = 0; q < 4; ++q)
-                        for (int x = 0; x < o.n_blk[q]; ++x) {
-                            const Block &s = H.pool[ch.pool0 + o.blk_off[q] + x];
-                            b.push_back(age_block{s.start1, s.start2, s.length});
-                        }
-                }
+        for (size_t i = 0; i < sl.pair_ids.size(); ++i) {
+            const HostPair &hp = B.pairs[sl.pair_ids[i]];
+            for (int k = 0; k < 2; ++k) {
+                if (hp.a[k] < 0) continue;
+                const Aligner &al = B.aligners[hp.a[k]];
+                const AlignerOut &o = H.outs[al.out];
+                memcpy(&B.outs[hp.a[k]], &o, offsetof(AlignerOut, bp) + sizeof(o.bp[0]) * (size_t)std::max(o.n_bp, 0));
+                std::vector<age_block> &b = B.blocks[hp.a[k]];
+                b.clear();
+                for (int q = 0; q < 4; ++q)
+                    for (int x = 0; x < o.n_blk[q]; ++x) {
+                        const Block &s = H.pool[o.blk_off[q] + x];
+                        b.push_back(age_block{s.start1, s.start2, s.length});
+                    }
             }
         }
         float ms = 0;
@@ -580,7 +498,7 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[3]) == cudaSuccess) st.fill_ms += ms;
         if (cudaEventElapsedTime(&ms, sl.ev[2], sl.ev[4]) == cudaSuccess) st.kernel_ms += ms;
         if (cudaEventElapsedTime(&ms, sl.ev[5], sl.ev[6]) == cudaSuccess) st.d2h_ms += ms;
-        st.launches += sl.launches; st.fill_launches += sl.n_chunks;
+        st.launches += 1 + sl.launches; st.fill_launches += 1;          // pack + the batch's kernels
         return true;
     }
     dev.err = "block pool overflow";
@@ -826,20 +744,11 @@ extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
         ctx->devs.push_back(d);
     }
     for (Device &d : ctx->devs) {
-        bool ok = cudaSetDevice(d.id) == cudaSuccess;
-        int prio_lo = 0, prio_hi = 0;
-        if (ok) cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        ok = ok && cudaStreamCreateWithPriority(&d.sw[0], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&d.sw[1], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&d.p2, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-             cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking) == cudaSuccess &&
-             cudaStreamCreateWithFlags(&d.rb, cudaStreamNonBlocking) == cudaSuccess;
-        for (Slot &sl : d.slot) {
+        bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&d.rb, cudaStreamNonBlocking) == cudaSuccess;
+        for (Slot &sl : d.slot)
             for (int e = 0; ok && e < 7; ++e) ok = cudaEventCreate(&sl.ev[e]) == cudaSuccess;
-            for (Chunk &ch : sl.chunk)
-                ok = ok && cudaEventCreateWithFlags(&ch.ev_sw, cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&ch.ev_p2, cudaEventDisableTiming) == cudaSuccess;
-        }
         if (!ok) { g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); age_destroy(ctx); return nullptr; }
     }
     if (g_hprof) fprintf(stderr, "[host prof] age_create %.1f ms\n", wall_ms() - t_create);
@@ -851,14 +760,13 @@ extern "C" void age_destroy(age_ctx *ctx)
     if (!ctx) return;
     for (Device &d : ctx->devs) {
         cudaSetDevice(d.id);
-        for (cudaStream_t st : {d.sw[0], d.sw[1], d.p2, d.cp, d.rb}) if (st) cudaStreamSynchronize(st);
+        for (cudaStream_t st : {d.st, d.cp, d.rb}) if (st) cudaStreamSynchronize(st);
         d.scratch.release();
         for (Slot &sl : d.slot) {
             sl.in.release(); sl.outbuf.release(); sl.aux.release(); sl.hin.release(); sl.hout.release();
             for (auto &e : sl.ev) if (e) cudaEventDestroy(e);
-            for (Chunk &ch : sl.chunk) { if (ch.ev_sw) cudaEventDestroy(ch.ev_sw); if (ch.ev_p2) cudaEventDestroy(ch.ev_p2); }
         }
-        for (cudaStream_t st : {d.sw[0], d.sw[1], d.p2, d.cp, d.rb}) if (st) cudaStreamDestroy(st);
+        for (cudaStream_t st : {d.st, d.cp, d.rb}) if (st) cudaStreamDestroy(st);
     }
     delete ctx;
 }
@@ -913,7 +821,7 @@ extern "C" int age_stage(age_ctx *ctx, const age_job *jobs, size_t n)
         B.on_dev[d] = 1;
         B.stats.h2d_bytes += sl.in_bytes;
     }
-    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.cp); }
+    for (Device &dev : ctx->devs) { cudaSetDevice(dev.id); cudaStreamSynchronize(dev.cp); cudaStreamSynchronize(dev.st); }
     ctx->stats = B.stats;
     ctx->staged = true;
     return 0;
@@ -955,10 +863,10 @@ extern "C" int age_run_staged_many(age_ctx *ctx, int reps, double *total_ms)
         if (!B.on_dev[d]) continue;
         cudaSetDevice(dev.id);
         cudaEventCreate(&e0[d]);
-        cudaEventRecord(e0[d], dev.sw[0]);
+        cudaEventRecord(e0[d], dev.st);
     }
     int rc = 0;
-    for (int r = 0; r < reps && rc == 0; ++r)            // repeats are queued back to back: chunk c of repeat r+1 follows pass 2 of chunk c of repeat r
+    for (int r = 0; r < reps && rc == 0; ++r)            // repeats are queued back to back on the compute stream
         for (size_t d = 0; d < nd; ++d)
             if (B.on_dev[d] && !run_on_device(ctx->devs[d], ctx->devs[d].slot[0])) { ctx->err = ctx->devs[d].err; rc = AGE_ERR_CUDA; break; }
     double worst = 0;

@@ -11,6 +11,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -53,14 +54,16 @@ struct Out {
     }
 };
 
-static int calc_width(int v1, int v2)
-{   // AGEaligner.cpp:382-390
-    int w1 = 0; if (v1 < 0) v1++;
-    while (v1 != 0) { w1++; v1 /= 10; }
-    int w2 = 0; if (v2 < 0) v2++;
-    while (v2 != 0) { w2++; v2 /= 10; }
-    return w1 > w2 ? w1 : w2;
+// Column width of the coordinate pairs in the header lines (the reference's calcWidth, AGEaligner.cpp:382-390): the
+// larger digit count of the two values, where 0 has no digit and a negative value counts the digits of -(v + 1).
+static int digit_count(long v)
+{
+    unsigned long u = v < 0 ? (unsigned long)(-(v + 1)) : (unsigned long)v;
+    int d = 0;
+    for (; u; u /= 10) ++d;
+    return d;
 }
+static int calc_width(int v1, int v2) { return std::max(digit_count(v1), digit_count(v2)); }
 
 // One aligned fragment (class AliFragment, AGEaligner.hh:179-273)
 struct Frag {
@@ -103,64 +106,76 @@ static void build_frags(const SeqHdr &s1, const SeqHdr &s1rc, const SeqHdr &s2, 
     }
 }
 
-// getExcisedRange (AGEaligner.cpp:156-177)
-static bool excised_range(int flag, bool rev1, const Frag &f, const Frag &nx, int &s, int &e,
-                          int add_s = 0, int add_e = 0)
+// The excised region between two consecutive fragments in first-sequence coordinates (semantics of getExcisedRange,
+// AGEaligner.cpp:156-177).  Per mode, which fragment end opens the region and whether that end itself belongs to it:
+//   INDEL  (f.end1, nx.start1) both exclusive      TDUPLICATION  [nx.start1, f.end1]: the duplicated stretch, ends swapped
+//   INVL   (f.end1, nx.start1] left exclusive      INVR          [f.end1, nx.start1) right exclusive
+static bool excised_range(int flag, bool rev1, const Frag &f, const Frag &nx, int &s, int &e, int add_s = 0, int add_e = 0)
 {
-    int inc1 = rev1 ? -1 : 1;
-    if (flag & AGE_INDEL_FLAG)             { s = f.end1 + inc1;  e = nx.start1 - inc1; }
-    else if (flag & AGE_TDUPLICATION_FLAG) { s = nx.start1;      e = f.end1; }
-    else if (flag & AGE_INVL_FLAG)         { s = f.end1 + inc1;  e = nx.start1; }
-    else if (flag & AGE_INVR_FLAG)         { s = f.end1;         e = nx.start1 - inc1; }
-    else return false;
-    s += inc1 * add_s;
-    e += inc1 * add_e;
+    const int step = rev1 ? -1 : 1;
+    const int mode = (flag & AGE_INDEL_FLAG) ? 0 : (flag & AGE_TDUPLICATION_FLAG) ? 1 : (flag & AGE_INVL_FLAG) ? 2 : (flag & AGE_INVR_FLAG) ? 3 : -1;
+    if (mode < 0) return false;
+    if (mode == 1) { s = nx.start1; e = f.end1; }
+    else {
+        s = f.end1 + ((mode == 0 || mode == 2) ? step : 0);
+        e = nx.start1 - ((mode == 0 || mode == 3) ? step : 0);
+    }
+    s += step * add_s;
+    e += step * add_e;
     return true;
 }
 
-// calcOutsideIdentity / calcInsideIdentity / calcIdentity (AGEaligner.cpp:392-447)
+// Longest m <= n such that the m bases starting at `head` equal the m bases ending at `tail` (Sequence::sameNuc: both
+// valid nucleotides, case-insensitive), by the prefix function of  head[0..n) # tail-n+1..tail  -- one pass instead of the
+// reference's restart per candidate length.  Bases that are not nucleotides never match, not even themselves: they get
+// different codes on the two sides of the separator, and inside a matched prefix there are none, so the prefix function
+// is only ever consulted on proper nucleotides.
+static int head_tail_overlap(const SeqHdr &q, long head, long tail, int n)
+{
+    if (n <= 0) return 0;
+    auto norm = [&](long i, char bad) {
+        const char c = (char)up(at(q, i));
+        return (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'U') ? c : bad;
+    };
+    std::vector<char> t((size_t)2 * n + 1);
+    for (int i = 0; i < n; i++) { t[i] = norm(head + i, 1); t[n + 1 + i] = norm(tail - n + 1 + i, 2); }
+    t[n] = 3;
+    std::vector<int> pf(t.size(), 0);
+    for (size_t i = 1; i < t.size(); i++) {
+        int k = pf[i - 1];
+        while (k > 0 && t[i] != t[k]) k = pf[k - 1];
+        pf[i] = k + (t[i] == t[k] ? 1 : 0);
+    }
+    return pf.back();
+}
+
+// "Identity outside breakpoints" (calcOutsideIdentity, AGEaligner.cpp:392-409): the longest stretch that ends at bp1 and is
+// repeated starting at bp2 (0-based positions), at most as long as the room on either side.
 static int outside_identity(const SeqHdr &q, int bp1, int bp2)
 {
     if (bp1 >= bp2) return 0;
-    int n = q.len, d1 = bp1 + 1, d2 = n - bp2;
-    int n_check = d1 < d2 ? d1 : d2;   // (d2 < d1) ? d2 : d1
-    if (d2 < d1) n_check = d2; else n_check = d1;
-    int start1 = bp1 - n_check + 1;
-    for (int i = 0; i < n_check; i++) {
-        int n_same = 0, start2 = bp2 - i;
-        for (int j = i; j < n_check; j++)
-            if (same_nuc(at(q, (long)start1 + j), at(q, (long)start2 + j))) n_same++;
-            else break;
-        if (n_same == n_check - i) return n_same;
-    }
-    return 0;
+    return head_tail_overlap(q, bp2, bp1, std::min(bp1 + 1, q.len - bp2));
 }
 
+// "Identity inside breakpoints" (calcInsideIdentity, AGEaligner.cpp:411-427): the longest stretch that starts at bp1 and is
+// repeated ending at bp2, at most half of the region.
 static int inside_identity(const SeqHdr &q, int bp1, int bp2)
 {
     if (bp1 >= bp2) return 0;
-    int n_check = (bp2 - bp1 + 1) / 2, start2 = bp2 - n_check + 1;
-    for (int i = 0; i < n_check; i++) {
-        int n_same = 0, start1 = bp1 - i;
-        for (int j = i; j < n_check; j++)
-            if (same_nuc(at(q, (long)start1 + j), at(q, (long)start2 + j))) n_same++;
-            else break;
-        if (n_same == n_check - i) return n_same;
-    }
-    return 0;
+    return head_tail_overlap(q, bp1, bp2, (bp2 - bp1 + 1) / 2);
 }
 
+// "Identity at breakpoints" (calcIdentity, AGEaligner.cpp:429-447): how far the sequence keeps agreeing with itself shifted
+// by bp2 - bp1, to the left of bp1 (left <= 0) and from bp1 on to the right (right >= 0).
 static int at_identity(const SeqHdr &q, int bp1, int bp2, int &left, int &right)
 {
     if (bp1 >= bp2) return 0;
-    int n = q.len, delta = bp2 - bp1;
-    if (delta == 0) return 0;
-    int start = bp1 - 1;
-    left = right = 0;
-    while (start >= 0 && same_nuc(at(q, start), at(q, (long)start + delta))) { start--; left--; }
-    int end = bp1;
-    while (end < n && same_nuc(at(q, end), at(q, (long)end + delta))) { end++; right++; }
-    return right - left;
+    const long shift = (long)bp2 - bp1;
+    int down = 0, up = 0;
+    for (long i = bp1 - 1; i >= 0 && same_nuc(at(q, i), at(q, i + shift)); --i) ++down;
+    for (long i = bp1; i < q.len && same_nuc(at(q, i), at(q, i + shift)); ++i) ++up;
+    left = -down; right = up;
+    return up + down;
 }
 
 static void range_line(Out &o, const char *label, int len, int s, int e)

@@ -112,25 +112,31 @@ void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st)
 
 struct SweepSmem { WarpRings rings; DStage dstage; };
 
-// The hot kernel: one warp per pair, pairs in longest-first order, four pairs per CTA.  The forward sweep of all strips
-// streams D, the reverse sweep folds it back in; both leave a checkpoint per window and no trace.  The grid is one CTA per
-// four pairs (no persistent loop): CTAs retire all through the launch, so the pass-2 kernels of an earlier chunk and the
-// sweep of the next one move into the freed SM slots (launch_batch).
+// The hot kernel: persistent, one warp per pair; the work counter hands out the pairs longest first.  The forward sweep of
+// all strips streams D, the reverse sweep folds it back in; both leave a checkpoint per window and no trace.
+// (Tried in round 2 and dropped, DESIGN.md section 4: pass 2 of a pair by the warp that swept it -- 98.6 ms per batch instead
+// of 57.4, and even compiled in but not executed it costs the sweep 13 %; one CTA per four pairs with the batch cut into
+// chunks on several streams so that pass 2 overlaps the next chunk's sweep -- 56-60 ms instead of 55.3.)
 template <bool WIDE>
 __global__ void __launch_bounds__(SWEEP_WARPS * 32, SWEEP_OCC)
-age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs)
+age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepSmem *sm = reinterpret_cast<SweepSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int item = blockIdx.x * SWEEP_WARPS + w;
-    if (item >= n_pairs) return;
-    const PairTask &T = pairs[item];
-    sweep_pair_fast<+1, WIDE>(T, sm[w].rings, sm[w].dstage, lane);
-    __threadfence_block();
-    __syncwarp();
-    sweep_pair_fast<-1, WIDE>(T, sm[w].rings, sm[w].dstage, lane);
-    cp_async_wait_all();
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= n_pairs) break;
+        const PairTask &T = pairs[item];
+        sweep_pair_fast<+1, WIDE>(T, sm[w].rings, sm[w].dstage, lane);
+        __threadfence_block();
+        __syncwarp();
+        sweep_pair_fast<-1, WIDE>(T, sm[w].rings, sm[w].dstage, lane);
+        cp_async_wait_all();
+        __syncwarp();
+    }
 }
 
 // Long alignments / small batches: the NW warps of a CTA share one pair and run its strips as a pipeline
@@ -193,23 +199,27 @@ static void launch_sweeps_t(const PairTask *d_pairs, int n_pairs, int nw, int32_
         age_sweep_long_kernel<WIDE><<<std::min(n_pairs, sms * per_sm), nw * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
         return;
     }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = std::min((n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * SWEEP_OCC);   // persistent: the work counter feeds the warps
     const int smem = SWEEP_WARPS * (int)sizeof(SweepSmem);
     cudaFuncSetAttribute(age_sweep_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    age_sweep_kernel<WIDE><<<(n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS, SWEEP_WARPS * 32, smem, st>>>(d_pairs, n_pairs);
+    age_sweep_kernel<WIDE><<<blocks, SWEEP_WARPS * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
 }
 
 template <bool WIDE> static void launch_pass2_t(const Pass2Params &p, cudaStream_t st);
 
-// The sweep kernels of one chunk (wide pairs first) on `st`
-void launch_chunk_sweeps(const BatchLaunch &b, cudaStream_t st)
+// The sweep kernels of a sub-batch (wide pairs first) on `st`
+void launch_sweeps(const BatchLaunch &b, cudaStream_t st)
 {
     cudaMemsetAsync(b.counters, 0, 32 * sizeof(int32_t), st);
     if (b.n_wide > 0) launch_sweeps_t<true>(b.pairs, b.n_wide, b.nw_wide, b.counters + 16, st);
     if (b.n_pairs > b.n_wide) launch_sweeps_t<false>(b.pairs + b.n_wide, b.n_pairs - b.n_wide, b.nw, b.counters + 0, st);
 }
 
-// Pass 2 of one chunk on `st`: select -> pre-sweep -> enumerate -> pre-sweep -> blocks, per kind of pair
-void launch_chunk_pass2(const BatchLaunch &b, cudaStream_t st)
+// Pass 2 of a sub-batch on `st`: select -> pre-sweep -> enumerate -> pre-sweep -> blocks, per kind of pair
+void launch_pass2(const BatchLaunch &b, cudaStream_t st)
 {
     for (int wide = 1; wide >= 0; --wide) {
         const int first = wide ? 0 : b.n_wide, n = wide ? b.n_wide : b.n_pairs - b.n_wide;
@@ -225,7 +235,7 @@ void launch_chunk_pass2(const BatchLaunch &b, cudaStream_t st)
     }
 }
 
-int launches_per_chunk(const BatchLaunch &b)
+int launches_per_batch(const BatchLaunch &b)
 {
     const int kinds = (b.n_wide > 0) + (b.n_pairs > b.n_wide);
     return kinds * 6;                                       // sweep, select, 2 pre-sweeps, enumerate, blocks

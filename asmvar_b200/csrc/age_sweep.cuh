@@ -32,7 +32,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Lane arithmetic of the recurrence.  Ar<false>: two aligners per word, 2*score + tag in signed 16-bit halves (the fast
 // path).  Ar<true> ("wide"): one aligner per word in 32 bits, with the reference's storage type made explicit -- every
 // score is stored as `unsigned short` (AGEaligner.hh:86, AGEaligner.cpp:1019,1073), so the doubled value is reduced
-// modulo 2^17 after the trace decision (`wrap`), and the split sum `unsigned short val = *maxf + *maxr` (:479,548)
+// modulo 2^17 after the trace decision (`store`), and the split sum `unsigned short val = *maxf + *maxr` (:479,548)
 // modulo 2^17 as well (`sum`); the equality tests of findBPs (:493,565) compare plain ints and are not wrapped.
 template <bool WIDE> struct Ar;
 template <> struct Ar<false> {
@@ -42,7 +42,7 @@ template <> struct Ar<false> {
     static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
     static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
     static __device__ __forceinline__ uint32_t maxu(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
-    static __device__ __forceinline__ uint32_t wrap(uint32_t x) { return x; }
+    static __device__ __forceinline__ uint32_t store(uint32_t x, uint32_t, uint32_t) { return x; }
     static __device__ __forceinline__ uint32_t sum(uint32_t x) { return x; }
     static __device__ __forceinline__ uint32_t pack(int a, int b) { return (uint32_t)(a & 0xFFFF) | ((uint32_t)b << 16); }
     static __device__ __forceinline__ int lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
@@ -55,7 +55,11 @@ template <> struct Ar<true> {
     static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
     static __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)__vimax3_s32((int)a, (int)b, (int)c); }
     static __device__ __forceinline__ uint32_t maxu(uint32_t a, uint32_t b) { return max(a, b); }
-    static __device__ __forceinline__ uint32_t wrap(uint32_t x) { return x & 0x1FFFFu; }
+    // what the matrix holds: the u16 store (rowmask = 0x1FFFF on rows of the contig) -- and 0 in padding rows / columns
+    // (rowmask or colmask 0), one LOP3.  With gap costs >= 0 padding cells would otherwise grow scores of their own and
+    // leak into the reverse sweep, which meets them first; zeroed they behave exactly like the matrix border (H = 0, trace
+    // 0, G = gap open).  The packed path needs none of this: its gap costs are negative, so padding never exceeds 0.
+    static __device__ __forceinline__ uint32_t store(uint32_t x, uint32_t rowmask, uint32_t colmask) { return x & rowmask & colmask; }
     static __device__ __forceinline__ uint32_t sum(uint32_t x) { return x & 0x1FFFEu; }
     static __device__ __forceinline__ uint32_t pack(int a, int) { return (uint32_t)a; }
     static __device__ __forceinline__ int lo(uint32_t v) { return (int)v; }
@@ -116,6 +120,7 @@ template <int DIR> struct StripCtx {
     size_t sbase;                           // s * nsteps
     uint32_t c0x, kabs, flip, gborder, m2, mm2;
     uint32_t Ta[RPT], Tb[RPT];
+    uint32_t rmask[RPT];                    // wide arithmetic only: 0x1FFFF on rows of the contig, 0 on padding rows (Ar<true>::store)
     const uint4 *xblk;
     const uint8_t *ycode;
     const uint4 *bin; uint4 *bout;          // boundary planes in / out (nullptr at the first / last strip)
@@ -137,7 +142,7 @@ template <int DIR> struct StripCtx {
         sbase = (size_t)s * nsteps;
         c0x = T.c0x; kabs = T.kabs; flip = T.flip; gborder = T.gborder; m2 = T.m2; mm2 = T.mm2;
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) { const uint2 y = __ldg(T.ytab + q0 + k); Ta[k] = y.x; Tb[k] = y.y; }
+        for (int k = 0; k < RPT; ++k) { const uint2 y = __ldg(T.ytab + q0 + k); Ta[k] = y.x; Tb[k] = y.y; rmask[k] = q0 + k < T.len2 ? 0x1FFFFu : 0u; }
         xblk = FWD ? T.xblk_f : T.xblk_r;
         ycode = T.ycode;
         uint4 *bnd = FWD ? T.bnd_f : T.bnd_r;
@@ -153,6 +158,13 @@ template <int DIR> struct StripCtx {
         live = q0 <= T.len2;
     }
 };
+
+// wide arithmetic: all-ones when column w of the lane's block b is a column of the window, 0 when it is padding behind len1
+template <int DIR> __device__ __forceinline__ uint32_t col_mask(const StripCtx<DIR> &C, int b, int w)
+{
+    const int c = DIR > 0 ? W * (b - 1) + 1 + w : W * (C.nb - b + 1) - w;
+    return c <= C.len1 ? 0xFFFFFFFFu : 0u;
+}
 
 __device__ __forceinline__ void state_init(LaneState &S, uint32_t gborder)
 {
@@ -319,12 +331,13 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
                         colbase = (W - 1 - w) == 0 ? dbase.x : (W - 1 - w) == 1 ? dbase.y : (W - 1 - w) == 2 ? dbase.z : dbase.w;
                     }
                 }
+                const uint32_t cmask = WIDE ? col_mask(C, b, w) : 0xFFFFFFFFu;
                 uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
                     const int k = FWD ? j : RPT - 1 - j;
                     const uint32_t g  = A::maxs(S.Gl[k], vG);
-                    const uint32_t s2 = A::wrap(A::addmax_relu(dg, S2[k], g));    // max(2d, 2h+1, 2v+1, 0)
+                    const uint32_t s2 = A::store(A::addmax_relu(dg, S2[k], g), C.rmask[k], cmask);    // max(2d, 2h+1, 2v+1, 0)
                     const uint32_t tg = (s2 ^ C.flip) & A::TAG;
                     const uint32_t G2 = A::add(tg * C.kabs + s2, C.c0x);          // 2*(s + (gap ? ge : go)) + 1
                     const uint32_t Hc = s2 & A::NTAG;
@@ -467,12 +480,13 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                         colbase = (W - 1 - w) == 0 ? dbase.x : (W - 1 - w) == 1 ? dbase.y : (W - 1 - w) == 2 ? dbase.z : dbase.w;
                     }
                 }
+                const uint32_t cmask = WIDE ? col_mask(C, t - p, w) : 0xFFFFFFFFu;
                 uint32_t vG = uG[w], vM = uM[w], dg = w == 0 ? S.pH : uH[w - 1];
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
                     const int k = FWD ? j : RPT - 1 - j;
                     const uint32_t g  = A::maxs(S.Gl[k], vG);
-                    const uint32_t s2 = A::wrap(A::addmax_relu(dg, S2[k], g));
+                    const uint32_t s2 = A::store(A::addmax_relu(dg, S2[k], g), C.rmask[k], cmask);
                     const uint32_t tg = FLIP ? (~s2 & A::TAG) : (s2 & A::TAG);
                     const uint32_t G2 = A::add(tg * C.kabs + s2, C.c0x);
                     // clearing the tags: with FLIP = false tg IS the tag pair, and s2 - tg cannot borrow between the halves,
@@ -663,12 +677,13 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
                     for (int k = 0; k < RPT; ++k) dk[k] = base + d8_offset(o, k);
                 }
             }
+            const uint32_t cmask = WIDE ? col_mask(C, b, w) : 0xFFFFFFFFu;
             uint32_t vG = upG, vM = upM, codes = 0;
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 const int k = FWD ? j : RPT - 1 - j;
                 const uint32_t g  = A::maxs(S.Gl[k], vG);
-                const uint32_t s2 = A::wrap(A::addmax_relu(dg, S2[k], g));
+                const uint32_t s2 = A::store(A::addmax_relu(dg, S2[k], g), C.rmask[k], cmask);
                 const uint32_t tg = (s2 ^ C.flip) & A::TAG;
                 const uint32_t G2 = A::add(tg * C.kabs + s2, C.c0x);
                 const uint32_t Hc = s2 & A::NTAG;

@@ -9,13 +9,12 @@ Each rank (one process per GPU, torchrun) aligns its own shard -- candidates are
 data-path collective -- so scaling is weak and `value` is the candidates all ranks finished / the max time.
 
   value        kernel-only realignments/s: inputs staged in HBM before the timed region (age_stage); the K steps are
-               queued back to back (age_run_staged_many) and timed with CUDA events on the library's streams
+               queued back to back (age_run_staged_many) and timed with CUDA events on the library's stream
   e2e          the same metric through the C ABI with HOST buffers (age_submit / age_collect, two steps in flight):
                packing, H2D, kernels, D2H, gather of every step inside the timed region; e2e.sync_value = one blocking
                age_align_batch call per step
   roofline     the dominant kernel (age_sweep_kernel) against the binding roofline, integer SIMD issue on the ALU pipe
-               (peak = the age_int16_peak microbenchmark on this GPU); timed alone (one chunk per step, nothing
-               overlapping) with CUDA events
+               (peak = the age_int16_peak microbenchmark on this GPU); CUDA events around the kernel on the library's stream
   hbm          the secondary roofline of the same kernel: bytes it moves by construction / the same time / measured HBM peak
   extra        C4 (-inv, 20 kb x 4 kb) and C5 (-indel -both, 50 kb x 10 kb) kernel-only throughput
   inproc       a fixed C3-style mixed set (12 length bins, 70 % indel / 30 % tdup, two invocations) through ONE context
@@ -277,23 +276,18 @@ def kernel_leg(eng, arr, n, steps, warmup, barrier, sampler=None):
     return total, int(eng.stats()["launches"] - l0)
 
 
-def serial_sweep_leg(eng, arr, n, steps):
-    """The sweep kernel alone: one chunk per step (AGE_CHUNKS=1), so nothing overlaps it; CUDA events around it.
-    Returns (mean sweep-kernel ms, mean ms of all kernels of a step run serially, sweep bytes of the batch)."""
-    os.environ["AGE_CHUNKS"] = "1"
-    try:
-        eng.stage(arr, n)
+def sweep_kernel_leg(eng, arr, n, steps):
+    """The dominant kernel by itself: one age_run_staged per step, CUDA events around the sweep kernel(s) on the library's
+    stream (age_stats.fill_ms).  Returns (mean sweep-kernel ms, mean ms of all kernels of a step, sweep bytes of the batch)."""
+    eng.stage(arr, n)
+    eng.run_staged()
+    fill = k = 0.0
+    for _ in range(steps):
         eng.run_staged()
-        fill = k = 0.0
-        for _ in range(steps):
-            eng.run_staged()
-            st = eng.stats()
-            fill += st["fill_ms"]; k += st["kernel_ms"]
-        res = eng.fetch(n)
         st = eng.stats()
-    finally:
-        del os.environ["AGE_CHUNKS"]
-    return fill / steps, k / steps, st["sweep_bytes"], res
+        fill += st["fill_ms"]; k += st["kernel_ms"]
+    eng.fetch(n)
+    return fill / steps, k / steps, eng.stats()["sweep_bytes"]
 
 
 def inproc_leg(devices, single_device_results=None):
@@ -429,8 +423,7 @@ def main():
     sync_s = time.perf_counter() - t0
 
     # ---- the dominant kernel alone (roofline) ---------------------------------------------------------------------
-    fill_ms, serial_ms, sweep_bytes, res_serial = serial_sweep_leg(eng, arr, n, min(args.steps, 4))
-    same_serial = all(res_serial[i].score == res[i].score and res_serial[i].n_bp == res[i].n_bp for i in range(n))
+    fill_ms, serial_ms, sweep_bytes = sweep_kernel_leg(eng, arr, n, min(args.steps, 4))
 
     t = torch.tensor([k_ms, e2e_s * 1e3, sync_s * 1e3, fill_ms, serial_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -455,7 +448,7 @@ def main():
                     "api": "age_submit/age_collect, two steps in flight",
                     "sync_value": total_c / (sync_ms / 1e3), "sync_api": "one age_align_batch call per step, no overlap between steps"},
             "gpu_launches": launches,
-            "serial_ms_per_step": serial_ms, "serial_identical": same_serial,
+            "sync_ms_per_step": serial_ms,
         }
         peak = C.c_double(0.0)
         ach_i = ALU_INSTR_PER_CELL_UPDATE * cu / (fill_ms / 1e3) / 1e9
@@ -466,9 +459,8 @@ def main():
             "frac": ach_i / peak.value if have_peak else None, "traffic": traffic, "traffic_unit": "GB of DRAM read+write per launch (ncu capture of round 1, scaled by cell updates)",
             "kernel": "age_sweep_kernel", "kernel_ms": fill_ms, "cell_updates_per_launch": cu, "alu_instr_per_cell_update": ALU_INSTR_PER_CELL_UPDATE,
             "note": "achieved = 3.5 ALU-pipe instructions per cell update (6 forward / 8 reverse per packed pair cell; the FMA-pipe multiply-adds are not "
-                    "counted) x cell updates of one launch / the kernel's CUDA-event time, timed alone (one chunk, nothing overlapping; the event pair "
-                    "also spans the 0.3 ms pack kernel); peak = age_int16_peak microbenchmark on this GPU (independent chains of the same ALU "
-                    "instruction mix on every SM)"}
+                    "counted) x cell updates of one launch / the kernel's CUDA-event time; peak = age_int16_peak microbenchmark on this GPU "
+                    "(independent chains of the same ALU instruction mix on every SM)"}
         line["hbm"] = {"bound": "hbm", "achieved": sweep_bytes / (fill_ms / 1e3) / 1e9, "peak": hbm, "unit": "GB/s", "peak_source": which,
                        "frac": sweep_bytes / (fill_ms / 1e3) / 1e9 / hbm, "bytes_per_cell_update": sweep_bytes / cu,
                        "ncu_dram_bytes_per_cell_update": NCU_DRAM_BYTES_PER_CELL_UPDATE if args.workload == "c2" else None,
