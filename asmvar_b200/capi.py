@@ -106,7 +106,7 @@ class AgeStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged", "age_run_staged_many",
     "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version", "age_int16_peak",
-    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment", "age_plan",
+    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment", "age_plan", "age_reserve",
 ]
 
 _lib = None
@@ -117,11 +117,12 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = Path(os.environ.get("AGE_LIB", LIB_PATH))      # AGE_LIB: another build of the same library (A/B measurements)
+    if not path.exists():
         raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
-    lib = C.CDLL(str(LIB_PATH))
+    lib = C.CDLL(str(path))
     vp = C.c_void_p
     lib.age_create.restype = vp
     lib.age_create.argtypes = [C.POINTER(C.c_int), C.c_int]
@@ -147,6 +148,8 @@ def load() -> C.CDLL:
     lib.age_fetch.argtypes = [vp, C.POINTER(AgeResult), C.c_size_t]
     lib.age_get_stats.restype = C.c_int
     lib.age_get_stats.argtypes = [vp, C.POINTER(AgeStats)]
+    lib.age_reserve.restype = C.c_int
+    lib.age_reserve.argtypes = [vp, C.c_size_t]
     lib.age_plan.restype = C.c_int
     lib.age_plan.argtypes = [C.POINTER(AgeJob), C.c_size_t, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     lib.age_format_alignment.restype = C.c_size_t

@@ -13,6 +13,7 @@
 
 #include <getopt.h>
 #include <sys/time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -154,8 +155,16 @@ void create_ctx()
         stringstream ss(e); string tok;
         while (getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
     }
-    g_ctx = age_create(devs.empty() ? nullptr : devs.data(), (int)devs.size());
+    if (devs.empty()) devs.push_back(0);
+    // CUDA initialises every visible GPU (0.5 s and more on an 8-GPU box): show it only the ones this run uses
+    if (!getenv("CUDA_VISIBLE_DEVICES")) {
+        string vis;
+        for (size_t i = 0; i < devs.size(); ++i) { vis += (i ? "," : "") + to_string(devs[i]); devs[i] = (int)i; }
+        setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
+    }
+    g_ctx = age_create(devs.data(), (int)devs.size());
     if (!g_ctx) g_ctx_error = age_last_error(nullptr);
+    else age_reserve(g_ctx, 0);                    // the scratch arenas, while the FASTA files are still being parsed
     prof("device context ready");
 }
 age_ctx *ctx()
@@ -271,8 +280,8 @@ bool print_chunk(Chunk &ch)
             for (const age_result *r : {r0, r1})
                 if (r && r->status < 0 && !bad[i]) {
                     bad[i] = 1;
-                    note[i] = "[ERROR] alignment of '" + c.s1.name + "' vs '" + c.s2.name + "' is outside the supported range (status " +
-                              to_string(r->status) + "): scores must fit 16 bits, gap penalties must be negative\n";
+                    note[i] = "[ERROR] alignment of '" + c.s1.name + "' vs '" + c.s2.name + "' failed (status " + to_string(r->status) +
+                              (r->status == AGE_ERR_RANGE ? "): |match| and |mismatch| must not exceed 16383\n" : ")\n");
                 }
             if (bad[i]) return;
             const bool ok0 = r0->status == AGE_OK, ok1 = r1 && r1->status == AGE_OK;
@@ -380,8 +389,14 @@ int mode_count(int flag)
     return n;
 }
 
-// candidates per batch: 2.5 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
-const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 5920); }();
+// candidates per batch and device: 2.5 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
+size_t device_count()
+{
+    size_t n = 0;
+    if (const char *e = getenv("AGE_DEVICES")) { stringstream ss(e); string tok; while (getline(ss, tok, ',')) if (!tok.empty()) ++n; }
+    return n ? n : 1;
+}
+const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 5920 * device_count()); }();
 
 // ---------------------------------------------------------------------------------------------------------
 // batch dialect (age_align.cpp)
@@ -708,6 +723,10 @@ int main(int argc, char **argv)
     const int rc = looks_original(argc, argv) ? orig_main(argc, argv) : batch_main(argc, argv);
     if (g_warm.joinable()) g_warm.join();
     prof("main done");
+    // Everything is printed.  Tearing the context down piece by piece (a > 100 GB arena, pinned buffers, the CUDA runtime's
+    // own exit handlers) only delays the exit: the driver reclaims it all with the process.  AGE_CLEAN_EXIT=1 keeps the long way.
+    cout.flush(); cerr.flush(); fflush(stdout); fflush(stderr);
+    if (!getenv("AGE_CLEAN_EXIT")) _exit(rc);
     if (g_ctx) age_destroy(g_ctx);
     prof("context destroyed");
     return rc;

@@ -771,6 +771,24 @@ extern "C" void age_destroy(age_ctx *ctx)
     delete ctx;
 }
 
+extern "C" int age_reserve(age_ctx *ctx, size_t scratch_bytes)
+{
+    if (!ctx) return AGE_ERR_ARG;
+    if (ctx->in_flight) { ctx->err = "age_reserve: batches are in flight"; return AGE_ERR_ARG; }
+    for (Device &dev : ctx->devs) {
+        if (cudaSetDevice(dev.id) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return AGE_ERR_CUDA; }
+        size_t want = scratch_bytes;
+        if (!want) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); want = (size_t)(0.8 * (double)(fr + dev.scratch.cap)); }
+        if (want > dev.scratch.cap) {
+            cudaStreamSynchronize(dev.st);
+            dev.scratch.release();
+            if (cudaMalloc(&dev.scratch.ptr, want) != cudaSuccess) { cudaGetLastError(); ctx->err = "age_reserve: device allocation failed"; return AGE_ERR_CUDA; }
+            dev.scratch.cap = want;
+        }
+    }
+    return 0;
+}
+
 extern "C" const char *age_last_error(const age_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 extern "C" int age_submit(age_ctx *ctx, const age_job *jobs, size_t n)

@@ -124,6 +124,7 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepSmem *sm = reinterpret_cast<SweepSmem *>(smem_raw);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    dstage_init(sm[w].dstage, lane);
     for (;;) {
         int item = 0;
         if (lane == 0) item = atomicAdd(counter, 1);
@@ -152,6 +153,7 @@ age_sweep_long_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *
     __shared__ int prog[MAX_STRIPS_LONG];
     __shared__ int s_item;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    dstage_init(sm[w].dstage, lane);
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);

@@ -66,6 +66,33 @@ template <> struct Ar<true> {
     static __device__ __forceinline__ int hi(uint32_t v) { return (int)v; }
 };
 
+// ---- bulk asynchronous copies (TMA engine, 1-D form) on an mbarrier -------------------------------------------------
+#ifndef AGE_DSTAGE_BULK
+#define AGE_DSTAGE_BULK 1            // 1: the reverse sweep stages its D slots with cp.async.bulk; 0: per-lane cp.async (LDGSTS)
+#endif
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+// `bytes` (a multiple of 16) from global to shared memory; completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 // substitution score (x2) of one half for a special column (Scorer.hh:24-39): codes >= 5 score 0
 __device__ __forceinline__ int subst2(int xc, int yc, int m2, int mm2)
 {
@@ -97,9 +124,23 @@ struct WarpRings {                          // shared memory of one warp
     uint4 out[3][32];                       // boundary rows produced by lane p = 31
 };
 
-struct DStage {                             // reverse main sweep: the D slot of the next step, fetched with cp.async
+// Reverse main sweep: the D slot of the next step, staged in shared memory one step ahead.  A slot is one contiguous piece
+// of the diagonal-major plane (2560 B in the OFF8 format, 4096 B raw): one elected lane issues a single bulk copy per step
+// (cp.async.bulk, the TMA engine) that completes on the buffer's mbarrier; every lane then waits on the barrier's parity.
+struct DStage {
     uint4 d[2][W * 2][32];                  // [step parity][block column x half of rows][lane]  (8 KB per warp)
+    uint64_t bar[2];                        // one mbarrier per buffer
+    uint32_t phase;                         // bit b: the parity buffer b completes next (kept in a register while a pair is swept)
+    uint32_t pad_;
 };
+
+__device__ __forceinline__ void dstage_init(DStage &DS, int lane)
+{
+#if AGE_DSTAGE_BULK
+    if (lane == 0) { mbar_init(&DS.bar[0], 1); mbar_init(&DS.bar[1], 1); DS.phase = 0; mbar_init_fence(); }
+    __syncwarp();
+#endif
+}
 
 struct TraceOut {                           // trace re-sweep outputs (one half of the pair, one kind of trace)
     uint2 *P;                               // 2-bit codes: [slot][lane], 16 bits per block column, 2 bits per row
@@ -243,12 +284,30 @@ __device__ __forceinline__ void stcg16(uint4 *p, uint32_t a, uint32_t b, uint32_
 template <int DIR>
 __device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS, int t)
 {
+#if AGE_DSTAGE_BULK
+    if (t <= C.nsteps && C.lane == 0) {     // (lanes whose rows lie beyond the contig get their part of the slot too: never looked at)
+        const uint32_t bytes = (uint32_t)C.dstep * 16u;
+        mbar_expect_tx(&DS.bar[t & 1], bytes);
+        bulk_g2s(&DS.d[t & 1][0][0], C.D4 + (C.sbase + (size_t)(C.nb + 31 - t)) * C.dstep, bytes, &DS.bar[t & 1]);
+    }
+#else
     if (t <= C.nsteps && C.live) {
         const uint4 *src = C.D4 + (C.sbase + (size_t)(C.nb + 31 - t)) * C.dstep + C.lane;
 #pragma unroll
         for (int i = 0; i < W * 2; ++i) if (i < 5 || C.dfmt == DFMT_RAW) cp_async16(&DS.d[t & 1][i][C.lane], src + i * 32);
     }
     cp_async_commit();
+#endif
+}
+// the D slot of step t has landed (it was fetched during step t-1)
+__device__ __forceinline__ void dstage_wait(DStage &DS, int t, uint32_t &dph)
+{
+#if AGE_DSTAGE_BULK
+    mbar_wait(&DS.bar[t & 1], (dph >> (t & 1)) & 1u);
+    dph ^= 1u << (t & 1);
+#else
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+#endif
 }
 
 // One window (steps t0 .. t1) of one strip of the main sweep in which some lanes are idle in some steps: the first
@@ -256,7 +315,7 @@ __device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS,
 // The windows in between go through sweep_window_steady.
 template <int DIR, int DFMT, bool WIDE>
 __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
-                                                  const int t0, const int t1, uint32_t &best)
+                                                  const int t0, const int t1, uint32_t &best, uint32_t &dph)
 {
     using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
@@ -269,14 +328,14 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
     for (int t = t0; t <= t1; ++t) {
         const uint4 xb = xnext;
         xnext = xload(t + 1 - p);
-        if (!FWD) {                             // D of the next step in flight, D of this step landed (each lane reads its own)
-            dstage_fetch(C, DS, t + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        }
         // ---- values of the row above for the 4 columns of this block -------------------------------------
         uint32_t uH[W], uG[W], uM[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
+        if (!FWD) {                             // D of the next step in flight, D of this step landed (each lane reads its own).
+            dstage_fetch(C, DS, t + 1);         // Behind the shuffles: every lane is through with the buffer that is refilled.
+            dstage_wait(DS, t, dph);
+        }
         if (p == 0) {
             const int e = (t - 1) & 31;
             const uint4 h = R.in[buf][0][e], g = R.in[buf][1][e], m = R.in[buf][2][e];
@@ -388,7 +447,7 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
 // column loop (one copy of the step body without it, one with it).
 template <int DIR, int DFMT, bool FLIP, bool WIDE>
 __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, const int win,
-                                                    const int t0, const int t1, uint32_t &best)
+                                                    const int t0, const int t1, uint32_t &best, uint32_t &dph)
 {
     using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
@@ -416,18 +475,25 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         xnext = __ldg(reinterpret_cast<const uint2 *>(++xp));
         const bool special = spec & 1u;
         spec >>= 1;
-        if (!FWD) {
+        uint32_t uH[W], uG[W], uM[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
+        if (!FWD) {                             // behind the shuffles: every lane is through with the buffer that is refilled
+#if AGE_DSTAGE_BULK
+            if (lane == 0) {                    // step t + 1 <= nb + 1 <= nsteps: always a valid slot in a steady window
+                mbar_expect_tx(&DS.bar[(t + 1) & 1], DSTEP * 16);
+                bulk_g2s(&DS.d[(t + 1) & 1][0][0], dptr - lane, DSTEP * 16, &DS.bar[(t + 1) & 1]);
+            }
+#else
             if (live) {
 #pragma unroll
                 for (int i = 0; i < NPL; ++i) cp_async16(&DS.d[(t + 1) & 1][i][lane], dptr + i * 32);
             }
             cp_async_commit();
+#endif
             dptr -= DSTEP;
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            dstage_wait(DS, t, dph);
         }
-        uint32_t uH[W], uG[W], uM[W];
-#pragma unroll
-        for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
         if (p == 0) {
             const int e = (t - 1) & 31;
             const uint4 h = R.in[buf][0][e], g = R.in[buf][1][e], m = R.in[buf][2][e];
@@ -541,14 +607,14 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
 
 // dispatch on whether the window is steady (all lanes active in all of its steps)
 template <int DIR, int DFMT, bool WIDE>
-__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win, uint32_t &best)
+__device__ __forceinline__ void sweep_window_any(const StripCtx<DIR> &C, LaneState &S, WarpRings &R, DStage &DS, int win, uint32_t &best, uint32_t &dph)
 {
     const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, C.nsteps);
     if (t0 >= 32 && t1 <= C.nb) {
-        if (C.flip == 0) sweep_window_steady<DIR, DFMT, false, WIDE>(C, S, R, DS, win, t0, t1, best);
-        else             sweep_window_steady<DIR, DFMT, true, WIDE>(C, S, R, DS, win, t0, t1, best);
+        if (C.flip == 0) sweep_window_steady<DIR, DFMT, false, WIDE>(C, S, R, DS, win, t0, t1, best, dph);
+        else             sweep_window_steady<DIR, DFMT, true, WIDE>(C, S, R, DS, win, t0, t1, best, dph);
     }
-    else                        sweep_window_edge<DIR, DFMT, WIDE>(C, S, R, DS, win, t0, t1, best);
+    else                        sweep_window_edge<DIR, DFMT, WIDE>(C, S, R, DS, win, t0, t1, best, dph);
 }
 
 // The main sweep of one pair in one direction: checkpoints, tile maxima, all windows of the strips si0, si0 + stride, ...
@@ -560,6 +626,7 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
                                 const int si0 = 0, const int stride = 1, volatile int *prog = nullptr)
 {
     constexpr bool FWD = DIR > 0;
+    uint32_t dph = FWD ? 0u : DS.phase;          // parities of the D staging barriers, in a register while the pair is swept
     for (int si = si0; si < T.nstrips; si += stride) {
         const int s = FWD ? si : T.nstrips - 1 - si;
         StripCtx<DIR> C;
@@ -583,8 +650,8 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
             __syncwarp();
             if (!C.first && win + 1 < C.nwin) { wait_blocks(win + 1); ring_prefetch(C, R, win + 1, (win + 1) & 1); }
             state_save(S, C.ckpt + ((size_t)(s * C.nwin + win) * CKW) * 32 + lane);
-            if (!WIDE && C.dfmt == DFMT_OFF8) sweep_window_any<DIR, DFMT_OFF8, false>(C, S, R, DS, win, best);
-            else                              sweep_window_any<DIR, DFMT_RAW, WIDE>(C, S, R, DS, win, best);
+            if (!WIDE && C.dfmt == DFMT_OFF8) sweep_window_any<DIR, DFMT_OFF8, false>(C, S, R, DS, win, best, dph);
+            else                              sweep_window_any<DIR, DFMT_RAW, WIDE>(C, S, R, DS, win, best, dph);
             if (!FWD) { C.tilemax[(size_t)(s * C.nwin + win) * 32 + lane] = best; best = 0; }
         }
         // the maxima at the last processed column: Fmax[.][len1] (forward) / Rmax[.][1] (reverse)
@@ -594,6 +661,7 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
         if (s == 0 && lane == 0) col[0] = 0;
         __syncwarp();
     }
+    if (!FWD) { if (lane == 0) DS.phase = dph; __syncwarp(); }
 }
 
 // Shared-memory staging of the compact trace re-sweep (one per warp): the per-column values that the fast sweep

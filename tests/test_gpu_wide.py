@@ -70,7 +70,7 @@ def test_mixed_batch_wide_and_packed(eng):
     rng = np.random.default_rng(43)
     jobs = []
     for i in range(24):
-        w, q = sv_pair(rng, int(rng.integers(200, 900)), int(rng.integers(30, 120)), ["del", "ins", "tdup", "inv"][i % 4])
+        w, q = sv_pair(rng, int(rng.integers(420, 900)), int(rng.integers(30, 120)), ["del", "ins", "tdup", "inv"][i % 4])
         sc = (1, -1, -10, -1) if i % 2 else (90, -70, -200, -15)
         flag = FLAGS[i % len(FLAGS)]
         k = len(jobs)
