@@ -124,20 +124,23 @@ struct WarpRings {                          // shared memory of one warp
     uint4 out[3][32];                       // boundary rows produced by lane p = 31
 };
 
-// Reverse main sweep: the D slot of the next step, staged in shared memory one step ahead.  A slot is one contiguous piece
-// of the diagonal-major plane (2560 B in the OFF8 format, 4096 B raw): one elected lane issues a single bulk copy per step
-// (cp.async.bulk, the TMA engine) that completes on the buffer's mbarrier; every lane then waits on the barrier's parity.
+// Reverse main sweep: the D slots of the coming steps, staged in shared memory.  A slot is one contiguous piece of the
+// diagonal-major plane (2560 B in the OFF8 format, 4096 B raw).  Bulk form: one elected lane issues a single bulk copy per
+// step (cp.async.bulk, the TMA engine) that completes on the buffer's mbarrier; every lane then waits on the barrier's
+// parity.  The 8 KB hold three OFF8 slots (fetched two steps ahead: a bulk copy takes longer to land than per-lane
+// cp.async, and one step of lead leaves the warps spinning on the barrier) or two raw ones (one step ahead).
 struct DStage {
-    uint4 d[2][W * 2][32];                  // [step parity][block column x half of rows][lane]  (8 KB per warp)
-    uint64_t bar[2];                        // one mbarrier per buffer
-    uint32_t phase;                         // bit b: the parity buffer b completes next (kept in a register while a pair is swept)
+    uint4 d[512];                           // NB slots of DSTEP uint4 each: [slot][plane][lane]
+    uint64_t bar[3];                        // one mbarrier per slot
+    uint32_t phase;                         // bit b: the parity slot b completes next (kept in a register while a pair is swept)
     uint32_t pad_;
 };
+__host__ __device__ constexpr int dstage_slots(int dfmt) { return (AGE_DSTAGE_BULK && dfmt == DFMT_OFF8) ? 3 : 2; }
 
 __device__ __forceinline__ void dstage_init(DStage &DS, int lane)
 {
 #if AGE_DSTAGE_BULK
-    if (lane == 0) { mbar_init(&DS.bar[0], 1); mbar_init(&DS.bar[1], 1); DS.phase = 0; mbar_init_fence(); }
+    if (lane == 0) { mbar_init(&DS.bar[0], 1); mbar_init(&DS.bar[1], 1); mbar_init(&DS.bar[2], 1); DS.phase = 0; mbar_init_fence(); }
     __syncwarp();
 #endif
 }
@@ -280,31 +283,32 @@ __device__ __forceinline__ void stcg16(uint4 *p, uint32_t a, uint32_t b, uint32_
     asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// D slot of reverse step t (written by the forward sweep in step nb+32-t) -> shared memory, asynchronously
+// D slot of reverse step t (written by the forward sweep in step nb+32-t) -> staging slot t mod NB, asynchronously
 template <int DIR>
 __device__ __forceinline__ void dstage_fetch(const StripCtx<DIR> &C, DStage &DS, int t)
 {
+    const int b = t % dstage_slots(C.dfmt);
 #if AGE_DSTAGE_BULK
     if (t <= C.nsteps && C.lane == 0) {     // (lanes whose rows lie beyond the contig get their part of the slot too: never looked at)
         const uint32_t bytes = (uint32_t)C.dstep * 16u;
-        mbar_expect_tx(&DS.bar[t & 1], bytes);
-        bulk_g2s(&DS.d[t & 1][0][0], C.D4 + (C.sbase + (size_t)(C.nb + 31 - t)) * C.dstep, bytes, &DS.bar[t & 1]);
+        mbar_expect_tx(&DS.bar[b], bytes);
+        bulk_g2s(DS.d + b * C.dstep, C.D4 + (C.sbase + (size_t)(C.nb + 31 - t)) * C.dstep, bytes, &DS.bar[b]);
     }
 #else
     if (t <= C.nsteps && C.live) {
         const uint4 *src = C.D4 + (C.sbase + (size_t)(C.nb + 31 - t)) * C.dstep + C.lane;
 #pragma unroll
-        for (int i = 0; i < W * 2; ++i) if (i < 5 || C.dfmt == DFMT_RAW) cp_async16(&DS.d[t & 1][i][C.lane], src + i * 32);
+        for (int i = 0; i < W * 2; ++i) if (i < 5 || C.dfmt == DFMT_RAW) cp_async16(DS.d + b * C.dstep + i * 32 + C.lane, src + i * 32);
     }
     cp_async_commit();
 #endif
 }
-// the D slot of step t has landed (it was fetched during step t-1)
-__device__ __forceinline__ void dstage_wait(DStage &DS, int t, uint32_t &dph)
+// the D slot of step t (staging slot b) has landed
+__device__ __forceinline__ void dstage_wait(DStage &DS, int b, uint32_t &dph)
 {
 #if AGE_DSTAGE_BULK
-    mbar_wait(&DS.bar[t & 1], (dph >> (t & 1)) & 1u);
-    dph ^= 1u << (t & 1);
+    mbar_wait(&DS.bar[b], (dph >> b) & 1u);
+    dph ^= 1u << b;
 #else
     asm volatile("cp.async.wait_group 1;" ::: "memory");
 #endif
@@ -319,7 +323,7 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
 {
     using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
-    constexpr int DSTEP = 32 * (DFMT == DFMT_OFF8 ? 5 : 2 * W);
+    constexpr int DSTEP = 32 * (DFMT == DFMT_OFF8 ? 5 : 2 * W), NB = dstage_slots(DFMT);
     const int lane = C.lane, p = C.p, nb = C.nb;
     const int buf = win & 1;
     auto xload = [&](int b) { return __ldg(C.xblk + min(max(b, 0), nb + 1)); };
@@ -332,9 +336,10 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
         uint32_t uH[W], uG[W], uM[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
-        if (!FWD) {                             // D of the next step in flight, D of this step landed (each lane reads its own).
-            dstage_fetch(C, DS, t + 1);         // Behind the shuffles: every lane is through with the buffer that is refilled.
-            dstage_wait(DS, t, dph);
+        const uint4 *dcur = DS.d + (t % NB) * DSTEP;
+        if (!FWD) {                             // D of the coming step(s) in flight, D of this step landed (each lane reads its own).
+            dstage_fetch(C, DS, t + NB - 1);    // Behind the shuffles: every lane is through with the slot that is refilled.
+            dstage_wait(DS, t % NB, dph);
         }
         if (p == 0) {
             const int e = (t - 1) & 31;
@@ -348,7 +353,7 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
             uint4 *dst = C.D4 + (C.sbase + (size_t)(t - 1)) * DSTEP + lane;      // forward: the D slot of this step
             if (FWD && C.live && DFMT == DFMT_OFF8) stcg16(dst, S.pM, uM[0], uM[1], uM[2]);
             uint4 dbase = make_uint4(0, 0, 0, 0);
-            if (!FWD && C.live && DFMT == DFMT_OFF8) dbase = DS.d[t & 1][0][lane];
+            if (!FWD && C.live && DFMT == DFMT_OFF8) dbase = dcur[lane];
             const bool special = (xb.z & 0x01010101u) != 0;
 #pragma unroll
             for (int w = 0; w < W; ++w) {
@@ -384,9 +389,9 @@ __device__ __forceinline__ void sweep_window_edge(const StripCtx<DIR> &C, LaneSt
                 uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
                 uint32_t colbase = 0, colbest = 0;
                 if (!FWD && C.live) {
-                    if (DFMT == DFMT_RAW) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                    if (DFMT == DFMT_RAW) { dc0 = dcur[((W - 1 - w) * 2 + 0) * 32 + lane]; dc1 = dcur[((W - 1 - w) * 2 + 1) * 32 + lane]; }
                     else {
-                        dc0 = DS.d[t & 1][1 + (W - 1 - w)][lane];
+                        dc0 = dcur[(1 + (W - 1 - w)) * 32 + lane];
                         colbase = (W - 1 - w) == 0 ? dbase.x : (W - 1 - w) == 1 ? dbase.y : (W - 1 - w) == 2 ? dbase.z : dbase.w;
                     }
                 }
@@ -452,6 +457,7 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
     using A = Ar<WIDE>;
     constexpr bool FWD = DIR > 0;
     constexpr int NPL = DFMT == DFMT_OFF8 ? 5 : 2 * W, DSTEP = 32 * NPL;     // uint4 of D per (lane, step) / per step
+    constexpr int NB = dstage_slots(DFMT);                                    // staging slots; the fetch runs NB - 1 steps ahead
     const int lane = C.lane, p = C.p, nb = C.nb;
     const int buf = win & 1;
     // Column descriptors: only the selectors (.x, .y) are loaded per step, one step ahead.  The per-step "has an N / IUPAC
@@ -466,9 +472,10 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         if (t1 - t0 < 31) spec &= (1u << (t1 - t0 + 1)) - 1u;
     }
     uint2 xnext = __ldg(reinterpret_cast<const uint2 *>(xp));
-    // forward: D slot of step t; reverse: D slot of the step fetched next (t + 1), i.e. forward step nb + 32 - (t + 1)
-    uint4 *dptr = C.D4 + (C.sbase + (size_t)(FWD ? t0 - 1 : nb + 30 - t0)) * DSTEP + lane;
+    // forward: D slot of step t; reverse: D slot of the step fetched next (t + NB - 1), i.e. forward step nb + 32 - (t + NB - 1)
+    uint4 *dptr = C.D4 + (C.sbase + (size_t)(FWD ? t0 - 1 : nb + 32 - NB - t0)) * DSTEP + lane;
     const bool live = C.live;
+    int cb = t0 % NB;                                // staging slot of step t
 
     for (int t = t0; t <= t1; ++t) {
         const uint2 xb = xnext;
@@ -478,21 +485,23 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         uint32_t uH[W], uG[W], uM[W];
 #pragma unroll
         for (int w = 0; w < W; ++w) { uH[w] = shfl_prev<DIR>(S.oH[w]); uG[w] = shfl_prev<DIR>(S.oG[w]); uM[w] = shfl_prev<DIR>(S.oM[w]); }
-        if (!FWD) {                             // behind the shuffles: every lane is through with the buffer that is refilled
+        const uint4 *dcur = DS.d + cb * DSTEP;
+        if (!FWD) {                             // behind the shuffles: every lane is through with the slot that is refilled
+            const int pb = cb == 0 ? NB - 1 : cb - 1;        // slot of step t + NB - 1 (<= nb + 2 <= nsteps: always a valid step here)
 #if AGE_DSTAGE_BULK
-            if (lane == 0) {                    // step t + 1 <= nb + 1 <= nsteps: always a valid slot in a steady window
-                mbar_expect_tx(&DS.bar[(t + 1) & 1], DSTEP * 16);
-                bulk_g2s(&DS.d[(t + 1) & 1][0][0], dptr - lane, DSTEP * 16, &DS.bar[(t + 1) & 1]);
+            if (lane == 0) {
+                mbar_expect_tx(&DS.bar[pb], DSTEP * 16);
+                bulk_g2s(DS.d + pb * DSTEP, dptr - lane, DSTEP * 16, &DS.bar[pb]);
             }
 #else
             if (live) {
 #pragma unroll
-                for (int i = 0; i < NPL; ++i) cp_async16(&DS.d[(t + 1) & 1][i][lane], dptr + i * 32);
+                for (int i = 0; i < NPL; ++i) cp_async16(DS.d + pb * DSTEP + i * 32 + lane, dptr + i * 32);
             }
             cp_async_commit();
 #endif
             dptr -= DSTEP;
-            dstage_wait(DS, t, dph);
+            dstage_wait(DS, cb, dph);
         }
         if (p == 0) {
             const int e = (t - 1) & 31;
@@ -503,7 +512,7 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         }
         if (FWD && live && DFMT == DFMT_OFF8) stcg16(dptr, S.pM, uM[0], uM[1], uM[2]);       // entry k = 0 of the four columns
         uint4 dbase = make_uint4(0, 0, 0, 0);
-        if (!FWD && live && DFMT == DFMT_OFF8) dbase = DS.d[t & 1][0][lane];
+        if (!FWD && live && DFMT == DFMT_OFF8) dbase = dcur[lane];
         auto columns = [&](auto sp) {
             constexpr bool SPECIAL = decltype(sp)::value;
             // the per-column N / IUPAC codes are only fetched on the rare path: even a predicated-off load in the common
@@ -540,9 +549,9 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
                 uint4 dc0 = make_uint4(0, 0, 0, 0), dc1 = dc0;
                 uint32_t colbase = 0, colbest = 0;
                 if (!FWD && live) {
-                    if (DFMT == DFMT_RAW) { dc0 = DS.d[t & 1][(W - 1 - w) * 2 + 0][lane]; dc1 = DS.d[t & 1][(W - 1 - w) * 2 + 1][lane]; }
+                    if (DFMT == DFMT_RAW) { dc0 = dcur[((W - 1 - w) * 2 + 0) * 32 + lane]; dc1 = dcur[((W - 1 - w) * 2 + 1) * 32 + lane]; }
                     else {
-                        dc0 = DS.d[t & 1][1 + (W - 1 - w)][lane];
+                        dc0 = dcur[(1 + (W - 1 - w)) * 32 + lane];
                         colbase = (W - 1 - w) == 0 ? dbase.x : (W - 1 - w) == 1 ? dbase.y : (W - 1 - w) == 2 ? dbase.z : dbase.w;
                     }
                 }
@@ -580,6 +589,7 @@ __device__ __forceinline__ void sweep_window_steady(const StripCtx<DIR> &C, Lane
         if (!special) columns(std::false_type{});
         else                           columns(std::true_type{});
         if (FWD) dptr += DSTEP;
+        cb = cb + 1 == NB ? 0 : cb + 1;
         S.pH = uH[W - 1]; S.pM = uM[W - 1];
         const int b = t - p;
         if (FWD && C.Dtail4) C.Dtail4[b - 1] = make_uint4(S.oM[0], S.oM[1], S.oM[2], S.oM[3]);
@@ -644,7 +654,7 @@ __device__ void sweep_pair_fast(const PairTask &T, WarpRings &R, DStage &DS, con
         if (C.first) ring_fill_border(R, lane, C.gborder);
         else { wait_blocks(0); ring_prefetch(C, R, 0, 0); }
         uint32_t best = 0;
-        if (!FWD) dstage_fetch(C, DS, 1);
+        if (!FWD) for (int t = 1; t < dstage_slots(C.dfmt); ++t) dstage_fetch(C, DS, t);
         for (int win = 0; win < C.nwin; ++win) {
             cp_async_wait_all();
             __syncwarp();

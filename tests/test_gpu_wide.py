@@ -89,16 +89,18 @@ def test_mixed_batch_wide_and_packed(eng):
 
 
 def long_pair(rng, len1, len2, mode):
+    """a window and a contig of about len2 bases around one event in the middle of the window"""
     w = rand_seq(rng, len1, "ACGT")
     half = len2 // 2
-    a = int(rng.integers(half + 10, len1 - 2 * half - 500))
-    L = int(rng.integers(200, len1 - a - half - 10))
+    L = int(rng.integers(150, 400))
+    a = len1 // 2 - L // 2
+    hl, hr = min(half, a), min(half, len1 - a - L)
     if mode == "del":
-        q = w[a - half:a] + w[a + L:a + L + half]
+        q = w[a - hl:a] + w[a + L:a + L + hr]
     elif mode == "tdup":
-        q = w[a + L - half:a + L] + w[a:a + half]
+        q = w[a + L - min(hl, L):a + L] + w[a:a + hr]
     else:
-        q = w[a - half:a] + U.revcom_str(w[a:a + half].decode()).encode()
+        q = w[a - hl:a] + U.revcom_str(w[a:a + hr].decode()).encode()
     return w, mutate(rng, q, 0.01, 0.001)
 
 
