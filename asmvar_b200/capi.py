@@ -43,6 +43,34 @@ class AgeBlock(C.Structure):
     _fields_ = [("start1", C.c_int32), ("start2", C.c_int32), ("length", C.c_int32)]
 
 
+class AgeCounts(C.Structure):
+    _fields_ = [("n_aligned", C.c_int32 * 2), ("n_identic", C.c_int32 * 2), ("n_gap", C.c_int32 * 2),
+                ("homo_at1", C.c_int32 * 3), ("homo_at2", C.c_int32 * 3),
+                ("homo_out1", C.c_int32), ("homo_out2", C.c_int32), ("homo_in1", C.c_int32), ("homo_in2", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {"n_aligned": list(self.n_aligned), "n_identic": list(self.n_identic), "n_gap": list(self.n_gap),
+                "homo_at1": list(self.homo_at1), "homo_at2": list(self.homo_at2),
+                "homo_out": [self.homo_out1, self.homo_out2], "homo_in": [self.homo_in1, self.homo_in2]}
+
+
+class AgeVariant(C.Structure):
+    _fields_ = [("n_identity", C.c_int32), ("identity", (C.c_int32 * 2) * 3), ("strand", C.c_int32), ("good_align", C.c_int32),
+                ("n_frag", C.c_int32), ("frag", (C.c_int32 * 4) * 2),
+                ("ci_start1", C.c_int32 * 2), ("ci_end1", C.c_int32 * 2), ("ci_start2", C.c_int32 * 2), ("ci_end2", C.c_int32 * 2),
+                ("homo_run", C.c_int32), ("has_variant", C.c_int32), ("type", C.c_int32), ("tlen", C.c_int32), ("qlen", C.c_int32),
+                ("target_start", C.c_int64), ("target_end", C.c_int64), ("query_start", C.c_int64), ("query_end", C.c_int64),
+                ("cipos", C.c_int32 * 2), ("ciend", C.c_int32 * 2)]
+
+    def as_dict(self) -> dict:
+        return {"identity": [list(self.identity[i]) for i in range(self.n_identity)], "strand": chr(self.strand), "good_align": bool(self.good_align),
+                "frag": [list(self.frag[i]) for i in range(self.n_frag)],
+                "ci_start1": list(self.ci_start1), "ci_end1": list(self.ci_end1), "ci_start2": list(self.ci_start2), "ci_end2": list(self.ci_end2),
+                "homo_run": self.homo_run, "has_variant": bool(self.has_variant), "type": self.type, "tlen": self.tlen, "qlen": self.qlen,
+                "target": [self.target_start, self.target_end], "query": [self.query_start, self.query_end],
+                "cipos": list(self.cipos), "ciend": list(self.ciend)}
+
+
 class AgeResult(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("detail", C.c_int32), ("score", C.c_int32), ("flag", C.c_int32), ("used_aux", C.c_int32),
@@ -53,6 +81,7 @@ class AgeResult(C.Structure):
         ("n_alt_left", C.c_int32), ("n_alt_right", C.c_int32),
         ("left", C.POINTER(AgeBlock)), ("right", C.POINTER(AgeBlock)),
         ("alt_left", C.POINTER(AgeBlock)), ("alt_right", C.POINTER(AgeBlock)),
+        ("counts", AgeCounts),
     ]
 
     def bpoints(self):
@@ -72,6 +101,7 @@ class AgeResult(C.Structure):
             "left": self.blocks("left"), "right": self.blocks("right"),
             "alt_left": self.blocks("alt_left") if self.alt_index >= 1 else [],
             "alt_right": self.blocks("alt_right") if self.alt_index >= 1 else [],
+            "counts": self.counts.as_dict(),
         }
 
 
@@ -106,7 +136,7 @@ class AgeStats(C.Structure):
 EXPORTED_SYMBOLS = [
     "age_create", "age_destroy", "age_last_error", "age_align_batch", "age_stage", "age_run_staged", "age_run_staged_many",
     "age_fetch", "age_get_stats", "age_format_alignment", "age_revcom", "age_subst_score", "age_version", "age_int16_peak",
-    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment", "age_plan", "age_reserve",
+    "age_submit", "age_collect", "age_in_flight", "age_describe_alignment", "age_plan", "age_reserve", "age_recall_variant", "age_variant_type_name", "age_format_vcf_age",
 ]
 
 _lib = None
@@ -148,6 +178,12 @@ def load() -> C.CDLL:
     lib.age_fetch.argtypes = [vp, C.POINTER(AgeResult), C.c_size_t]
     lib.age_get_stats.restype = C.c_int
     lib.age_get_stats.argtypes = [vp, C.POINTER(AgeStats)]
+    lib.age_recall_variant.restype = C.c_int
+    lib.age_recall_variant.argtypes = [C.POINTER(AgeSeqView), C.POINTER(AgeSeqView), C.POINTER(AgeResult), C.POINTER(AgeVariant)]
+    lib.age_variant_type_name.restype = C.c_char_p
+    lib.age_variant_type_name.argtypes = [C.c_int]
+    lib.age_format_vcf_age.restype = C.c_size_t
+    lib.age_format_vcf_age.argtypes = [C.POINTER(AgeVariant), C.c_int, C.c_char_p, C.c_size_t]
     lib.age_reserve.restype = C.c_int
     lib.age_reserve.argtypes = [vp, C.c_size_t]
     lib.age_plan.restype = C.c_int
@@ -179,6 +215,21 @@ def format_alignment(s1: AgeSeqView, s2: AgeSeqView, job: AgeJob, res: AgeResult
         buf = C.create_string_buffer(n + 1)
         lib.age_format_alignment(C.byref(s1), C.byref(s2), C.byref(job), C.byref(res), buf, n + 1)
     return buf.raw[:n].decode("latin-1")
+
+
+def recall_variant(s1: AgeSeqView, s2: AgeSeqView, res: AgeResult) -> dict:
+    """age_recall_variant as a dict (None when res holds no alignment detail)"""
+    lib = load()
+    v = AgeVariant()
+    if lib.age_recall_variant(C.byref(s1), C.byref(s2), C.byref(res), C.byref(v)) != 0:
+        return None
+    d = v.as_dict()
+    d["type_name"] = lib.age_variant_type_name(v.type).decode()
+    for good in (0, 1):
+        buf = C.create_string_buffer(160)
+        lib.age_format_vcf_age(C.byref(v), good, buf, 160)
+        d["AGE=F" if not good else "AGE=T"] = buf.value.decode()
+    return d
 
 
 def describe_alignment(s1: AgeSeqView, s2: AgeSeqView, res: AgeResult) -> dict:

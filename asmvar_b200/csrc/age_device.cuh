@@ -84,10 +84,16 @@ struct PairTask {
                                          //    (Ar<true>, age_sweep.cuh): every scoring / length the 16-bit halves cannot hold
 };
 
+// Numbers of the printed alignment (bpoint 0) that the host would otherwise have to rebuild the gapped strings for:
+// what AliFragment::countAligned counts per fragment, and the three "identity at / outside / inside breakpoints" runs of
+// printAlignment (AGEaligner.cpp:308-369) on either sequence, in positions of the sequences as passed (age_counts).
+enum { CALL_ALIGNED = 0, CALL_IDENTIC = 2, CALL_GAP = 4, CALL_AT1 = 6, CALL_AT2 = 9, CALL_OUT1 = 12, CALL_OUT2 = 13, CALL_IN1 = 14, CALL_IN2 = 15, CALL_N = 16 };
+
 struct AlignerOut {
     int32_t status, score, n_bp, alt_index;   // n_bp = -1: score only (the half lost its selection)
     int32_t n_blk[4];                    // left, right, alt_left, alt_right
     int32_t blk_off[4];                  // offsets into the block pool (in blocks)
+    int32_t call[CALL_N];
     int32_t bp[MAX_BP][4];
 };
 

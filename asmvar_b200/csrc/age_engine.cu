@@ -585,6 +585,7 @@ void assemble(const Batch &B, age_result *out, size_t n)
     for (size_t i = 0; i < n; ++i) {
         age_result &r = out[i];
         memset(&r, 0, offsetof(age_result, bp));          // header only: bp rows beyond n_bp are not part of the result
+        memset(&r.counts, 0, sizeof(r.counts));
         r.alt_index = -1; r.n_left = r.n_right = r.n_alt_left = r.n_alt_right = 0;
         r.left = r.right = r.alt_left = r.alt_right = nullptr;
         r.status = B.job_status[i];
@@ -609,6 +610,10 @@ void assemble(const Batch &B, age_result *out, size_t n)
         r.n_left = o.n_blk[0]; r.n_right = o.n_blk[1]; r.n_alt_left = o.n_blk[2]; r.n_alt_right = o.n_blk[3];
         const age_block *b = B.blocks[pick].data();
         r.left = b; r.right = b + r.n_left; r.alt_left = r.right + r.n_right; r.alt_right = r.alt_left + r.n_alt_left;
+        age_counts &c = r.counts;
+        for (int k = 0; k < 2; ++k) { c.n_aligned[k] = o.call[CALL_ALIGNED + k]; c.n_identic[k] = o.call[CALL_IDENTIC + k]; c.n_gap[k] = o.call[CALL_GAP + k]; }
+        for (int k = 0; k < 3; ++k) { c.homo_at1[k] = o.call[CALL_AT1 + k]; c.homo_at2[k] = o.call[CALL_AT2 + k]; }
+        c.homo_out1 = o.call[CALL_OUT1]; c.homo_out2 = o.call[CALL_OUT2]; c.homo_in1 = o.call[CALL_IN1]; c.homo_in2 = o.call[CALL_IN2];
     }
     // Mutual -both partners that did not share a warp (wide jobs) both come back complete: keep the details of the one
     // age_align prints only (the lower index unless the other scores strictly higher, age_align.cpp:273), as the
@@ -622,6 +627,7 @@ void assemble(const Batch &B, age_result *out, size_t n)
         lose.detail = 0; lose.n_bp = 0; lose.alt_index = -1; lose.used_aux = 0;
         lose.n_left = lose.n_right = lose.n_alt_left = lose.n_alt_right = 0;
         lose.left = lose.right = lose.alt_left = lose.alt_right = nullptr;
+        memset(&lose.counts, 0, sizeof(lose.counts));
     }
 }
 

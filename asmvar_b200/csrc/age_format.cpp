@@ -498,7 +498,135 @@ size_t describe_alignment(const age_seqview *v1, const age_seqview *v2, const ag
     return o.n;
 }
 
+// ---- variant re-calling from the excised region -----------------------------------------------------
+// Semantics: AgeAlignment::VarReCall / CallVarInExcise (src/AsmvarDetect/VarUnit.cpp:339-466) on top of the AlignResult
+// that SetAlignResult fills (src/AsmvarDetect/AGEaligner.cpp:179-332).  Everything is derived from the block lists and
+// the numbers the device left in age_result::counts; no gapped string is built.
+int recall_variant(const age_seqview *v1, const age_seqview *v2, const age_result *res, age_variant *out)
+{
+    memset(out, 0, sizeof(*out));
+    out->strand = '.';
+    if (!res || res->status != AGE_OK || !res->detail) return AGE_ERR_ARG;
+    const int flag = res->flag;
+    const age_counts &cn = res->counts;
+    const int step1 = v1->reverse ? -1 : 1, step2 = v2->reverse ? -1 : 1;
+    // coordinates of the fragments (findAlignment, AGEaligner.cpp:686-700): the right fragment of INVL and the left one of
+    // INVR live on the reverse complement of the first sequence, whose header starts at the other end and runs the other way
+    const age_block *bl[2] = {res->left, res->right};
+    const int nb[2] = {res->n_left, res->n_right};
+    Frag fr[2];
+    int side[2], n_frag = 0;
+    for (int k = 0; k < 2; k++) {
+        if (nb[k] <= 0 || !bl[k] || cn.n_aligned[k] <= 0) continue;
+        const bool rc = ((flag & AGE_INVL_FLAG) && k == 1) || ((flag & AGE_INVR_FLAG) && k == 0);
+        const int origin = rc ? v1->start + step1 * (v1->len - 1) : v1->start, dir = rc ? -step1 : step1;
+        const age_block &first = bl[k][0], &last = bl[k][nb[k] - 1];
+        Frag &f = fr[n_frag];
+        f.start1 = origin + dir * (first.start1 - 1);
+        f.end1 = origin + dir * (last.start1 + last.length - 2);
+        f.start2 = v2->start + step2 * (first.start2 - 1);
+        f.end2 = v2->start + step2 * (last.start2 + last.length - 2);
+        side[n_frag++] = k;
+    }
+    out->n_frag = n_frag;
+    long ali = 0, idn = 0;
+    for (int i = 0; i < n_frag; i++) {
+        const Frag &f = fr[i];
+        out->frag[i][0] = f.start1; out->frag[i][1] = f.end1; out->frag[i][2] = f.start2; out->frag[i][3] = f.end2;
+        ali += cn.n_aligned[side[i]]; idn += cn.n_identic[side[i]];
+    }
+    auto pct = [](long n, long of) { return (int)(100.0 * n / of + 0.5); };
+    if (ali > 0) {
+        out->identity[0][0] = (int)idn; out->identity[0][1] = pct(idn, ali); out->n_identity = 1;
+        out->strand = fr[0].start2 > fr[0].end2 ? '-' : '+';
+    }
+    if (n_frag < 2) return 0;
+    for (int i = 0; i < 2; i++) {
+        out->identity[1 + i][0] = cn.n_identic[side[i]];
+        out->identity[1 + i][1] = pct(cn.n_identic[side[i]], cn.n_aligned[side[i]]);
+    }
+    out->n_identity = 3;
+    out->good_align = out->identity[0][1] > 98 && out->identity[1][0] > 30 && out->identity[1][1] > 95 &&
+                      out->identity[2][0] > 30 && out->identity[2][1] > 95;
+
+    // the span the breakpoints can slide over: union of what the three runs allow (SetAlignResult's Boundary())
+    struct Span { bool any = false; int lo = 0, hi = 0; void add(int a, int b) { if (!any) { lo = a; hi = b; any = true; } else { lo = std::min(lo, a); hi = std::max(hi, b); } } };
+    Span s1, e1, s2, e2;
+    const Frag &f = fr[0], &nx = fr[1];
+    int s, e;
+    if (excised_range(flag, v1->reverse != 0, f, nx, s, e, 0, 1)) {                     // at the breakpoints
+        int h = cn.homo_at1[0];
+        if (h > 0) { s1.add(s + step1 * cn.homo_at1[1], s + step1 * (cn.homo_at1[2] - 1)); e1.add(e + step1 * cn.homo_at1[1], e + step1 * (cn.homo_at1[2] - 1)); }
+        s = f.end2 + step2; e = nx.start2; h = cn.homo_at2[0];
+        if (h > 0) { s2.add(s + step2 * cn.homo_at2[1], s + step2 * (cn.homo_at2[2] - 1)); e2.add(e + step2 * cn.homo_at2[1], e + step2 * (cn.homo_at2[2] - 1)); }
+    }
+    if (excised_range(flag, v1->reverse != 0, f, nx, s, e, -1, 1)) {                    // outside
+        int h = cn.homo_out1;
+        if (h > 0) { s1.add(s - step1 * (h - 1), s); e1.add(e, e + step1 * (h - 1)); }
+        s = f.end2; e = nx.start2; h = cn.homo_out2;
+        if (h > 0) { s2.add(s - step2 * (h - 1), s); e2.add(e, e + step2 * (h - 1)); }
+    }
+    if (excised_range(flag, v1->reverse != 0, f, nx, s, e)) {                           // inside
+        int h = cn.homo_in1;
+        if (h > 0) { s1.add(s, s + step1 * (h - 1)); e1.add(e - step1 * (h - 1), e); }
+        s = f.end2 + step2; e = nx.start2 - step2; h = cn.homo_in2;
+        if (h > 0) { s2.add(s, s + step2 * (h - 1)); e2.add(e - step2 * (h - 1), e); }
+    }
+    out->ci_start1[0] = s1.lo; out->ci_start1[1] = s1.hi; out->ci_end1[0] = e1.lo; out->ci_end1[1] = e1.hi;
+    out->ci_start2[0] = s2.lo; out->ci_start2[1] = s2.hi; out->ci_end2[0] = e2.lo; out->ci_end2[1] = e2.hi;
+    out->homo_run = cn.homo_at1[0];
+
+    // The variant in the excised region.  What lies between the fragments on the target (tlen bases) and on the query
+    // (qlen bases) decides the type; events that change the length are reported with the base in front of them (so that a
+    // VCF line needs no extra reference base), same-length substitutions without it.  On the reverse strand the query
+    // coordinates run downwards, so the query start is taken from the right fragment.
+    out->has_variant = 1;
+    const int tlen = nx.start1 - f.end1 - 1, qlen = std::abs(nx.start2 - f.end2) - 1;
+    out->tlen = tlen; out->qlen = qlen;
+    const bool forward = out->strand == '+';
+    if (tlen > 0 && qlen == 0)      out->type = AGE_VAR_DEL;
+    else if (qlen > 0 && tlen == 0) out->type = AGE_VAR_INS;
+    else if (tlen == qlen)          out->type = tlen == 1 ? AGE_VAR_SNP : AGE_VAR_MNP;
+    else                            out->type = AGE_VAR_REPLACEMENT;
+    const int lead = (out->type == AGE_VAR_SNP || out->type == AGE_VAR_MNP) ? 1 : 0;   // no anchor base: start one further, end one earlier
+    out->target_start = f.end1 + lead;
+    out->target_end = out->target_start + tlen - lead;
+    if (out->type == AGE_VAR_DEL) out->query_start = out->query_end = f.end2;
+    else {
+        out->query_start = forward ? f.end2 + lead : nx.start2 + 1;
+        out->query_end = out->query_start + qlen - lead;
+    }
+    out->cipos[0] = out->ci_start1[0] > 0 ? out->ci_start1[0] - (int)out->target_start : 0;
+    out->cipos[1] = out->ci_start1[1] > 0 ? out->ci_start1[1] - (int)out->target_start : 0;
+    out->ciend[0] = out->ci_end1[0] > 0 ? out->ci_end1[0] - (int)out->target_end : 0;
+    out->ciend[1] = out->ci_end1[1] > 0 ? out->ci_end1[1] - (int)out->target_end : 0;
+    return 0;
+}
+
 } // namespace age
+
+extern "C" int age_recall_variant(const age_seqview *s1, const age_seqview *s2, const age_result *res, age_variant *out)
+{
+    if (!s1 || !s2 || !out) return AGE_ERR_ARG;
+    return age::recall_variant(s1, s2, res, out);
+}
+
+extern "C" const char *age_variant_type_name(int type)
+{
+    static const char *names[] = {"", "DEL", "INS", "SNP", "MNP", "REPLACEMENT"};
+    return (type >= 0 && type <= AGE_VAR_REPLACEMENT) ? names[type] : "";
+}
+
+extern "C" size_t age_format_vcf_age(const age_variant *v, int good_realign, char *buf, size_t cap)
+{
+    char tmp[160];
+    int n;
+    if (!v || v->n_identity < 3) n = snprintf(tmp, sizeof tmp, ".");
+    else n = snprintf(tmp, sizeof tmp, "%c,%c,%d,%d,%d,%d,%d,%d", good_realign ? 'T' : 'F', (char)v->strand, v->identity[0][0], v->identity[0][1],
+                      v->identity[1][0], v->identity[1][1], v->identity[2][0], v->identity[2][1]);
+    if (buf && cap) { const size_t m = std::min((size_t)n, cap - 1); memcpy(buf, tmp, m); buf[m] = '\0'; }
+    return (size_t)n;
+}
 
 extern "C" size_t age_format_alignment(const age_seqview *s1, const age_seqview *s2, const age_job *job,
                                        const age_result *res, char *buf, size_t cap)

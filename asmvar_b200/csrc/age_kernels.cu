@@ -459,7 +459,7 @@ age_blocks_kernel(Pass2Params prm)
             __syncwarp();
             for (int i = lane; i < L.n * 4; i += 32) L.bp[i >> 2][i & 3] = O.bp[i >> 2][i & 3];
             __syncwarp();
-            emit_blocks(V, L, O, prm.pool, prm.pool_cap, prm.pool_used, lane);
+            emit_blocks(V, T.flag[h], L, O, prm.pool, prm.pool_cap, prm.pool_used, lane);
         }
     }
 }

@@ -606,9 +606,141 @@ __device__ void enumerate_aligner(const View<WIDE> &V, int flag, BpList &L, Alig
     for (int i = lane; i < L.n * 4; i += 32) O.bp[i >> 2][i & 3] = L.bp[i >> 2][i & 3];
 }
 
+// ---- numbers of the printed alignment (AlignerOut::call) ----------------------------------------------------------------
+__device__ __forceinline__ int nuc_up(char c)               // upper-case nucleotide, 0 for everything Sequence::sameNuc rejects (Sequence.hh:182-188)
+{
+    const int u = (c >= 'a' && c <= 'z') ? c - 32 : c;
+    return (u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'U') ? u : 0;
+}
+__device__ __forceinline__ bool same_nuc_d(char a, char b) { const int x = nuc_up(a); return x != 0 && x == nuc_up(b); }
+__device__ __forceinline__ bool is_gap_d(char c) { return c == ' ' || c == '-'; }           // Sequence.hh:175-180
+__device__ __forceinline__ char complement_d(char c)        // Sequence.hh:138-150
+{
+    switch (c) {
+    case 'a': return 't'; case 'c': return 'g'; case 't': return 'a'; case 'g': return 'c';
+    case 'A': return 'T'; case 'C': return 'G'; case 'T': return 'A'; case 'G': return 'C';
+    case 'u': return 'a'; case 'U': return 'A';
+    default:  return c;
+    }
+}
+struct SeqD {                                               // a sequence as passed (0-based positions; '\0' outside)
+    const char *s; int n;
+    __device__ __forceinline__ char at(int i) const { return (i >= 0 && i < n) ? s[i] : '\0'; }
+};
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// AliFragment::countAligned of one fragment from its diagonal blocks: alignment columns, identical columns, gap columns.
+// rc1: the fragment's first-sequence positions are positions of the reverse complement (right fragment of INVL, left of INVR).
+__device__ void fragment_counts(const Block *blk, int n, const SeqD &q1, const SeqD &q2, bool rc1, int lane, int &n_ali, int &n_id, int &n_gap)
+{
+    int al = 0, id = 0, gp = 0;
+    for (int b = 0; b < n; ++b) {
+        const Block B = blk[b];
+        if (b + 1 < n && lane == 0) {                       // the columns between two blocks pair a base with a gap
+            const int g = (blk[b + 1].start1 - (B.start1 + B.length)) + (blk[b + 1].start2 - (B.start2 + B.length));
+            al += g; gp += g;
+        }
+        for (int i = lane; i < B.length; i += 32) {
+            const char c1 = rc1 ? complement_d(q1.at(q1.n - (B.start1 + i))) : q1.at(B.start1 - 1 + i);
+            const char c2 = q2.at(B.start2 - 1 + i);
+            ++al;
+            id += same_nuc_d(c1, c2) ? 1 : 0;
+            gp += (is_gap_d(c1) || is_gap_d(c2)) ? 1 : 0;
+        }
+    }
+    n_ali = warp_sum(al); n_id = warp_sum(id); n_gap = warp_sum(gp);
+}
+
+// calcIdentity (AGEaligner.cpp:429-447): how far q keeps agreeing with itself shifted by bp2 - bp1, below bp1 and from bp1 on
+__device__ int at_identity_d(const SeqD &q, int bp1, int bp2, int lane, int &left, int &right)
+{
+    left = right = 0;
+    if (bp1 >= bp2) return 0;
+    const int shift = bp2 - bp1;
+    int down = 0, up = 0;
+    for (int i0 = bp1 - 1;; i0 -= 32) {
+        const int i = i0 - lane;
+        const unsigned bad = __ballot_sync(0xFFFFFFFFu, !(i >= 0 && same_nuc_d(q.at(i), q.at(i + shift))));
+        if (bad) { down += __ffs(bad) - 1; break; }
+        down += 32;
+    }
+    for (int i0 = bp1;; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned bad = __ballot_sync(0xFFFFFFFFu, !(i < q.n && same_nuc_d(q.at(i), q.at(i + shift))));
+        if (bad) { up += __ffs(bad) - 1; break; }
+        up += 32;
+    }
+    left = -down; right = up;
+    return up + down;
+}
+
+// Longest m <= n such that the m bases of q from `head` on equal the m bases that end at `tail` (the common core of
+// calcOutsideIdentity / calcInsideIdentity, AGEaligner.cpp:392-427).  32 candidate lengths are checked side by side, the
+// longest first; a lane gives up at its first mismatch.
+__device__ int head_tail_overlap_d(const SeqD &q, int head, int tail, int n, int lane)
+{
+    for (int base = n; base >= 1; base -= 32) {
+        const int m = base - lane;
+        bool ok = m >= 1;
+        for (int k = 0; __any_sync(0xFFFFFFFFu, ok && k < m); ++k)
+            if (ok && k < m) ok = same_nuc_d(q.at(head + k), q.at(tail - m + 1 + k));
+        const unsigned full = __ballot_sync(0xFFFFFFFFu, ok);
+        if (full) return base - (__ffs(full) - 1);
+    }
+    return 0;
+}
+__device__ int outside_identity_d(const SeqD &q, int bp1, int bp2, int lane)
+{
+    return bp1 >= bp2 ? 0 : head_tail_overlap_d(q, bp2, bp1, min(bp1 + 1, q.n - bp2), lane);
+}
+__device__ int inside_identity_d(const SeqD &q, int bp1, int bp2, int lane)
+{
+    return bp1 >= bp2 ? 0 : head_tail_overlap_d(q, bp1, bp2, (bp2 - bp1 + 1) / 2, lane);
+}
+
+// AlignerOut::call of the alignment whose blocks were just written (left: nl blocks, right: nr blocks)
+template <bool WIDE>
+__device__ void alignment_numbers(const View<WIDE> &V, int flag, const Block *left, int nl, const Block *right, int nr, AlignerOut &O, int lane)
+{
+    const SeqD q1{V.T->raw1[V.half], V.len1}, q2{V.T->raw2[V.half], V.len2};
+    int call[CALL_N];
+#pragma unroll
+    for (int i = 0; i < CALL_N; ++i) call[i] = 0;
+    __syncwarp();                                           // the block lists were written by lane 0
+    if (nl > 0) fragment_counts(left, nl, q1, q2, (flag & F_INVR) != 0, lane, call[CALL_ALIGNED], call[CALL_IDENTIC], call[CALL_GAP]);
+    if (nr > 0) fragment_counts(right, nr, q1, q2, (flag & F_INVL) != 0, lane, call[CALL_ALIGNED + 1], call[CALL_IDENTIC + 1], call[CALL_GAP + 1]);
+    if (nl > 0 && nr > 0) {
+        // 0-based positions in the sequences as passed: a position p of the reverse complement is position len1 - p
+        const Block le = left[nl - 1], rs = right[0];
+        const int e1 = le.start1 + le.length - 1, e2 = le.start2 + le.length - 1;
+        const int A = (flag & F_INVR) ? V.len1 - e1 : e1 - 1, B = (flag & F_INVL) ? V.len1 - rs.start1 : rs.start1 - 1;
+        int s, e;                                           // the excised region (getExcisedRange, AGEaligner.cpp:156-177)
+        if (flag & F_INDEL)      { s = A + 1; e = B - 1; }
+        else if (flag & F_TDUP)  { s = B;     e = A; }
+        else if (flag & F_INVL)  { s = A + 1; e = B; }
+        else                     { s = A;     e = B - 1; }
+        call[CALL_AT1] = at_identity_d(q1, s, e + 1, lane, call[CALL_AT1 + 1], call[CALL_AT1 + 2]);
+        call[CALL_OUT1] = outside_identity_d(q1, s - 1, e + 1, lane);
+        call[CALL_IN1] = inside_identity_d(q1, s, e, lane);
+        const int L2 = e2 - 1, R2 = rs.start2 - 1;
+        call[CALL_AT2] = at_identity_d(q2, L2 + 1, R2, lane, call[CALL_AT2 + 1], call[CALL_AT2 + 2]);
+        call[CALL_OUT2] = outside_identity_d(q2, L2, R2, lane);
+        call[CALL_IN2] = inside_identity_d(q2, L2 + 1, R2 - 1, lane);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < CALL_N; ++i) O.call[i] = call[i];
+    }
+}
+
 // K10-K12: the tracebacks of bpoint 0 and of the alternative printAlignment shows (:287-306) into the block pool
 template <bool WIDE>
-__device__ void emit_blocks(const View<WIDE> &V, const BpList &L, AlignerOut &O, Block *pool, int pool_cap, int32_t *pool_used, int lane)
+__device__ void emit_blocks(const View<WIDE> &V, int flag, const BpList &L, AlignerOut &O, Block *pool, int pool_cap, int32_t *pool_used, int lane)
 {
     int alt = -1;
     P2_PROF_T0(pc);
@@ -633,8 +765,9 @@ __device__ void emit_blocks(const View<WIDE> &V, const BpList &L, AlignerOut &O,
             if (off + nl + nr <= pool_cap) {
                 left_blocks(V, L.bp[idx][0], L.bp[idx][1], pool + off, nl, lane);
                 right_blocks(V, L.bp[idx][2], L.bp[idx][3], pool + off + nl, lane);
+                if (which == 0) alignment_numbers(V, flag, pool + off, nl, pool + off + nl, nr, O, lane);
             } else if (lane == 0) O.status = -4;          // pool overflow: host retries with a larger pool
-        }
+        } else if (which == 0 && lane < CALL_N) O.call[lane] = 0;
         if (lane == 0) {
             O.n_blk[2 * which] = nl; O.n_blk[2 * which + 1] = nr;
             O.blk_off[2 * which] = off; O.blk_off[2 * which + 1] = off + nl;

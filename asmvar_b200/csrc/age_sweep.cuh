@@ -67,8 +67,13 @@ template <> struct Ar<true> {
 };
 
 // ---- bulk asynchronous copies (TMA engine, 1-D form) on an mbarrier -------------------------------------------------
+// AGE_DSTAGE_BULK = 1: the reverse sweep stages its D slots with cp.async.bulk (one elected lane, mbarrier); 0: per-lane
+// cp.async (LDGSTS).  Measured on a B200 with the bench batch (round 2, profiles/r2_dstage_bulk_vs_ldgsts.md): sweep kernel
+// 40.8 ms with LDGSTS, 42.9 ms with bulk copies one step ahead, 44.6 ms two steps ahead (three slots) -- the bulk form
+// executes 4 % more instructions (the barrier wait spins where cp.async.wait_group just stalls) and a bulk copy takes
+// longer to land than 32 lanes' own 16-byte copies.  Hence the default.
 #ifndef AGE_DSTAGE_BULK
-#define AGE_DSTAGE_BULK 1            // 1: the reverse sweep stages its D slots with cp.async.bulk; 0: per-lane cp.async (LDGSTS)
+#define AGE_DSTAGE_BULK 0
 #endif
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {

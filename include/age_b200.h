@@ -58,6 +58,19 @@ typedef struct {
 /* A gap-free diagonal run; 1-based positions in seq1 / seq2 (class Block, AGEaligner.hh:128-177). */
 typedef struct { int32_t start1, start2, length; } age_block;
 
+/* Numbers of the printed alignment (bpoint 0), computed on the device from the block lists and the sequences, so that a
+ * caller who wants figures and not text never has to rebuild the gapped strings:
+ *   per fragment (0 = left, 1 = right) what AliFragment::countAligned counts (AGEaligner.hh:203-216): alignment columns,
+ *   identical columns, columns with a gap;
+ *   the runs printAlignment reports as "Identity at / outside / inside breakpoints" (AGEaligner.cpp:308-369, calcIdentity /
+ *   calcOutsideIdentity / calcInsideIdentity :392-447) on the first and on the second sequence: run length, and for the "at"
+ *   runs how far it reaches below (<= 0) and from the breakpoint on (>= 0).  All zero unless there are two fragments. */
+typedef struct {
+    int32_t n_aligned[2], n_identic[2], n_gap[2];
+    int32_t homo_at1[3], homo_at2[3];
+    int32_t homo_out1, homo_out2, homo_in1, homo_in2;
+} age_counts;
+
 /* Everything AGEaligner::score() / printAlignment() need (AGEaligner.cpp:149-154,179-380). */
 typedef struct {
     int32_t status;
@@ -72,6 +85,7 @@ typedef struct {
     int32_t n_left, n_right;            /* findLeftBlocks / findRightBlocks of bpoint 0 (AGEaligner.cpp:752-860) */
     int32_t n_alt_left, n_alt_right;    /* the same for bpoint alt_index */
     const age_block *left, *right, *alt_left, *alt_right;  /* owned by the ctx, valid until the next age_align_batch / age_stage call (age_submit: see there) */
+    age_counts counts;                  /* of the alignment of bpoint 0 (left / right) */
 } age_result;
 
 /* A Sequence header: name, 1-based start coordinate and orientation (Sequence.hh:22-31). */
@@ -170,6 +184,41 @@ typedef struct {
 } age_align_info;
 size_t age_describe_alignment(const age_seqview *s1, const age_seqview *s2, const age_result *res,
                               age_align_info *info, char *text, size_t cap);
+
+/* Replaces: AgeAlignment::VarReCall / CallVarInExcise of AsmvarDetect (src/AsmvarDetect/VarUnit.cpp:339-466) and the AGE=
+ * sample field of the VCF (Variant.cpp:1259-1270) -- SURVEY 8(f)3.  From one age_result (its block lists and the counts the
+ * device computed) and the headers of the two sequences, without going through text:
+ *   identity      AlignResult::_identity: (identical bases, percent) of the whole alignment, then of either fragment when
+ *                 there are two (AGEaligner.cpp:213-246 of the AsmvarDetect flavour)
+ *   good_align    the good-alignment rule: average identity > 98 %, each flank > 30 identical bases and > 95 % (VarUnit.cpp:347-353)
+ *   frag          the MapData of the fragments: start1, end1, start2, end2 in sequence coordinates
+ *   ci_*          AlignResult::_ci_start1 ... _ci_end2: the span the breakpoints can slide over, from the three runs
+ *   has_variant   two fragments, hence an excised region; then type / target_* / query_* / tlen / qlen are the variant
+ *                 CallVarInExcise reports for it and cipos / ciend its confidence intervals relative to target_start / target_end
+ * Returns 0, or AGE_ERR_ARG when res holds no alignment detail. */
+#define AGE_VAR_NONE        0
+#define AGE_VAR_DEL         1
+#define AGE_VAR_INS         2
+#define AGE_VAR_SNP         3
+#define AGE_VAR_MNP         4
+#define AGE_VAR_REPLACEMENT 5
+typedef struct {
+    int32_t n_identity, identity[3][2];
+    int32_t strand;                     /* '+', '-' or '.' */
+    int32_t good_align;
+    int32_t n_frag, frag[2][4];
+    int32_t ci_start1[2], ci_end1[2], ci_start2[2], ci_end2[2];
+    int32_t homo_run;                   /* AlignResult::_homo_run_atbp1 */
+    int32_t has_variant, type, tlen, qlen;
+    int64_t target_start, target_end, query_start, query_end;
+    int32_t cipos[2], ciend[2];
+} age_variant;
+int age_recall_variant(const age_seqview *s1, const age_seqview *s2, const age_result *res, age_variant *out);
+const char *age_variant_type_name(int type);       /* "DEL", "INS", "SNP", "MNP", "REPLACEMENT" ("" for AGE_VAR_NONE) */
+/* The value of the AGE= field: "T,+,<n>,<pct>,<n>,<pct>,<n>,<pct>" -- T/F = good_realign (the caller's isGoodReAlign: good_align
+ * and a mis-mapping probability < 0.01, VarUnit.cpp:367), or "." when there is nothing to report (fewer than three
+ * identity entries).  Returns the length needed. */
+size_t age_format_vcf_age(const age_variant *v, int good_realign, char *buf, size_t cap);
 
 /* Replaces: Sequence::revcom() string part (Sequence.hh:195-197) and Scorer lookup (Scorer.hh:24-39). */
 void age_revcom(const char *in, int32_t n, char *out);

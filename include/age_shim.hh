@@ -140,6 +140,17 @@ public:
         os.write(buf.data(), (std::streamsize)n);
     }
     const age_result &result() const { return _res; }                         // breakpoints and blocks, without re-parsing text
+    // The variant in the excised region and the figures around it (age_recall_variant: AgeAlignment::VarReCall /
+    // CallVarInExcise, src/AsmvarDetect/VarUnit.cpp:339-466), from the block lists and the counts the device computed.
+    // false where the reference's AlignResult would be empty: nothing aligned, or the auxiliary INVR aligner printed.
+    bool recall(age_variant &v) const {
+        if (!_aligned || _res.used_aux) return false;
+        const age_result r = owned_result();
+        const age_seqview v1 = view1(), v2 = view2();
+        return age_recall_variant(&v1, &v2, &r, &v) == 0;
+    }
+    const std::string &name1() const { return _s1.name(); }
+    const std::string &name2() const { return _s2.name(); }
 
     // src/AsmvarDetect/AGEaligner.cpp:179-332.  As there: when the auxiliary INVR aligner of -inv scored higher, its
     // record is printed and the AlignResult keeps its defaults.

@@ -12,6 +12,7 @@
 
 #include "age_shim.hh"
 
+#include <algorithm>
 #include <cstdlib>
 #include <iostream>
 #include <memory>
@@ -140,6 +141,7 @@ public:
             if (res1) pick = aligner1_.get();
             else { std::cerr << "No alignment made.\n"; isalign_ = false; }
         }
+        picked_ = pick;
         if (pick) {
             pick->SetAlignResult(os);
             alignResult_ = pick->align_result();
@@ -156,82 +158,49 @@ public:
     std::pair<int, int> cipos() { return alignResult_._ci_start1; }
     std::pair<int, int> ciend() { return alignResult_._ci_end1; }
 
-    std::vector<VarUnit> VarReCall() {            // VarUnit.cpp:339-397
-        const double MISMAP_VALE = 0.01;
+    // VarUnit.cpp:339-466 (VarReCall + CallVarInExcise): at most one variant, the one in the excised region between the two
+    // fragments.  The classification, its coordinates, the confidence intervals and the good-alignment rule come from
+    // age_recall_variant (computed from the block lists; the gapped strings are not consulted).
+    std::vector<VarUnit> VarReCall() {
         std::vector<VarUnit> vus;
-        if (!isalign_) return vus;
-        const AlignResult &a = alignResult_;
-        isgoodAlign_ = a._identity.size() >= 3 && a._identity[0].second > 98 && a._identity[1].first > 30 && a._identity[1].second > 95 &&
-                       a._identity[2].first > 30 && a._identity[2].second > 95;
-        if (a._map.empty()) return vus;           // the reference reads _map[0] here (undefined when the aux aligner printed)
-        std::pair<MapData, MapData> pre_map = a._map[0];
-        for (size_t i = 1; i < a._map.size(); ++i) {
-            std::pair<MapData, MapData> cur = a._map[i];
-            VarUnit var = CallVarInExcise(pre_map, cur, a._strand);
-            var.isSuccessAlign = true;
-            var.isGoodReAlign = isgoodAlign() && (var.mismap < MISMAP_VALE);
-            var.homoRun = HomoRun();
-            var.cipos.first = (cipos().first > 0) ? cipos().first - (int)var.target.start : 0;
-            var.cipos.second = (cipos().second > 0) ? cipos().second - (int)var.target.start : 0;
-            var.ciend.first = (ciend().first > 0) ? ciend().first - (int)var.target.end : 0;
-            var.ciend.second = (ciend().second > 0) ? ciend().second - (int)var.target.end : 0;
-            var.identity = a._identity;
-            vus.push_back(var);
-            pre_map = cur;
-        }
+        age_variant v;
+        if (!isalign_ || !picked_ || !picked_->recall(v)) return vus;
+        isgoodAlign_ = v.good_align != 0;
+        if (!v.has_variant) return vus;
+        if (v.tlen < 0) std::cerr << "[WARNING] It'll cause bug below!\n";
+        VarUnit var;
+        var.type = age_variant_type_name(v.type);
+        var.strand = (char)v.strand;
+        var.score = vu_.score; var.mismap = vu_.mismap;           // of the alignment the candidate came from
+        var.target.id = picked_->name1(); var.query.id = picked_->name2();
+        var.target.start = (long)v.target_start; var.target.end = (long)v.target_end;
+        var.query.start = (long)v.query_start; var.query.end = (long)v.query_end;
+        var.isSuccessAlign = true;
+        var.isGoodReAlign = isgoodAlign_ && var.mismap < 0.01;    // mis-mapping probability of the original alignment
+        var.homoRun = v.homo_run;
+        var.cipos = std::make_pair((int)v.cipos[0], (int)v.cipos[1]);
+        var.ciend = std::make_pair((int)v.ciend[0], (int)v.ciend[1]);
+        for (int i = 0; i < v.n_identity; ++i) var.identity.push_back(std::make_pair((int)v.identity[i][0], (int)v.identity[i][1]));
+        vus.push_back(var);
         return vus;
     }
 
 private:
-    VarUnit CallVarInExcise(std::pair<MapData, MapData> &lf, std::pair<MapData, MapData> &rt, char strand) {   // VarUnit.cpp:399-466
-        if (lf.first._id != rt.first._id || lf.second._id != rt.second._id) {
-            std::cerr << "[BUG] The id is not match!!\n" << lf.first._id << ", " << rt.first._id << "; " << lf.second._id << ", " << rt.second._id << "\n";
-            exit(1);
-        }
-        const int qlen = abs(rt.second._start - lf.second._end) - 1;
-        const int tlen = rt.first._start - lf.first._end - 1;
-        if (tlen < 0) std::cerr << "[WARNING] It'll cause bug below!\n";
-        VarUnit vu;
-        vu.strand = strand;
-        vu.score = vu_.score; vu.mismap = vu_.mismap;
-        vu.target.id = lf.first._id; vu.query.id = lf.second._id;
-        if (tlen > 0 && qlen == 0) {
-            vu.type = "DEL";
-            vu.target.start = lf.first._end; vu.target.end = vu.target.start + tlen;
-            vu.query.start = lf.second._end; vu.query.end = vu.query.start;
-        } else if (qlen > 0 && tlen == 0) {
-            vu.type = "INS";
-            vu.target.start = lf.first._end; vu.target.end = vu.target.start;
-            vu.query.start = (strand == '+') ? lf.second._end : rt.second._start + 1;
-            vu.query.end = vu.query.start + qlen;
-        } else if (tlen == qlen) {
-            vu.type = (tlen == 1) ? "SNP" : "MNP";
-            vu.target.start = lf.first._end + 1; vu.target.end = vu.target.start + tlen - 1;
-            vu.query.start = (strand == '+') ? lf.second._end + 1 : rt.second._start + 1;
-            vu.query.end = vu.query.start + qlen - 1;
-        } else {
-            vu.type = "REPLACEMENT";
-            vu.target.start = lf.first._end; vu.target.end = vu.target.start + tlen;
-            vu.query.start = (strand == '+') ? lf.second._end : rt.second._start + 1;
-            vu.query.end = vu.query.start + qlen;
-        }
-        return vu;
+    // VarUnit.cpp:585-603: widen both windows by the flank, inside the records
+    void ExtendVU(long int tarFaSize, long int qryFaSize, int flank) {
+        auto widen = [flank](Region &r, long int size) { r.start = std::max<long int>(1, r.start - flank); r.end = std::min<long int>(size, r.end + flank); };
+        widen(vu_.target, tarFaSize);
+        widen(vu_.query, qryFaSize);
     }
-    void ExtendVU(long int tarFaSize, long int qryFaSize, int extandFlankSzie) {       // VarUnit.cpp:585-603
-        vu_.target.start -= extandFlankSzie; vu_.target.end += extandFlankSzie;
-        vu_.query.start -= extandFlankSzie; vu_.query.end += extandFlankSzie;
-        if (vu_.target.start < 1) vu_.target.start = 1;
-        if (vu_.target.end > tarFaSize) vu_.target.end = tarFaSize;
-        if (vu_.query.start < 1) vu_.query.start = 1;
-        if (vu_.query.end > qryFaSize) vu_.query.end = qryFaSize;
-    }
-    static bool IsHugeMemory(long int n, long int m) { return ((((long double)(5 * n * m)) / 1000000000.0 + 0.5) > 10.0); }   // VarUnit.cpp:605-609
+    // VarUnit.cpp:605-609: the reference's matrices take 5 bytes per cell; windows beyond ~10 GB (9.5 GB after its rounding) are skipped
+    static bool IsHugeMemory(long int n, long int m) { return 5.0L * (long double)n * (long double)m > 9.5e9L; }
 
     VarUnit vu_, rvu_;
     AgeOption para_;
     AlignResult alignResult_;
     bool isInit_, isalign_, isgoodAlign_, huge_;
     int flag_ = 0, first_job_ = 0;
+    AGEaligner *picked_ = nullptr;
     std::unique_ptr<Sequence> tar_, qry_, qryClone_;
     std::unique_ptr<AGEaligner> aligner1_, aligner2_;
 };

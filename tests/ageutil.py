@@ -111,6 +111,97 @@ def summary_to_result(d: dict):
     return r, keep
 
 
+# ---- age_counts by the definitions (what the device computes from the block lists; tests/test_recall.py) ---------------
+def _same(a, b):
+    a, b = a.upper(), b.upper()
+    return a == b and a in "ACGTU"
+
+
+def _ch(s, i):
+    return s[i] if 0 <= i < len(s) else "\0"
+
+
+def run_at(s, bp1, bp2):
+    """calcIdentity (AGEaligner.cpp:429-447): (run, left extent <= 0, right extent >= 0)"""
+    if bp1 >= bp2:
+        return [0, 0, 0]
+    d, down, up = bp2 - bp1, 0, 0
+    i = bp1 - 1
+    while i >= 0 and _same(_ch(s, i), _ch(s, i + d)):
+        down += 1; i -= 1
+    i = bp1
+    while i < len(s) and _same(_ch(s, i), _ch(s, i + d)):
+        up += 1; i += 1
+    return [up + down, -down, up]
+
+
+def run_outside(s, bp1, bp2):
+    if bp1 >= bp2:
+        return 0
+    for m in range(min(bp1 + 1, len(s) - bp2), 0, -1):
+        if all(_same(_ch(s, bp1 - m + 1 + k), _ch(s, bp2 + k)) for k in range(m)):
+            return m
+    return 0
+
+
+def run_inside(s, bp1, bp2):
+    if bp1 >= bp2:
+        return 0
+    for m in range((bp2 - bp1 + 1) // 2, 0, -1):
+        if all(_same(_ch(s, bp1 + k), _ch(s, bp2 - m + 1 + k)) for k in range(m)):
+            return m
+    return 0
+
+
+def counts_by_definition(seq1: str, seq2: str, summary: dict) -> dict:
+    """age_counts of a result summary, in plain Python: columns of the two fragments from their diagonal blocks, and the
+    three runs around the excised region in positions of the sequences as passed."""
+    flag, len1 = summary["flag"], len(seq1)
+    rc = revcom_str(seq1)
+    out = {"n_aligned": [0, 0], "n_identic": [0, 0], "n_gap": [0, 0], "homo_at1": [0, 0, 0], "homo_at2": [0, 0, 0], "homo_out": [0, 0], "homo_in": [0, 0]}
+    for k, name in enumerate(("left", "right")):
+        bl = summary[name]
+        on_rc = (flag & capi.INVL_FLAG and k == 1) or (flag & capi.INVR_FLAG and k == 0)
+        q1 = rc if on_rc else seq1
+        for i, (s1, s2, n) in enumerate(bl):
+            if i + 1 < len(bl):
+                g = (bl[i + 1][0] - (s1 + n)) + (bl[i + 1][1] - (s2 + n))
+                out["n_aligned"][k] += g; out["n_gap"][k] += g
+            for j in range(n):
+                a, b = q1[s1 - 1 + j], seq2[s2 - 1 + j]
+                out["n_aligned"][k] += 1
+                out["n_identic"][k] += int(_same(a, b))
+                out["n_gap"][k] += int(a in " -" or b in " -")
+    if summary["left"] and summary["right"]:
+        le, rs = summary["left"][-1], summary["right"][0]
+        e1, e2 = le[0] + le[2] - 1, le[1] + le[2] - 1
+        A = len1 - e1 if flag & capi.INVR_FLAG else e1 - 1
+        B = len1 - rs[0] if flag & capi.INVL_FLAG else rs[0] - 1
+        if flag & capi.INDEL_FLAG:
+            s, e = A + 1, B - 1
+        elif flag & capi.TDUPLICATION_FLAG:
+            s, e = B, A
+        elif flag & capi.INVL_FLAG:
+            s, e = A + 1, B
+        else:
+            s, e = A, B - 1
+        L2, R2 = e2 - 1, rs[1] - 1
+        out["homo_at1"] = run_at(seq1, s, e + 1); out["homo_at2"] = run_at(seq2, L2 + 1, R2)
+        out["homo_out"] = [run_outside(seq1, s - 1, e + 1), run_outside(seq2, L2, R2)]
+        out["homo_in"] = [run_inside(seq1, s, e), run_inside(seq2, L2 + 1, R2 - 1)]
+    return out
+
+
+def set_counts(r, c: dict):
+    """fill capi.AgeResult.counts from a counts dict"""
+    for k in range(2):
+        r.counts.n_aligned[k], r.counts.n_identic[k], r.counts.n_gap[k] = c["n_aligned"][k], c["n_identic"][k], c["n_gap"][k]
+    for k in range(3):
+        r.counts.homo_at1[k], r.counts.homo_at2[k] = c["homo_at1"][k], c["homo_at2"][k]
+    r.counts.homo_out1, r.counts.homo_out2 = c["homo_out"]
+    r.counts.homo_in1, r.counts.homo_in2 = c["homo_in"]
+
+
 def make_job(seq1: bytes, seq2: bytes, flag, match, mismatch, go, ge):
     j = capi.AgeJob()
     j.seq1, j.len1, j.seq2, j.len2 = seq1, len(seq1), seq2, len(seq2)
