@@ -172,19 +172,28 @@ age_sweep_long_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *
     }
 }
 
-// Warps that share one pair in the sweep of a sub-batch: one warp per pair fills the GPU from ~sms * 16 pairs on; below
-// that each pair is shared among up to 16 warps (age_sweep_long_kernel).
+// Warps that share one pair in the sweep of a sub-batch.  From sms * 16 pairs on, one warp per pair fills the GPU (the
+// persistent kernel).  Below that each pair is shared by nw = 2 .. 16 warps of one CTA (age_sweep_long_kernel, 16 / nw CTAs
+// per SM): the nw is taken that keeps most of the SMs' warp slots busy -- pairs in flight x nw over the slots of the waves
+// they need, times the share of a pair's strip rounds that all nw warps work in; ties go to the smaller nw, whose pipeline
+// has fewer fill and drain steps.
 int sweep_warps_per_pair(int n_pairs, int max_strips)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int nw = 1;
     const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;   // test knob: 1 = one warp per pair, 2..16 = pipelined
-    while (nw < 16 && nw * 2 <= max_strips && n_pairs * nw * 2 <= sms * 16) nw *= 2;
-    if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) nw = force_nw;
-    if (max_strips > MAX_STRIPS_LONG) nw = 1;
-    return nw;
+    if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) return max_strips > MAX_STRIPS_LONG ? 1 : force_nw;
+    if (n_pairs <= 0 || n_pairs >= sms * 16 || max_strips > MAX_STRIPS_LONG) return 1;
+    int best = 1;
+    double best_score = 0;
+    for (int nw = 1; nw <= 16 && nw <= std::max(1, max_strips); nw *= 2) {
+        const int cap = sms * (16 / nw);                                  // CTAs (pairs) in flight
+        const int waves = (n_pairs + cap - 1) / cap, rounds = (max_strips + nw - 1) / nw;
+        const double score = (double)n_pairs / ((double)waves * cap) * ((double)max_strips / ((double)rounds * nw));
+        if (score > best_score * 1.0001) { best_score = score; best = nw; }
+    }
+    return best;
 }
 
 template <bool WIDE>
@@ -197,8 +206,7 @@ static void launch_sweeps_t(const PairTask *d_pairs, int n_pairs, int nw, int32_
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const int smem = nw * (int)sizeof(SweepSmem);
         cudaFuncSetAttribute(age_sweep_long_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        const int per_sm = std::max(1, std::min(16 / nw, 4));
-        age_sweep_long_kernel<WIDE><<<std::min(n_pairs, sms * per_sm), nw * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
+        age_sweep_long_kernel<WIDE><<<std::min(n_pairs, sms * (16 / nw)), nw * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
         return;
     }
     int dev = 0, sms = 148;
