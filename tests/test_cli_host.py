@@ -53,3 +53,16 @@ def test_original_commands_from_stdin_are_parsed_per_line():
     p = run([], stdin="-indel -bogus a.fa b.fa\n-tdup -indel a.fa b.fa\n")
     assert p.returncode == 1
     assert "Unknown option '-bogus'." in p.stderr and "More than one mode is specified." in p.stderr
+
+
+def test_age2text_host_errors(tmp_path):
+    """the converter of the binary side channel needs no device: usage, and a file that is not a record stream"""
+    exe = ROOT / "asmvar_b200" / "age2text"
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 1 and "Usage: age2text" in p.stderr
+    bad = tmp_path / "x.agb"
+    bad.write_bytes(b"not a record stream, but long enough to pass the size test")
+    fa = tmp_path / "a.fa"
+    fa.write_text(">a\nACGT\n")
+    p = subprocess.run([str(exe), "-t", str(fa), "-q", str(fa), str(bad)], capture_output=True, text=True)
+    assert p.returncode == 1 and "not an AGB1 file" in p.stderr
