@@ -104,15 +104,12 @@ bool slurp(const string &file, string &out)
 
 inline bool is_space(char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }     // isspace() of the C locale
 
-// Fa::Load (Backup/Fa.h:27-50): per line the first whitespace-delimited token; '>' tokens start a record.
+// Fa::Load (Backup/Fa.h:27-50): per line the first whitespace-delimited token; '>' tokens start a record, a record whose
+// id was seen before replaces the earlier one.  The file is cut at record starts and the pieces are parsed side by side.
 // false = the file cannot be opened.
-bool load_fa(const string &file, map<string, string> &fa)
+void parse_fa_piece(const char *p, const char *end, vector<pair<string, string>> &recs)
 {
-    string data;
-    if (!slurp(file, data)) return false;
-    string id;
     string *cur = nullptr;
-    const char *p = data.data(), *end = p + data.size();
     while (p < end) {
         while (p < end && is_space(*p)) ++p;                           // operator>> skips leading white space (and empty lines)
         if (p >= end) break;
@@ -120,10 +117,41 @@ bool load_fa(const string &file, map<string, string> &fa)
         const char *le = nl ? nl : end;
         const char *q = p;
         while (q < le && !is_space(*q)) ++q;                           // the token ends at the first white space
-        if (*p == '>') { id.assign(p + 1, (size_t)(q - p - 1)); cur = &fa[id]; cur->clear(); }
-        else { if (!cur) cur = &fa[id]; cur->append(p, (size_t)(q - p)); }
+        if (*p == '>') { recs.emplace_back(string(p + 1, (size_t)(q - p - 1)), string()); cur = &recs.back().second; }
+        else {
+            if (!cur) { recs.emplace_back(string(), string()); cur = &recs.back().second; }   // bases before any header: the record ""
+            cur->append(p, (size_t)(q - p));
+        }
         p = nl ? nl + 1 : end;                                         // getline drops the rest of the line
     }
+}
+
+bool load_fa(const string &file, map<string, string> &fa, unsigned threads = 1)
+{
+    string data;
+    if (!slurp(file, data)) return false;
+    const char *base = data.data(), *end = base + data.size();
+    const size_t pieces = max<size_t>(1, min<size_t>(threads, data.size() >> 22));     // 4 MB and more per piece
+    vector<const char *> cut(pieces + 1, end);
+    cut[0] = base;
+    for (size_t t = 1; t < pieces; ++t) {
+        const char *from = max(cut[t - 1], base + data.size() / pieces * t);
+        const char *hit = nullptr;
+        for (const char *x = from; x + 1 < end; ) {                    // the next '>' at the start of a line
+            x = (const char *)memchr(x, '\n', (size_t)(end - x - 1));
+            if (!x) break;
+            if (x[1] == '>') { hit = x + 1; break; }
+            ++x;
+        }
+        cut[t] = hit ? hit : end;
+    }
+    vector<vector<pair<string, string>>> recs(pieces);
+    vector<thread> th;
+    for (size_t t = 1; t < pieces; ++t) th.emplace_back([&, t] { parse_fa_piece(cut[t], cut[t + 1], recs[t]); });
+    parse_fa_piece(cut[0], cut[1], recs[0]);
+    for (auto &x : th) x.join();
+    for (auto &piece : recs)
+        for (auto &r : piece) fa[r.first] = std::move(r.second);
     return true;
 }
 
@@ -531,8 +559,9 @@ int batch_main(int argc, char **argv)
     warm_up_device();
     map<string, string> tfa, qfa;
     bool qok = false;
-    thread qload([&] { qok = load_fa(qfile, qfa); });                  // both files are parsed side by side
-    const bool tok = load_fa(tfile, tfa);
+    const unsigned half = max(1u, thread::hardware_concurrency() / 2);
+    thread qload([&] { qok = load_fa(qfile, qfa, half); });            // both files are parsed side by side, each in pieces
+    const bool tok = load_fa(tfile, tfa, half);
     qload.join();
     if (!tok) { cerr << "Cannot open file : " << tfile << endl; die(1); }
     if (!qok) { cerr << "Cannot open file : " << qfile << endl; die(1); }

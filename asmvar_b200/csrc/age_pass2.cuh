@@ -129,6 +129,19 @@ template <bool WIDE> struct View {
         const int w = W * ((c - 1) / W + 1) - c;
         return (sc.hot[slot(q, rstep(q, c))] >> (8 * w + (q & 7))) & 1u;
     }
+    // Row scans, one block of four columns per lane (128 cells per pass instead of 32).  A plane word holds the codes of
+    // 8 rows x 4 columns of one (lane, step) slot; word_codes() picks the row's four codes, 2 bits per block column w in
+    // processing order (forward planes: w = column offset in the block; reverse planes: w = 3 - offset).
+    __device__ __forceinline__ uint32_t word_codes(uint2 v, int q) const {
+        const int sh = 2 * (q & 7);
+        return ((v.x >> sh) & 3u) | (((v.x >> (16 + sh)) & 3u) << 2) | (((v.y >> sh) & 3u) << 4) | (((v.y >> (16 + sh)) & 3u) << 6);
+    }
+    // codes of FM (plane 1) or FS (plane 0) at row r (1-based, interior) of the forward block with columns c1 .. c1+3 (c1 = 4m + 1)
+    __device__ __forceinline__ uint32_t fwd_codes(int plane, int r, int c1) const { return word_codes(sc.P[plane][slot(r - 1, fstep(r - 1, c1))], r - 1); }
+    // codes of RM (plane 3) or RS (plane 2) at row r of the reverse block with columns c1 .. c1+3 (c1 = 4m + 1): column c1 + j is w = 3 - j
+    __device__ __forceinline__ uint32_t rev_codes(int plane, int r, int c1) const { return word_codes(sc.P[plane][slot(r - 1, rstep(r - 1, c1))], r - 1); }
+    __device__ __forceinline__ uint32_t hot_word(int r, int c) const { return sc.hot[slot(r - 1, rstep(r - 1, c))]; }     // of reverse cell (r, c)'s slot
+
     // Starting at (r, c) and stepping by (dr, dc): how many consecutive cells (at most 32) carry code t, and the
     // code of the first cell that does not (meaningful when the result is < 32).
     __device__ int run_len(int plane, int r, int c, int dr, int dc, uint32_t t, uint32_t &tnext) const {
@@ -254,23 +267,55 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
       while (rows && !stop) {
         const int r = rb + __ffs(rows) - 1; rows &= rows - 1;
         const int lo = rlo[r], hi = rhi[r];
-        for (int cb = lo & ~31; cb <= hi && !stop; cb += 32) {
-            const int c = cb + lane;
-            const bool in = c >= lo && c <= hi;
-            V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
-            const bool tie = in && V.tie_nc(r, c);
-            V.ensure_lanes(1, tie ? r : -1, c);
-            const bool hit = tie && V.code_nc(1, r, c) == T_STOP;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-            while (m && !stop) {
-                const int b = __ffs(m) - 1; m &= m - 1;
-                int lg1 = cb + b, lg2 = r, rg1 = cb + b + 1, rg2 = r + 1;
-                walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
-                const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-                if (res > 0) ++n_add;
-                if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+        auto candidate = [&](int c) {                                   // cell (r, c) ties at the maximum and starts a maxima chain
+            int lg1 = c, lg2 = r, rg1 = c + 1, rg2 = r + 1;
+            walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
+            const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+            if (res > 0) ++n_add;
+            if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+        };
+        auto slow = [&](int a, int b) {                                 // 32 cells per pass; any cell, borders included
+            for (int cb = a & ~31; cb <= b && !stop; cb += 32) {
+                const int c = cb + lane;
+                const bool in = c >= a && c <= b;
+                V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
+                const bool tie = in && V.tie_nc(r, c);
+                V.ensure_lanes(1, tie ? r : -1, c);
+                unsigned m = __ballot_sync(0xFFFFFFFFu, tie && V.code_nc(1, r, c) == T_STOP);
+                while (m && !stop) { const int b2 = __ffs(m) - 1; m &= m - 1; candidate(cb + b2); }
             }
-        }
+        };
+        // Long runs along a row (a deletion: every column of the excised stretch ties): interior cells 1 <= c <= len1 - 1 of
+        // interior rows go through 128 cells per pass -- one forward block per lane: its FM word, and the hot words of the
+        // two reverse blocks that hold the reverse cells (r+1, c+1)
+        const int a = max(lo, 1), b = min(hi, V.len1 - 1);
+        if (r >= 1 && r <= len2 - 1 && b - a >= 96) {
+            if (lo < a) slow(lo, a - 1);
+            for (int g0 = (a - 1) >> 2; g0 <= (b - 1) >> 2 && !stop; g0 += 32) {
+                const int m = g0 + lane, c1 = 4 * m + 1;
+                const bool act = m <= (b - 1) >> 2, fourth = act && c1 + 4 <= V.len1;
+                V.ensure_lanes(1, act ? r : -1, c1);
+                V.ensure_lanes(3, act ? r + 1 : -1, c1 + 1);
+                V.ensure_lanes(3, fourth ? r + 1 : -1, c1 + 4);
+                uint32_t hits = 0;
+                if (act) {
+                    const uint32_t fm = V.fwd_codes(1, r, c1), hA = V.hot_word(r + 1, c1 + 1), hB = fourth ? V.hot_word(r + 1, c1 + 4) : 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = c1 + j;
+                        const uint32_t tie = j < 3 ? (hA >> (8 * (2 - j) + (r & 7))) & 1u : (hB >> (24 + (r & 7))) & 1u;
+                        if (c >= a && c <= b && tie && ((fm >> (2 * j)) & 3u) == T_STOP) hits |= 1u << j;
+                    }
+                }
+                unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
+                while (lanes && !stop) {
+                    const int src = __ffs(lanes) - 1; lanes &= lanes - 1;
+                    uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
+                    while (h && !stop) { const int j = __ffs(h) - 1; h &= h - 1; candidate(4 * (g0 + src) + 1 + j); }
+                }
+            }
+            if (hi > b && !stop) slow(b + 1, hi);
+        } else slow(lo, hi);
       }
     }
     n_add = 0; stop = false;
@@ -302,21 +347,48 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
       while (rows && !stop) {
         const int r = rb + 31 - __clz(rows); rows &= ~(1u << (r - rb));
         const int lo = rlo[r], hi = rhi[r];
-        for (int cb = hi & ~31; cb >= (lo & ~31) && !stop; cb -= 32) {
-            const int c = cb + lane;
-            const bool in = c >= lo && c <= hi;
-            V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
-            const bool hit = in && V.tie_nc(r, c) && V.code_nc(3, r + 1, c + 1) == T_STOP;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-            while (m && !stop) {
-                const int b = 31 - __clz(m); m &= ~(1u << b);
-                int lg1 = cb + b, lg2 = r, rg1 = cb + b + 1, rg2 = r + 1;
-                walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
-                const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-                if (res > 0) ++n_add;
-                if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+        auto candidate = [&](int c) {
+            int lg1 = c, lg2 = r, rg1 = c + 1, rg2 = r + 1;
+            walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
+            const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+            if (res > 0) ++n_add;
+            if (n_add >= MAX_BP / 2 || res < 0) stop = true;
+        };
+        auto slow = [&](int a, int b) {
+            for (int cb = b & ~31; cb >= (a & ~31) && !stop; cb -= 32) {
+                const int c = cb + lane;
+                const bool in = c >= a && c <= b;
+                V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
+                unsigned m = __ballot_sync(0xFFFFFFFFu, in && V.tie_nc(r, c) && V.code_nc(3, r + 1, c + 1) == T_STOP);
+                while (m && !stop) { const int b2 = 31 - __clz(m); m &= ~(1u << b2); candidate(cb + b2); }
             }
-        }
+        };
+        // the same long runs from the right: one reverse block per lane (reverse cells (r+1, c+1) with c + 1 = 4m+1 .. 4m+4),
+        // its RM word and its hot word, the block with the largest columns first
+        const int a = lo, b = min(hi, V.len1 - 1);
+        if (r <= len2 - 1 && b - a >= 96) {
+            if (hi > b) slow(b + 1, hi);
+            for (int g0 = b >> 2; g0 >= (a >> 2) && !stop; g0 -= 32) {
+                const int m = g0 - lane, c1 = 4 * m + 1;                // reverse cells (r+1, c1 .. c1+3) = cells (r, c1-1 .. c1+2)
+                const bool act = m >= (a >> 2);
+                V.ensure_lanes(3, act ? r + 1 : -1, c1);
+                uint32_t hits = 0;
+                if (act) {
+                    const uint32_t rm = V.rev_codes(3, r + 1, c1), hw = V.hot_word(r + 1, c1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = c1 + j - 1;
+                        if (c >= a && c <= b && ((hw >> (8 * (3 - j) + (r & 7))) & 1u) && ((rm >> (2 * (3 - j))) & 3u) == T_STOP) hits |= 1u << j;
+                    }
+                }
+                unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
+                while (lanes && !stop) {
+                    const int src = __ffs(lanes) - 1; lanes &= lanes - 1;
+                    uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
+                    while (h && !stop) { const int j = 31 - __clz(h); h &= ~(1u << j); candidate(4 * (g0 - src) + j); }
+                }
+            }
+        } else slow(lo, hi);
       }
     }
 }
@@ -398,81 +470,121 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
     int n_add = 0;
     bool stop = false;
     P2_PROF_T0(kc);
-    for (int r = 0; r <= len2 && !stop; ++r) {                            // forward (:485-504)
-        if (A(r) + B(r + 1) != max2) continue;
-        if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
-        for (int jb = 0; jb <= len1 && !stop; jb += 32) {
-            const int j = jb + lane;
-            V.ensure_lanes(1, j <= len1 ? r : -1, j);
-            unsigned m = __ballot_sync(0xFFFFFFFFu, j <= len1 && V.code_nc(1, r, j) == T_STOP);
-            while (m && !stop) {
-                const int j1 = jb + __ffs(m) - 1; m &= m - 1;
-                const int tv = max2 - V.F2(r, j1);
-                if (tv < 0) continue;
-                // columns x in [1, len1+1] of row r+1, values non-increasing: first x with value <= tv
-                int lo = 1, hi = len1 + 2;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.R2(r + 1, mid) <= tv) hi = mid; else lo = mid + 1; }
-                if (V.R2(r + 1, lo) != tv) continue;
-                // the run of columns with value tv ends before the first x with value < tv
-                int l2 = lo, h2 = len1 + 2;
-                while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (V.R2(r + 1, mid) < tv) h2 = mid; else l2 = mid + 1; }
-                const int xhi = l2 - 1;
-                for (int xb = lo; xb <= xhi && !stop; xb += 32) {
-                    const int xi = xb + lane;
-                    const bool in = xi <= xhi;
-                    const bool mg = V.merges_into_next(3, r + 1, xi, +1, in);      // warp-collective: every lane calls it
-                    unsigned am = __ballot_sync(0xFFFFFFFFu, in && !mg);
-                    while (am && !stop) {                                  // walks that do not merge into their neighbour's
-                        const int x = xb + __ffs(am) - 1; am &= am - 1;
-                        int rg1 = x, rg2 = r + 1, lg1 = j1, lg2 = r;
-                        walk_right(V, rg1, rg2);
-                        const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-                        if (res > 0) ++n_add;
-                        if (n_add >= MAX_BP / 2 || res < 0) stop = true;
-                    }
-                }
+    // one start cell (r, j1) of the forward scan: FM is 0 there
+    auto fwd_start = [&](int r, int j1) {
+        const int tv = max2 - V.F2(r, j1);
+        if (tv < 0) return;
+        // columns x in [1, len1+1] of row r+1, values non-increasing: first x with value <= tv
+        int lo = 1, hi = len1 + 2;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.R2(r + 1, mid) <= tv) hi = mid; else lo = mid + 1; }
+        if (V.R2(r + 1, lo) != tv) return;
+        // the run of columns with value tv ends before the first x with value < tv
+        int l2 = lo, h2 = len1 + 2;
+        while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (V.R2(r + 1, mid) < tv) h2 = mid; else l2 = mid + 1; }
+        const int xhi = l2 - 1;
+        for (int xb = lo; xb <= xhi && !stop; xb += 32) {
+            const int xi = xb + lane;
+            const bool in = xi <= xhi;
+            const bool mg = V.merges_into_next(3, r + 1, xi, +1, in);      // warp-collective: every lane calls it
+            unsigned am = __ballot_sync(0xFFFFFFFFu, in && !mg);
+            while (am && !stop) {                                  // walks that do not merge into their neighbour's
+                const int x = xb + __ffs(am) - 1; am &= am - 1;
+                int rg1 = x, rg2 = r + 1, lg1 = j1, lg2 = r;
+                walk_right(V, rg1, rg2);
+                const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+                if (res > 0) ++n_add;
+                if (n_add >= MAX_BP / 2 || res < 0) stop = true;
             }
         }
+    };
+    for (int rb = 0; rb <= len2 && !stop; rb += 32) {                     // forward (:485-504): the tie rows, 32 rows per look
+      unsigned tie_rows = __ballot_sync(0xFFFFFFFFu, rb + lane <= len2 && A(rb + lane) + B(rb + lane + 1) == max2);
+      while (tie_rows && !stop) {
+        const int r = rb + __ffs(tie_rows) - 1; tie_rows &= tie_rows - 1;
+        if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
+        if (r == 0) {                                                     // border row: only (0, 0) has FM = 0 (:874-882)
+            fwd_start(0, 0);
+            continue;
+        }
+        // interior row: column 0 carries FM = VERTICAL; columns 1 .. len1 one forward block per lane, 128 cells per pass
+        for (int g0 = 0; g0 <= (len1 - 1) >> 2 && !stop; g0 += 32) {
+            const int m = g0 + lane, c1 = 4 * m + 1;
+            const bool act = c1 <= len1;
+            V.ensure_lanes(1, act ? r : -1, c1);
+            uint32_t hits = 0;
+            if (act) {
+                const uint32_t fm = V.fwd_codes(1, r, c1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c1 + j <= len1 && ((fm >> (2 * j)) & 3u) == T_STOP) hits |= 1u << j;
+            }
+            unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
+            while (lanes && !stop) {
+                const int src = __ffs(lanes) - 1; lanes &= lanes - 1;
+                uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
+                while (h && !stop) { const int j = __ffs(h) - 1; h &= h - 1; fwd_start(r, 4 * (g0 + src) + 1 + j); }
+            }
+        }
+      }
     }
     P2_PROF_ADD(1, kc);
     P2_PROF_RESET(kc);
     n_add = 0; stop = false;
-    for (int i2 = len2 + 1; i2 >= 1 && !stop; --i2) {                     // reverse (:515-534)
-        if (A(i2 - 1) + B(i2) != max2) continue;
-        if (i2 <= len2) V.ensure_rm((i2 - 1) >> 8);
-        for (int jb = ((len1 + 1) / 32) * 32; jb >= 0 && !stop; jb -= 32) {
-            const int j = jb + lane;
-            V.ensure_lanes(3, (j >= 1 && j <= len1 + 1) ? i2 : -1, j);
-            unsigned m = __ballot_sync(0xFFFFFFFFu, j >= 1 && j <= len1 + 1 && V.code_nc(3, i2, j) == T_STOP);
-            while (m && !stop) {
-                const int b = 31 - __clz(m); m &= ~(1u << b);
-                const int j2 = jb + b;
-                const int tv = max2 - V.R2(i2, j2);
-                if (tv < 0) continue;
-                // columns x in [0, len1] of row i2-1, values non-decreasing: last x with value <= tv
-                int lo = -1, hi = len1;
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (V.F2(i2 - 1, mid) <= tv) lo = mid; else hi = mid - 1; }
-                if (lo < 0 || V.F2(i2 - 1, lo) != tv) continue;
-                // the run of columns with value tv starts after the last x with value < tv
-                int l2 = -1, h2 = lo;
-                while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (V.F2(i2 - 1, mid) < tv) l2 = mid; else h2 = mid - 1; }
-                const int xlo = l2 + 1;
-                for (int xb = lo; xb >= xlo && !stop; xb -= 32) {
-                    const int xi = xb - lane;
-                    const bool in = xi >= xlo;
-                    const bool mg = V.merges_into_next(1, i2 - 1, xi, -1, in);
-                    unsigned am = __ballot_sync(0xFFFFFFFFu, in && !mg);
-                    while (am && !stop) {
-                        const int x = xb - (__ffs(am) - 1); am &= am - 1;
-                        int lg1 = x, lg2 = i2 - 1, rg1 = j2, rg2 = i2;
-                        walk_left(V, lg1, lg2);
-                        const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
-                        if (res > 0) ++n_add;
-                        if (n_add >= MAX_BP / 2 || res < 0) stop = true;
-                    }
-                }
+    // one start cell (i2, j2) of the reverse scan: RM is 0 there
+    auto rev_start = [&](int i2, int j2) {
+        const int tv = max2 - V.R2(i2, j2);
+        if (tv < 0) return;
+        // columns x in [0, len1] of row i2-1, values non-decreasing: last x with value <= tv
+        int lo = -1, hi = len1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (V.F2(i2 - 1, mid) <= tv) lo = mid; else hi = mid - 1; }
+        if (lo < 0 || V.F2(i2 - 1, lo) != tv) return;
+        // the run of columns with value tv starts after the last x with value < tv
+        int l2 = -1, h2 = lo;
+        while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (V.F2(i2 - 1, mid) < tv) l2 = mid; else h2 = mid - 1; }
+        const int xlo = l2 + 1;
+        for (int xb = lo; xb >= xlo && !stop; xb -= 32) {
+            const int xi = xb - lane;
+            const bool in = xi >= xlo;
+            const bool mg = V.merges_into_next(1, i2 - 1, xi, -1, in);
+            unsigned am = __ballot_sync(0xFFFFFFFFu, in && !mg);
+            while (am && !stop) {
+                const int x = xb - (__ffs(am) - 1); am &= am - 1;
+                int lg1 = x, lg2 = i2 - 1, rg1 = j2, rg2 = i2;
+                walk_left(V, lg1, lg2);
+                const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
+                if (res > 0) ++n_add;
+                if (n_add >= MAX_BP / 2 || res < 0) stop = true;
             }
         }
+    };
+    for (int rb = (len2 + 1) & ~31; rb >= 0 && !stop; rb -= 32) {          // reverse (:515-534): the tie rows from the last one
+      unsigned tie_rows = __ballot_sync(0xFFFFFFFFu, rb + lane >= 1 && rb + lane <= len2 + 1 && A(rb + lane - 1) + B(rb + lane) == max2);
+      while (tie_rows && !stop) {
+        const int i2 = rb + 31 - __clz(tie_rows); tie_rows &= ~(1u << (i2 - rb));
+        if (i2 <= len2) V.ensure_rm((i2 - 1) >> 8);
+        if (i2 > len2) {                                                  // border row: RM is 0 in every column (:924-932)
+            for (int j2 = len1 + 1; j2 >= 1 && !stop; --j2) rev_start(i2, j2);
+            continue;
+        }
+        rev_start(i2, len1 + 1);                                          // border column
+        // columns len1 .. 1, one reverse block per lane, the block with the largest columns first
+        for (int g0 = (len1 - 1) >> 2; g0 >= 0 && !stop; g0 -= 32) {
+            const int m = g0 - lane, c1 = 4 * m + 1;
+            const bool act = m >= 0;
+            V.ensure_lanes(3, act ? i2 : -1, c1);
+            uint32_t hits = 0;
+            if (act) {
+                const uint32_t rm = V.rev_codes(3, i2, c1);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (c1 + j <= len1 && ((rm >> (2 * (3 - j))) & 3u) == T_STOP) hits |= 1u << j;
+            }
+            unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
+            while (lanes && !stop) {
+                const int src = __ffs(lanes) - 1; lanes &= lanes - 1;
+                uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
+                while (h && !stop) { const int j = 31 - __clz(h); h &= ~(1u << j); rev_start(i2, 4 * (g0 - src) + 1 + j); }
+            }
+        }
+      }
     }
     P2_PROF_ADD(2, kc);
 }
@@ -540,7 +652,17 @@ __device__ void pair_select(const PairTask &T, AlignerOut *outs, int lane, int (
     const int len2 = T.len2;
     uint32_t mx_indel = 0, mx_col = 0;                       // max of 2*(Fmax + Rmax), packed per half
     const int nwt = T.nstrips * T.nwin;
-    for (int i = lane; i < nwt * 32; i += 32) mx_indel = A::maxu(mx_indel, T.tilemax[i]);
+    {   // nwt * 32 words = nwt * 8 uint4: four independent 16-byte loads per lane and pass
+        const uint4 *tm = reinterpret_cast<const uint4 *>(T.tilemax);
+        const int n4 = nwt * 8;
+        for (int i = lane; i < n4; i += 128) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = (i + 32 * k < n4) ? __ldg(tm + i + 32 * k) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mx_indel = A::maxu(A::maxu(mx_indel, A::maxu(v[k].x, v[k].y)), A::maxu(v[k].z, v[k].w));
+        }
+    }
     for (int r = lane; r <= len2; r += 32) {
         const uint32_t f = r >= 1 ? T.Dlast[r] : 0u, q = r + 1 <= len2 ? T.Rfirst[r + 1] : 0u;
         mx_col = A::maxu(mx_col, A::sum(A::add(f, q)));
@@ -567,18 +689,32 @@ __device__ void pair_select(const PairTask &T, AlignerOut *outs, int lane, int (
     }
 }
 
-// INDEL: the reverse windows that hold a (lane, window) tile at the split maximum (sc.hotlist)
+// INDEL: the reverse windows that hold a (lane, window) tile at the split maximum (sc.hotlist), in window order.
+// 32 windows per pass: every lane looks through the 32 tile words of one window (eight 16-byte loads in flight), a
+// ballot collects the windows that hold the maximum.
 template <bool WIDE>
 __device__ int build_hotlist(const PairTask &T, const P2Scratch &sc, int h, int max2h, int lane)
 {
     const int nwt = T.nstrips * T.nwin;
+    const uint4 *tm = reinterpret_cast<const uint4 *>(T.tilemax);
     int nhot = 0;
-    for (int wi = 0; wi < nwt; ++wi) {
-        const uint32_t tm = T.tilemax[(size_t)wi * 32 + lane];
-        const bool hot = (WIDE ? (int)tm : (int)((tm >> (16 * h)) & 0xFFFFu)) == max2h;
-        if (!__any_sync(0xFFFFFFFFu, hot)) continue;
-        if (lane == 0) sc.hotlist[1 + nhot] = wi;
-        ++nhot;
+    for (int base = 0; base < nwt; base += 32) {
+        const int wi = base + lane;
+        bool hot = false;
+        if (wi < nwt) {
+            uint4 v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(tm + (size_t)wi * 8 + i);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t w4[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hot = hot || (WIDE ? (int)w4[j] : (int)((w4[j] >> (16 * h)) & 0xFFFFu)) == max2h;
+            }
+        }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hot);
+        if (hot) sc.hotlist[1 + nhot + __popc(m & ((1u << lane) - 1u))] = wi;
+        nhot += __popc(m);
     }
     if (lane == 0) sc.hotlist[0] = nhot;
     __syncwarp();

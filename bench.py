@@ -308,6 +308,9 @@ def inproc_leg(devices, single_device_results=None):
     with engine.Engine(list(devices)) as eng:
         for kind, flag in kinds.items():
             cands = [(w, q) for k, w, q in mixed if k == kind]
+            # length-binned: candidates of similar DP area share a batch, so no warp is left with one long pair while the
+            # others run out of short ones (the caller owns the order of its results; nothing is printed here)
+            cands.sort(key=lambda c: len(c[0]) * len(c[1]), reverse=True)
             batches = [cands[i:i + per_batch] for i in range(0, len(cands), per_batch)]
             prepared = [eng.make_jobs(both_jobs(b, flag)) for b in batches]
             outs = [(capi.AgeResult * max(1, p[2]))() for p in prepared[:2]]
@@ -335,7 +338,7 @@ def inproc_leg(devices, single_device_results=None):
             checks.append((kind, scores))
     return {"value": total_c / total_s, "unit": "realignments/s", "gcups": total_cu / total_s / 1e9, "candidates": total_c, "seconds": total_s,
             "devices": nd, "per_mode": summary, "generate_s": gen_s, "scaling": "strong",
-            "api": f"one age_create over {nd} device(s); age_submit/age_collect, batches of {per_batch} candidates, two in flight",
+            "api": f"one age_create over {nd} device(s); age_submit/age_collect, length-binned batches of {per_batch} candidates, two in flight",
             "workload": "C3-style fixed set: len1 in {1,2,4,8} kb x len2 in {0.5,1,2} kb, 70 % indel / 30 % tdup, -both"}, checks
 
 
@@ -534,8 +537,9 @@ def inproc_check_single(device: int):
     checks = []
     with engine.Engine([device]) as eng:
         for kind, flag in (("indel", capi.INDEL_FLAG), ("tdup", capi.TDUPLICATION_FLAG)):
-            cands = [(w, q) for k, w, q in mixed if k == kind][:1024]
-            arr, keep, n = eng.make_jobs(both_jobs(cands, flag))
+            cands = [(w, q) for k, w, q in mixed if k == kind]
+            cands.sort(key=lambda c: len(c[0]) * len(c[1]), reverse=True)
+            arr, keep, n = eng.make_jobs(both_jobs(cands[:1024], flag))
             res = eng.align_raw(arr, n)
             checks.append((kind, [(res[i].status, res[i].score, res[i].n_bp, res[i].detail) for i in range(min(n, 2048))]))
     return checks
