@@ -99,17 +99,25 @@ struct AlignerOut {
 
 struct Block { int32_t start1, start2, length; };
 
-// Trace planes of one aligner (pass 2), filled window by window by re-running the sweep from its checkpoints:
-// the windows of the split row / column by the parallel pre-sweep kernel, everything else on demand.
+// Trace planes of one aligner (pass 2), filled window by window by re-running the sweep from its checkpoints: the
+// windows of the split row / column by the parallel pre-sweep kernel, everything else on demand.  A window of a plane is
+// a PAGE taken from the batch's trace pool when it is first swept (a pair looks at a few dozen of its hundreds or
+// thousands of windows): `ptab` maps (plane, window) to the page.  Pages, in 4 KB granules of the pool:
+//   code planes FS, FM, RS (0 .. 2)   2 granules: [step in window][lane] uint2, 16 bits per block column, 2 bits per row
+//   RM (3)                            3 granules: the code page + [step][lane] hot words (bit 8w+k = Fmax + Rmax == max)
+//   reverse maxima Mp (4, K7 only)    32 granules: [step][column][half of rows][lane] uint4, as the raw D layout but unshifted
 struct P2Scratch {
-    uint2 *P[4];                         // 2-bit code planes FS, FM, RS, RM: [slots][32], 16 bits per block column
-    uint32_t *hot;                       // [slots][32]: bit 8w+k = reverse cell holds Fmax + Rmax == max (with RM)
-    uint32_t *Mp;                        // reverse maxima, same layout as D but unshifted (K7 only)
+    int32_t *ptab;                       // [5][nwt] first granule of the page
+    char *pool;                          // the batch's trace pool
+    uint32_t pool_granules;              // its size; granules 0 .. 31 are the dump every sweep writes to once the pool is full
+    uint32_t *pool_next;                 // granules handed out so far (beyond the dump); > pool_granules - 32: overflow, the host runs again
     uint32_t *valid;                     // [9][vwords] window bits: the four planes, Mp, queued for the pre-sweeps (FM, RM, FS, RS)
     int32_t *rowrange;                   // [2][len2 + 2]
     int32_t *hotlist;                    // [1 + nwt] number and indices (strip * nwin + window) of the reverse windows at the maximum
-    int32_t vwords;
+    int32_t vwords, nwt;
 };
+constexpr int P2_GRANULE = 4096, P2_DUMP_GRANULES = 32;
+__host__ __device__ inline int p2_page_granules(int plane) { return plane < 3 ? 2 : plane == 3 ? 3 : 32; }
 
 struct PairHdr { int32_t max2[2]; int32_t need[2]; };   // split maxima (x2) and which halves get breakpoints
 
@@ -121,26 +129,29 @@ struct Pass2Params {
     Block *pool; int32_t pool_cap; int32_t *pool_used;
     uint2 *queue; int32_t queue_cap; int32_t *queue_n;   // pre-sweep work items {pair, half | plane << 1 | strip << 4 | window << 16}
     int32_t *next;                       // work counters: select, pre-sweep 1, enumerate, blocks, pre-sweep 2
+    char *tpool; uint32_t tpool_granules; uint32_t *tpool_next;   // trace pool of the batch (P2Scratch)
 };
 
-// layout of one plane set (shared by host and device)
+// layout of the per-aligner part of pass 2 (shared by host and device): page table, window bits, row ranges, hot list
 __host__ __device__ inline size_t p2_up(size_t v) { return (v + 255) / 256 * 256; }
 __host__ __device__ inline size_t p2_vwords(size_t nwt) { return (nwt + 31) / 32 + 1; }
-__host__ __device__ inline size_t p2_set_bytes(size_t slots, size_t nwt, size_t len2, int k7)
+__host__ __device__ inline size_t p2_set_bytes(size_t nwt, size_t len2)
 {
-    return 4 * p2_up(slots * 32 * 8) + p2_up(slots * 32 * 4) + (k7 ? p2_up(slots * W * 2 * 32 * 16) : 0) +
-           p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4) + p2_up((nwt + 1) * 4);
+    return p2_up(5 * nwt * 4) + p2_up(9 * p2_vwords(nwt) * 4) + p2_up(2 * (len2 + 2) * 4) + p2_up((nwt + 1) * 4);
 }
+// granules all pages of one aligner would take (the bound the pool never has to exceed)
+__host__ __device__ inline size_t p2_full_granules(size_t nwt, int k7) { return nwt * (size_t)(2 + 2 + 2 + 3 + (k7 ? 32 : 0)); }
 
 // One sub-batch on one device: pairs [0, n_wide) run in the 32-bit kernels, the rest in the packed 16-bit ones.
 // counters: 32 ints, zeroed by launch_sweeps (0 / 16: pair counters of the packed / wide sweep kernel, 1: blocks used in
-// the pool, the rest: work counters of the pass-2 kernels).
+// the pool, 3: granules taken from the trace pool, the rest: work counters of the pass-2 kernels).
 struct BatchLaunch {
     const PairTask *pairs; int32_t n_pairs, n_wide;
     int32_t nw, nw_wide;                                // warps per pair in the sweep of the packed / wide pairs (sweep_warps_per_pair)
     AlignerOut *outs; Block *pool; int32_t pool_cap;
     int32_t *counters;
     PairHdr *hdr; uint2 *queue; int32_t queue_cap;
+    char *tpool; uint32_t tpool_granules;               // trace pool (P2Scratch); its counter is counters[3]
 };
 
 // launchers (age_kernels.cu)

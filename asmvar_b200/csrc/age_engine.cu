@@ -82,7 +82,9 @@ struct HostPair {
     int k7;                      // holds a TDUP / INVL / INVR aligner (pass 2 then needs the reverse maxima plane)
     int dfmt;                    // storage format of the D plane (DFMT_RAW / DFMT_OFF8, age_device.cuh)
     int wide;                    // one aligner in 32-bit words (PairTask::wide)
-    int nsets; size_t set_bytes;  // pass-2 trace plane sets (one per aligner that gets breakpoints)
+    int nsets; size_t set_bytes;  // pass-2 page tables and lists (one set per aligner that gets breakpoints)
+    size_t trace_share;          // this pair's contribution to the batch's trace pool, in granules (age_device.cuh: P2Scratch)
+    size_t trace_full;           // granules all trace pages of the pair would take
     size_t in_bytes, scratch_bytes;
     double cells;
 };
@@ -98,6 +100,7 @@ struct Slot {
     std::vector<size_t> sc_off;
     int n_outs = 0, pool_cap = 0, queue_cap = 0, n_wide = 0, nw = 1, nw_wide = 1, launches = 0;
     size_t in_bytes = 0, out_bytes = 0, sc_bytes = 0;
+    size_t tpool_off = 0, tpool_full = 0; uint32_t tpool_granules = 0;   // trace pool of the sub-batch: behind the pairs' scratch
 };
 
 struct Device {
@@ -228,8 +231,13 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
                            2 * align_up((size_t)hp.nstrips * hp.nwin * CKW * 32 * 4, 256);
         hp.scratch_bytes += 2 * align_up(((size_t)hp.nb + 2) * 16, 256) + align_up((size_t)hp.P * 8, 256) + align_up((size_t)hp.P, 256);
         hp.nsets = (select || a1 < 0) ? 1 : 2;
-        hp.set_bytes = p2_set_bytes(slots, (size_t)hp.nstrips * hp.nwin, (size_t)j.len2, hp.k7);
+        hp.set_bytes = p2_set_bytes((size_t)hp.nstrips * hp.nwin, (size_t)j.len2);
         hp.scratch_bytes += hp.nsets * hp.set_bytes;
+        // Trace pages come out of a pool of the batch: an INDEL aligner looks at a few dozen of its windows (about 5 % of all its
+        // pages in the C2 workload), a TDUP / inversion aligner at whole strips of the tie rows (about 10 % in C4).  The pool gets
+        // an eighth / a quarter of the full size; a batch that needs more is run again with a pool twice as large.
+        hp.trace_full = (size_t)hp.nsets * p2_full_granules((size_t)hp.nstrips * hp.nwin, hp.k7);
+        hp.trace_share = hp.trace_full / (hp.k7 ? 4 : 8) + 8;
         hp.cells = (double)j.len1 * j.len2;
         B->pairs.push_back(hp);
     };
@@ -377,7 +385,15 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     sl.nw = sweep_warps_per_pair((int)np - sl.n_wide, ms);
     sl.nw_wide = sweep_warps_per_pair(sl.n_wide, ms_wide);
     sl.n_outs = n_outs;
-    sl.sc_bytes = sl.sc_off[np];
+    // the trace pool of the sub-batch behind the scratch of its pairs
+    size_t share = 0;
+    sl.tpool_full = P2_DUMP_GRANULES;
+    for (size_t i = 0; i < np; ++i) { share += B.pairs[pair_ids[i]].trace_share; sl.tpool_full += B.pairs[pair_ids[i]].trace_full; }
+    size_t gran = std::min(sl.tpool_full, std::max<size_t>(share + P2_DUMP_GRANULES, (size_t)16384));          // at least 64 MB
+    if (const char *e = getenv("AGE_TRACE_POOL_GRANULES")) gran = std::max<size_t>(P2_DUMP_GRANULES + 64, (size_t)atol(e));   // test knob: a small pool forces the overflow re-run
+    sl.tpool_granules = (uint32_t)std::min<size_t>(gran, 0xFFFFFFF0u);
+    sl.tpool_off = align_up(sl.sc_off[np], P2_GRANULE);
+    sl.sc_bytes = sl.tpool_off + (size_t)sl.tpool_granules * P2_GRANULE;
     sl.queue_cap = (int)std::min<size_t>(2 * nwt_total + 64, (size_t)1 << 24);
     if (const char *e = getenv("AGE_QUEUE_CAP")) sl.queue_cap = std::max(1, atoi(e));   // test knob: a short work list forces on-demand re-sweeps
     const size_t task_bytes = align_up(np * sizeof(PairTask), 256);
@@ -428,6 +444,7 @@ bool run_on_device(Device &dev, Slot &sl)
     b.outs = L.outs; b.pool = L.pool; b.pool_cap = sl.pool_cap; b.counters = L.counters;
     b.hdr = (PairHdr *)sl.aux.ptr;
     b.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)); b.queue_cap = sl.queue_cap;
+    b.tpool = dev.scratch.ptr + sl.tpool_off; b.tpool_granules = sl.tpool_granules;
     launch_sweeps(b, dev.st);
     CK(cudaEventRecord(sl.ev[3], dev.st));
     launch_pass2(b, dev.st);
@@ -448,14 +465,16 @@ bool enqueue_fetch(Device &dev, Slot &sl)
     return true;
 }
 
-// The block pool of the slot was too small: run its sub-batch again with a larger one.  A later batch may have used
-// (or moved) the scratch arena in the meantime, so the sweeps are repeated as well; the packed inputs are still resident.
-bool rerun_with_pool(Batch &B, Device &dev, Slot &sl, int pool_cap)
+// The block pool or the trace pool of the slot was too small: run its sub-batch again with larger ones.  A later batch may
+// have used (or moved) the scratch arena in the meantime, so the sweeps are repeated as well; the packed inputs are still resident.
+bool rerun_with_pools(Batch &B, Device &dev, Slot &sl, int pool_cap, size_t tpool_granules)
 {
     if (!sync_device(dev)) return false;
     sl.pool_cap = pool_cap;
     sl.out_bytes = out_bytes_of(sl.n_outs, sl.pool_cap);
     if (!sl.outbuf.ensure(sl.out_bytes) || !sl.hout.ensure(sl.out_bytes)) { dev.err = "allocation failed (block pool)"; return false; }
+    sl.tpool_granules = (uint32_t)std::min<size_t>(std::min(tpool_granules, sl.tpool_full), 0xFFFFFFF0u);
+    sl.sc_bytes = sl.tpool_off + (size_t)sl.tpool_granules * P2_GRANULE;
     if (sl.sc_bytes + 256 > dev.scratch.cap && !dev.scratch.ensure(sl.sc_bytes + 256)) { dev.err = "device allocation failed (scratch)"; return false; }
     for (size_t i = 0; i < sl.tasks.size(); ++i) assign_scratch(B.pairs[sl.pair_ids[i]], dev.scratch.ptr + sl.sc_off[i], sl.tasks[i]);
     memcpy(sl.hin.ptr, sl.tasks.data(), sl.tasks.size() * sizeof(PairTask));
@@ -468,11 +487,14 @@ bool rerun_with_pool(Batch &B, Device &dev, Slot &sl, int pool_cap)
 bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
 {
     CK(cudaSetDevice(dev.id));
-    for (int attempt = 0; attempt < 4; ++attempt) {
+    for (int attempt = 0; attempt < 8; ++attempt) {
         CK(cudaEventSynchronize(sl.ev[6]));
         OutLayout H = out_layout(sl, sl.hout.ptr);
-        if (H.counters[1] > sl.pool_cap) {                // the block pool was too small: run again with a larger one
-            if (!rerun_with_pool(B, dev, sl, H.counters[1] + 4096)) return false;
+        const size_t tneed = (size_t)(uint32_t)H.counters[3] + P2_DUMP_GRANULES;
+        if (H.counters[1] > sl.pool_cap || tneed > sl.tpool_granules) {       // a pool was too small: run again with larger ones
+            const int pc = H.counters[1] > sl.pool_cap ? H.counters[1] + 4096 : sl.pool_cap;
+            const size_t tg = tneed > sl.tpool_granules ? std::max(2 * (size_t)sl.tpool_granules, tneed + tneed / 4) : sl.tpool_granules;
+            if (!rerun_with_pools(B, dev, sl, pc, tg)) return false;
             st.launches += 1 + sl.launches; st.fill_launches += 1;
             continue;
         }
@@ -501,7 +523,7 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
         st.launches += 1 + sl.launches; st.fill_launches += 1;          // pack + the batch's kernels
         return true;
     }
-    dev.err = "block pool overflow";
+    dev.err = "block / trace pool overflow";
     return false;
 }
 
@@ -542,7 +564,9 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx, const B
     const char *cap_env = getenv("AGE_MEM_BUDGET_MB");               // test knob: a small budget forces several sub-batches
     for (int d = 0; d < nd; ++d) {
         size_t sc = 256, in = align_up(per_dev[d].size() * sizeof(PairTask), 256);
-        for (int pi : per_dev[d]) { sc += B.pairs[pi].scratch_bytes; in += B.pairs[pi].in_bytes; }
+        size_t share = P2_DUMP_GRANULES;
+        for (int pi : per_dev[d]) { sc += B.pairs[pi].scratch_bytes; in += B.pairs[pi].in_bytes; share += B.pairs[pi].trace_share; }
+        sc += std::max<size_t>(share, 16384) * P2_GRANULE + P2_GRANULE;
         if (!cap_env && sc <= ctx->devs[d].scratch.cap && in <= ctx->devs[d].slot[slot].in.cap) {        // fits what is already allocated
             if (!per_dev[d].empty()) res[d].push_back(per_dev[d]);
             continue;
@@ -551,7 +575,7 @@ std::vector<std::vector<std::vector<int>>> make_subbatches(age_ctx *ctx, const B
         if (cap_env) budget[d] = (size_t)std::max(1L, atol(cap_env)) << 20;
         std::vector<int> cur; size_t used = 0;
         for (int pi : per_dev[d]) {
-            const size_t need = B.pairs[pi].scratch_bytes + B.pairs[pi].in_bytes + 4096;
+            const size_t need = B.pairs[pi].scratch_bytes + B.pairs[pi].in_bytes + 4096 + B.pairs[pi].trace_share * P2_GRANULE;
             if (!cur.empty() && used + need > budget[d]) { res[d].push_back(cur); cur.clear(); used = 0; }
             cur.push_back(pi); used += need;
         }

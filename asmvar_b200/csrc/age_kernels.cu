@@ -241,6 +241,7 @@ void launch_pass2(const BatchLaunch &b, cudaStream_t st)
         const int wq = b.n_wide ? (b.n_pairs > b.n_wide ? b.queue_cap / 4 : b.queue_cap) : 0;      // share of the work list for the wide pairs
         p.queue = b.queue + (wide ? 0 : wq); p.queue_cap = std::max(1, wide ? wq : b.queue_cap - wq); p.queue_n = cnt + 2;
         p.pool = b.pool; p.pool_cap = b.pool_cap; p.pool_used = b.counters + 1; p.next = cnt + 4;
+        p.tpool = b.tpool; p.tpool_granules = b.tpool_granules; p.tpool_next = reinterpret_cast<uint32_t *>(b.counters + 3);
         if (wide) launch_pass2_t<true>(p, st); else launch_pass2_t<false>(p, st);
     }
 }
@@ -279,7 +280,7 @@ age_select_kernel(Pass2Params prm)
         if (lane == 0) prm.hdr[item] = PairHdr{{max2[0], max2[1]}, {need[0] ? 1 : 0, need[1] ? 1 : 0}};
         for (int h = 0; h < 2; ++h) {
             if (!need[h]) continue;
-            const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+            const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
             for (int i = lane; i < 9 * sc.vwords; i += 32) sc.valid[i] = 0;
             __syncwarp();
             if (T.flag[h] != F_INDEL) {
@@ -360,10 +361,24 @@ age_presweep_kernel(Pass2Params prm, int round)
         const uint2 q = prm.queue[item];
         const PairTask &T = prm.pairs[q.x];
         const int h = q.y & 1, plane = (q.y >> 1) & 7, s = (q.y >> 4) & 0xFFF, win = q.y >> 16;
-        const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+        const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
         const bool with_mp = plane == 5;                     // reverse maxima trace + the maxima themselves (K7)
         const int pl = plane == 5 ? 3 : plane;
-        const TraceOut TO{sc.P[pl], sc.hot, with_mp ? sc.Mp : nullptr, WIDE ? 0 : 16 * h, prm.hdr[q.x].max2[h]};
+        // the window's pages come out of the trace pool (same rule as View::take_page)
+        auto take = [&](int plane_) {
+            uint32_t g = 0;
+            if (lane == 0) {
+                const uint32_t n = (uint32_t)p2_page_granules(plane_);
+                g = atomicAdd(sc.pool_next, n) + P2_DUMP_GRANULES;
+                if (g + n > sc.pool_granules) g = 0;
+                sc.ptab[plane_ * sc.nwt + s * T.nwin + win] = (int32_t)g;
+            }
+            g = __shfl_sync(0xFFFFFFFFu, g, 0);
+            return sc.pool + (size_t)g * P2_GRANULE;
+        };
+        char *pg = take(pl);
+        TraceOut TO{reinterpret_cast<uint2 *>(pg), reinterpret_cast<uint32_t *>(pg + 2 * P2_GRANULE), nullptr, WIDE ? 0 : 16 * h, prm.hdr[q.x].max2[h]};
+        if (with_mp) TO.Mp = reinterpret_cast<uint32_t *>(take(4));
         switch (pl) {
         case 0:  sweep_window_trace<+1, MODE_TRACE_S, WIDE>(T, rings[w], tsm[w], lane, s, win, TO); break;
         case 1:  sweep_window_trace<+1, MODE_TRACE_M, WIDE>(T, rings[w], tsm[w], lane, s, win, TO); break;
@@ -422,7 +437,7 @@ age_enum_kernel(Pass2Params prm)
         const PairHdr hd = prm.hdr[item];
         for (int h = 0; h < 2; ++h) {
             if (!hd.need[h]) continue;
-            const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+            const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
             const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
@@ -460,7 +475,7 @@ age_blocks_kernel(Pass2Params prm)
         const PairHdr hd = prm.hdr[item];
         for (int h = 0; h < 2; ++h) {
             if (!hd.need[h]) continue;
-            const P2Scratch sc = carve_set(T, T.select ? 0 : h);
+            const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
             const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{O.n_bp, bp_s[w]};

@@ -34,8 +34,35 @@ template <bool WIDE> struct View {
     // ---- geometry --------------------------------------------------------------------------------
     __device__ int fstep(int q, int c) const { return (c - 1) / W + 1 + ((q & 255) >> 3); }          // forward step of cell (q+1, c)
     __device__ int rstep(int q, int c) const { return nb - (c - 1) / W + 31 - ((q & 255) >> 3); }    // reverse step
-    __device__ size_t slot(int q, int t) const { return ((size_t)(q >> 8) * nsteps + (t - 1)) * 32 + ((q & 255) >> 3); }
     __device__ bool interior(int r, int c) const { return r >= 1 && c >= 1 && r <= len2 && c <= len1; }
+
+    // ---- pages of the trace pool (P2Scratch) -------------------------------------------------------------
+    // page of `plane` (0 .. 3 codes, 4 = Mp) that holds step t of the strip of row q (no residency check)
+    __device__ __forceinline__ char *page(int plane, int q, int t) const {
+        return sc.pool + (size_t)sc.ptab[plane * sc.nwt + (q >> 8) * nwin + ((t - 1) >> 5)] * P2_GRANULE;
+    }
+    __device__ __forceinline__ int in_page(int q, int t) const { return ((t - 1) & 31) * 32 + ((q & 255) >> 3); }   // [step in window][lane]
+    __device__ __forceinline__ uint2 code_word(int plane, int q, int t) const { return reinterpret_cast<const uint2 *>(page(plane, q, t))[in_page(q, t)]; }
+    __device__ __forceinline__ uint32_t hot_at(int q, int t) const { return reinterpret_cast<const uint32_t *>(page(3, q, t) + 2 * P2_GRANULE)[in_page(q, t)]; }
+    // take a page for (plane, strip s, window win) from the pool: lane 0 bumps the counter; once the pool is exhausted every
+    // further page is the dump at its start and the host runs the batch again with a larger pool
+    __device__ char *take_page(int plane, int s, int win) const {
+        uint32_t g = 0;
+        if (lane == 0) {
+            const uint32_t n = (uint32_t)p2_page_granules(plane);
+            g = atomicAdd(sc.pool_next, n) + P2_DUMP_GRANULES;
+            if (g + n > sc.pool_granules) g = 0;
+            sc.ptab[plane * sc.nwt + s * nwin + win] = (int32_t)g;
+        }
+        g = __shfl_sync(0xFFFFFFFFu, g, 0);
+        return sc.pool + (size_t)g * P2_GRANULE;
+    }
+    __device__ TraceOut trace_out(int plane, int s, int win, bool with_mp) const {
+        char *pg = take_page(plane, s, win);
+        TraceOut TO{reinterpret_cast<uint2 *>(pg), reinterpret_cast<uint32_t *>(pg + 2 * P2_GRANULE), nullptr, sh(), max2};
+        if (with_mp) TO.Mp = reinterpret_cast<uint32_t *>(take_page(4, s, win));
+        return TO;
+    }
 
     // ---- on-demand trace windows ---------------------------------------------------------------------
     // planes: 0 = FS, 1 = FM, 2 = RS, 3 = RM (+ hot bits), 4 = reverse maxima (K7)
@@ -53,7 +80,7 @@ template <bool WIDE> struct View {
     __device__ __noinline__ void ensure(int plane, int s, int win, bool with_mp = false) const {
         if (valid(with_mp ? 4 : plane, s, win)) return;
         P2_PROF_T0(c0);
-        const TraceOut TO{sc.P[plane], sc.hot, with_mp ? sc.Mp : nullptr, sh(), max2};
+        const TraceOut TO = trace_out(plane, s, win, with_mp);
         switch (plane) {
         case 0:  sweep_window_trace<+1, MODE_TRACE_S, WIDE>(*T, *R, *X, lane, s, win, TO); break;
         case 1:  sweep_window_trace<+1, MODE_TRACE_M, WIDE>(*T, *R, *X, lane, s, win, TO); break;
@@ -105,7 +132,7 @@ template <bool WIDE> struct View {
         if (r < 1 || c < 1 || r > len2 || c > len1) return 0;
         if (c == 1) return pick(T->Rfirst[r]);
         const int q = r - 1, l = (q & 255) >> 3, k = q & 7, t = rstep(q, c), w = W * ((c - 1) / W + 1) - c;
-        return pick(sc.Mp[(((((size_t)(q >> 8) * nsteps + (t - 1)) * W + w) * 2 + (k >> 2)) * 32 + l) * 4 + (k & 3)]);
+        return pick(reinterpret_cast<const uint32_t *>(page(4, q, t))[((((((t - 1) & 31) * W + w) * 2 + (k >> 2)) * 32 + l) * 4) + (k & 3)]);
     }
 
     // ---- trace codes (no residency check: callers ensure first) ---------------------------------------------------
@@ -120,14 +147,14 @@ template <bool WIDE> struct View {
         if (r < 0 || c < 0 || r > len2 + 1 || c > len1 + 1) return T_STOP;
         if (!interior(r, c)) return plane == 1 ? FM_border(r, c) : (uint32_t)T_STOP;
         const int q = r - 1, rev = plane >> 1;
-        const uint2 v = sc.P[plane][slot(q, rev ? rstep(q, c) : fstep(q, c))];
+        const uint2 v = code_word(plane, q, rev ? rstep(q, c) : fstep(q, c));
         const int w = rev ? W * ((c - 1) / W + 1) - c : (c - 1) % W;
         return (((w < 2 ? v.x : v.y) >> (16 * (w & 1))) >> (2 * (q & 7))) & 3u;
     }
     __device__ bool hot_nc(int r, int c) const {          // reverse cell (r, c): Fmax[r-1][c-1] + Rmax[r][c] == max
         const int q = r - 1;
         const int w = W * ((c - 1) / W + 1) - c;
-        return (sc.hot[slot(q, rstep(q, c))] >> (8 * w + (q & 7))) & 1u;
+        return (hot_at(q, rstep(q, c)) >> (8 * w + (q & 7))) & 1u;
     }
     // Row scans, one block of four columns per lane (128 cells per pass instead of 32).  A plane word holds the codes of
     // 8 rows x 4 columns of one (lane, step) slot; word_codes() picks the row's four codes, 2 bits per block column w in
@@ -137,10 +164,10 @@ template <bool WIDE> struct View {
         return ((v.x >> sh) & 3u) | (((v.x >> (16 + sh)) & 3u) << 2) | (((v.y >> sh) & 3u) << 4) | (((v.y >> (16 + sh)) & 3u) << 6);
     }
     // codes of FM (plane 1) or FS (plane 0) at row r (1-based, interior) of the forward block with columns c1 .. c1+3 (c1 = 4m + 1)
-    __device__ __forceinline__ uint32_t fwd_codes(int plane, int r, int c1) const { return word_codes(sc.P[plane][slot(r - 1, fstep(r - 1, c1))], r - 1); }
+    __device__ __forceinline__ uint32_t fwd_codes(int plane, int r, int c1) const { return word_codes(code_word(plane, r - 1, fstep(r - 1, c1)), r - 1); }
     // codes of RM (plane 3) or RS (plane 2) at row r of the reverse block with columns c1 .. c1+3 (c1 = 4m + 1): column c1 + j is w = 3 - j
-    __device__ __forceinline__ uint32_t rev_codes(int plane, int r, int c1) const { return word_codes(sc.P[plane][slot(r - 1, rstep(r - 1, c1))], r - 1); }
-    __device__ __forceinline__ uint32_t hot_word(int r, int c) const { return sc.hot[slot(r - 1, rstep(r - 1, c))]; }     // of reverse cell (r, c)'s slot
+    __device__ __forceinline__ uint32_t rev_codes(int plane, int r, int c1) const { return word_codes(code_word(plane, r - 1, rstep(r - 1, c1)), r - 1); }
+    __device__ __forceinline__ uint32_t hot_word(int r, int c) const { return hot_at(r - 1, rstep(r - 1, c)); }     // of reverse cell (r, c)'s slot
 
     // Starting at (r, c) and stepping by (dr, dc): how many consecutive cells (at most 32) carry code t, and the
     // code of the first cell that does not (meaningful when the result is < 32).
@@ -413,11 +440,12 @@ __device__ void indel_row_ranges(const View<WIDE> &V, int *rlo, int *rhi, int la
         const int s = wi / T.nwin, win = wi % T.nwin;
         V.ensure(3, s, win);
         const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, T.nsteps);
+        const uint32_t *hotpage = reinterpret_cast<const uint32_t *>(V.page(3, s * STRIP, t0) + 2 * P2_GRANULE);   // [step in window][lane]
         uint32_t hw[CKS];
 #pragma unroll
         for (int i = 0; i < CKS; ++i) {                               // the lane's hot words of all steps of the window, in flight together
             const int t = t0 + i, bq = t - 31 + lane;                 // logical reverse block of this lane in step t
-            hw[i] = (t <= t1 && bq >= 1 && bq <= nb) ? __ldcg(V.sc.hot + ((size_t)s * T.nsteps + (t - 1)) * 32 + lane) : 0u;
+            hw[i] = (t <= t1 && bq >= 1 && bq <= nb) ? __ldcg(hotpage + i * 32 + lane) : 0u;
         }
         // the hot cells of a lane lie in its own 8 rows: column ranges are gathered in registers, no atomics
         int lo8[RPT], hi8[RPT];
@@ -602,16 +630,16 @@ __device__ int left_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_
         const int len = V.run_len(0, r, c, dr, dc, t, tn);
         r += len * dr; c += len * dc;
         if (t == T_DIAG) run += len;
-        else if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{c - len * dc + 1, r - len * dr + 1, run}; ++n; run = 0; }
+        else if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n_total - 1 - n] = Block{c - len * dc + 1, r - len * dr + 1, run}; ++n; run = 0; }
         t = len < 32 ? tn : V.code_at(0, r, c);
     }
-    if (run > 0) { if (dst && lane == 0) dst[n_total - 1 - n] = Block{c + 1, r + 1, run}; ++n; }
-    return n;
+    if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n_total - 1 - n] = Block{c + 1, r + 1, run}; ++n; }
+    return n;       // (n <= n_total unless the trace pool overflowed between the counting and the writing pass: the batch is run again then)
 }
 
 // K12 findRightBlocks (:810-860)
 template <bool WIDE>
-__device__ int right_blocks(const View<WIDE> &V, int c, int r, Block *dst, int lane)
+__device__ int right_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_total, int lane)
 {
     int n = 0, run = 0, s1 = 0, s2 = 0;
     uint32_t t = V.code_at(2, r, c);
@@ -620,27 +648,30 @@ __device__ int right_blocks(const View<WIDE> &V, int c, int r, Block *dst, int l
         uint32_t tn;
         const int len = V.run_len(2, r, c, dr, dc, t, tn);
         if (t == T_DIAG) { if (run == 0) { s1 = c; s2 = r; } run += len; }     // interior cells only (:820 always holds)
-        else if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
+        else if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
         r += len * dr; c += len * dc;
         t = len < 32 ? tn : V.code_at(2, r, c);
     }
-    if (run > 0) { if (dst && lane == 0) dst[n] = Block{s1, s2, run}; ++n; }
+    if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n] = Block{s1, s2, run}; ++n; }
     return n;
 }
 
-__device__ __forceinline__ P2Scratch carve_set(const PairTask &T, int set)
+__device__ __forceinline__ P2Scratch carve_set(const PairTask &T, int set, char *tpool, uint32_t tpool_granules, uint32_t *tpool_next)
 {
-    const size_t slots = (size_t)T.nstrips * T.nsteps, nwt = (size_t)T.nstrips * T.nwin;
+    const size_t nwt = (size_t)T.nstrips * T.nwin;
     char *base = T.p2set + (size_t)set * T.p2stride;
     P2Scratch sc;
-    for (int i = 0; i < 4; ++i) { sc.P[i] = (uint2 *)base; base += p2_up(slots * 32 * 8); }
-    sc.hot = (uint32_t *)base; base += p2_up(slots * 32 * 4);
-    sc.Mp = T.k7 ? (uint32_t *)base : nullptr; base += T.k7 ? p2_up(slots * W * 2 * 32 * 16) : 0;
-    sc.vwords = (int)p2_vwords(nwt);
+    sc.ptab = (int32_t *)base; base += p2_up(5 * nwt * 4);
+    sc.pool = tpool; sc.pool_granules = tpool_granules; sc.pool_next = tpool_next;
+    sc.vwords = (int)p2_vwords(nwt); sc.nwt = (int)nwt;
     sc.valid = (uint32_t *)base; base += p2_up((size_t)9 * sc.vwords * 4);
     sc.rowrange = (int32_t *)base; base += p2_up(2 * ((size_t)T.len2 + 2) * 4);
     sc.hotlist = (int32_t *)base;
     return sc;
+}
+__device__ __forceinline__ P2Scratch carve_set(const PairTask &T, int set, const Pass2Params &prm)
+{
+    return carve_set(T, set, prm.tpool, prm.tpool_granules, prm.tpool_next);
 }
 
 // Split maxima of both halves (:545-550 / :476-481) and the -both / -inv selection (age_align.cpp:273 /
@@ -884,11 +915,11 @@ __device__ void emit_blocks(const View<WIDE> &V, int flag, const BpList &L, Alig
         int idx = 0, nl = 0, nr = 0;
         if (which == 0) {
             nl = left_blocks(V, L.bp[0][0], L.bp[0][1], nullptr, 0, lane);
-            nr = right_blocks(V, L.bp[0][2], L.bp[0][3], nullptr, lane);
+            nr = right_blocks(V, L.bp[0][2], L.bp[0][3], nullptr, 0, lane);
         } else {
             for (idx = L.n - 1; idx >= 1; --idx) {
                 nl = left_blocks(V, L.bp[idx][0], L.bp[idx][1], nullptr, 0, lane);
-                nr = right_blocks(V, L.bp[idx][2], L.bp[idx][3], nullptr, lane);
+                nr = right_blocks(V, L.bp[idx][2], L.bp[idx][3], nullptr, 0, lane);
                 if (nl + nr > 0) break;
             }
             if (idx < 1) { nl = nr = 0; idx = -1; }
@@ -900,7 +931,7 @@ __device__ void emit_blocks(const View<WIDE> &V, int flag, const BpList &L, Alig
             off = __shfl_sync(0xFFFFFFFFu, off, 0);
             if (off + nl + nr <= pool_cap) {
                 left_blocks(V, L.bp[idx][0], L.bp[idx][1], pool + off, nl, lane);
-                right_blocks(V, L.bp[idx][2], L.bp[idx][3], pool + off + nl, lane);
+                right_blocks(V, L.bp[idx][2], L.bp[idx][3], pool + off + nl, nr, lane);
                 if (which == 0) alignment_numbers(V, flag, pool + off, nl, pool + off + nl, nr, O, lane);
             } else if (lane == 0) O.status = -4;          // pool overflow: host retries with a larger pool
         } else if (which == 0 && lane < CALL_N) O.call[lane] = 0;

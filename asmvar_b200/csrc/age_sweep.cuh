@@ -150,9 +150,9 @@ __device__ __forceinline__ void dstage_init(DStage &DS, int lane)
 #endif
 }
 
-struct TraceOut {                           // trace re-sweep outputs (one half of the pair, one kind of trace)
-    uint2 *P;                               // 2-bit codes: [slot][lane], 16 bits per block column, 2 bits per row
-    uint32_t *hot;                          // MODE_TRACE_M, reverse: bit 8w+k = the cell holds Fmax + Rmax == max
+struct TraceOut {                           // trace re-sweep outputs (one half of the pair, one kind of trace): pages of ONE window
+    uint2 *P;                               // 2-bit codes: [step in window][lane], 16 bits per block column, 2 bits per row
+    uint32_t *hot;                          // MODE_TRACE_M, reverse: [step in window][lane], bit 8w+k = the cell holds Fmax + Rmax == max
     uint32_t *Mp;                           // MODE_TRACE_M, reverse, optional: the running maxima themselves (K7 rows)
     int sh;                                 // 0 / 16: the half whose trace is wanted
     int max2;
@@ -725,7 +725,7 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
         for (int w = 0; w < W; ++w) { X.uH[w][lane] = uH[w]; X.uG[w][lane] = uG[w]; X.uM[w][lane] = uM[w]; }
         __syncwarp();
         if (b < 1 || b > nb) continue;
-        const size_t slot = C.sbase + (size_t)(t - 1);
+        const int slot = t - t0;                  // step within the window: index into the window's pages
         uint32_t hotw = 0;
         uint32_t dg = S.pH;
 #pragma unroll 1
@@ -797,7 +797,7 @@ __device__ __forceinline__ void sweep_window_compact(const StripCtx<DIR> &C, Lan
             X.oH[w][lane] = S.Hl[last]; X.oG[w][lane] = S.Gl[last]; X.oM[w][lane] = S.Ml[last];
             X.tw[w][lane] = codes;
             if (TRACE_M && !FWD && TO.Mp) {
-                uint4 *dst = reinterpret_cast<uint4 *>(TO.Mp) + (slot * W + w) * 64 + lane;
+                uint4 *dst = reinterpret_cast<uint4 *>(TO.Mp) + (slot * W + w) * 64 + lane;      // (step, column) -> 2 x 32 uint4
                 dst[0]  = make_uint4(S.Ml[0], S.Ml[1], S.Ml[2], S.Ml[3]);
                 dst[32] = make_uint4(S.Ml[4], S.Ml[5], S.Ml[6], S.Ml[7]);
             }

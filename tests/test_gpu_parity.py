@@ -180,12 +180,14 @@ def test_two_devices_same_results(eng):
 
 
 @pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_DFMT": "raw"}, {"AGE_DFMT": "raw", "AGE_LONG_NW": "1"},
-                                  {"AGE_QUEUE_CAP": "4"}, {"AGE_QUEUE_CAP": "4", "AGE_LONG_NW": "1"}])
+                                  {"AGE_QUEUE_CAP": "4"}, {"AGE_QUEUE_CAP": "4", "AGE_LONG_NW": "1"}, {"AGE_TRACE_POOL_GRANULES": "400"},
+                                  {"AGE_TRACE_POOL_GRANULES": "400", "AGE_QUEUE_CAP": "4"}])
 def test_golden_records_other_kernel_paths(eng, knob, monkeypatch):
     """The same golden batch through the code paths a small batch does not take by itself: one warp per pair
     (the kernel large batches use), 16 warps per pair (long alignments), a work list too short for the
-    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand, and the 16-bit storage format of the
-    forward-maxima plane (by default only scorings with match or mismatch above 15 use it)."""
+    pre-sweeps, so that pass 2 re-sweeps nearly every window on demand, the 16-bit storage format of the
+    forward-maxima plane (by default only scorings with match or mismatch above 15 use it), and a trace pool far too
+    small for the batch: the engine notices the overflow and runs the batch again with a larger pool."""
     for k, v in knob.items():
         monkeypatch.setenv(k, v)
     jobs, owner = [], []
