@@ -147,7 +147,7 @@ __host__ __device__ inline size_t p2_full_granules(size_t nwt, int k7) { return 
 // the pool, 3: granules taken from the trace pool, the rest: work counters of the pass-2 kernels).
 struct BatchLaunch {
     const PairTask *pairs; int32_t n_pairs, n_wide;
-    int32_t nw, nw_wide;                                // warps per pair in the sweep of the packed / wide pairs (sweep_warps_per_pair)
+    int32_t nw, nw_wide, cs, cs_wide;                   // warps per CTA and CTAs per cluster that share a pair in the sweep (sweep_plan)
     AlignerOut *outs; Block *pool; int32_t pool_cap;
     int32_t *counters;
     PairHdr *hdr; uint2 *queue; int32_t queue_cap;
@@ -156,7 +156,7 @@ struct BatchLaunch {
 
 // launchers (age_kernels.cu)
 void launch_pack(const PairTask *d_pairs, int n_pairs, cudaStream_t st);
-int  sweep_warps_per_pair(int n_pairs, int max_strips);
+void sweep_plan(int n_pairs, int max_strips, int *nw, int *cs);
 void launch_sweeps(const BatchLaunch &b, cudaStream_t st);
 void launch_pass2(const BatchLaunch &b, cudaStream_t st);
 int  launches_per_batch(const BatchLaunch &b);          // kernels the two calls above start

@@ -98,7 +98,7 @@ struct Slot {
     std::vector<int> pair_ids;   // the sub-batch resident in this slot: wide pairs first, then longest first
     std::vector<PairTask> tasks;
     std::vector<size_t> sc_off;
-    int n_outs = 0, pool_cap = 0, queue_cap = 0, n_wide = 0, nw = 1, nw_wide = 1, launches = 0;
+    int n_outs = 0, pool_cap = 0, queue_cap = 0, n_wide = 0, nw = 1, nw_wide = 1, cs = 1, cs_wide = 1, launches = 0;
     size_t in_bytes = 0, out_bytes = 0, sc_bytes = 0;
     size_t tpool_off = 0, tpool_full = 0; uint32_t tpool_granules = 0;   // trace pool of the sub-batch: behind the pairs' scratch
 };
@@ -382,8 +382,8 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
         nwt_total += (size_t)hp.nstrips * hp.nwin * hp.nsets;
         for (int k = 0; k < 2; ++k) if (hp.a[k] >= 0) B.aligners[hp.a[k]].out = n_outs++;
     }
-    sl.nw = sweep_warps_per_pair((int)np - sl.n_wide, ms);
-    sl.nw_wide = sweep_warps_per_pair(sl.n_wide, ms_wide);
+    sweep_plan((int)np - sl.n_wide, ms, &sl.nw, &sl.cs);
+    sweep_plan(sl.n_wide, ms_wide, &sl.nw_wide, &sl.cs_wide);
     sl.n_outs = n_outs;
     // the trace pool of the sub-batch behind the scratch of its pairs
     size_t share = 0;
@@ -440,7 +440,7 @@ bool run_on_device(Device &dev, Slot &sl)
     OutLayout L = out_layout(sl, sl.outbuf.ptr);
     CK(cudaEventRecord(sl.ev[2], dev.st));
     BatchLaunch b{};
-    b.pairs = (const PairTask *)sl.in.ptr; b.n_pairs = (int)sl.tasks.size(); b.n_wide = sl.n_wide; b.nw = sl.nw; b.nw_wide = sl.nw_wide;
+    b.pairs = (const PairTask *)sl.in.ptr; b.n_pairs = (int)sl.tasks.size(); b.n_wide = sl.n_wide; b.nw = sl.nw; b.nw_wide = sl.nw_wide; b.cs = sl.cs; b.cs_wide = sl.cs_wide;
     b.outs = L.outs; b.pool = L.pool; b.pool_cap = sl.pool_cap; b.counters = L.counters;
     b.hdr = (PairHdr *)sl.aux.ptr;
     b.queue = (uint2 *)(sl.aux.ptr + align_up(sl.tasks.size() * sizeof(PairHdr), 256)); b.queue_cap = sl.queue_cap;

@@ -15,6 +15,7 @@
 //                    the sweep over the one window that holds it (MODE_TRACE), from that window's checkpoint.
 #include "age_pass2.cuh"
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <cstdlib>
 #include <cstdio>
 #include <algorithm>
@@ -140,78 +141,109 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
     }
 }
 
-// Long alignments / small batches: the NW warps of a CTA share one pair and run its strips as a pipeline
-// (warp w owns strips w, w + NW, ...; strip si trails strip si-1 by 32+ steps through the boundary rows in global memory).
+// Long alignments / small batches: several warps share one pair and run its strips as a pipeline (warp g of the group owns
+// strips g, g + G, ...; strip si trails strip si-1 by 32+ steps through the boundary rows in global memory).  The group is
+// the NW warps of a CTA -- or, when even 16 warps per pair leave SMs without work (a few dozen long pairs), the warps of a
+// thread-block cluster of 2 or 4 CTAs on neighbouring SMs: the strips' progress counters and the work item then live in the
+// shared memory of the cluster's first CTA and the others reach them through distributed shared memory.
 constexpr int MAX_STRIPS_LONG = 128;
 
 template <bool WIDE>
 __global__ void __launch_bounds__(512, 1)
 age_sweep_long_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
 {
+    namespace cg = cooperative_groups;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SweepSmem *sm = reinterpret_cast<SweepSmem *>(smem_raw);
-    __shared__ int prog[MAX_STRIPS_LONG];
-    __shared__ int s_item;
+    __shared__ int prog_own[MAX_STRIPS_LONG];
+    __shared__ int item_own;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();
+    int *prog = cluster.map_shared_rank(prog_own, 0);        // of the cluster's first CTA (our own when there is no cluster)
+    int *item_p = cluster.map_shared_rank(&item_own, 0);
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int g = rank * nw + w, G = nw * cs;                // this warp in the group that shares the pair
     dstage_init(sm[w].dstage, lane);
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_item = atomicAdd(counter, 1);
-        for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog[i] = 0;
-        __syncthreads();
-        const int item = s_item;
+        cluster.sync();
+        if (rank == 0) {
+            if (threadIdx.x == 0) item_own = atomicAdd(counter, 1);
+            for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog_own[i] = 0;
+        }
+        cluster.sync();
+        const int item = *reinterpret_cast<volatile int *>(item_p);
         if (item >= n_pairs) break;
         const PairTask &T = pairs[item];
-        sweep_pair_fast<+1, WIDE>(T, sm[w].rings, sm[w].dstage, lane, w, nw, prog);
+        sweep_pair_fast<+1, WIDE>(T, sm[w].rings, sm[w].dstage, lane, g, G, prog);
         __threadfence();
-        __syncthreads();
-        for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog[i] = 0;
-        __syncthreads();
-        sweep_pair_fast<-1, WIDE>(T, sm[w].rings, sm[w].dstage, lane, w, nw, prog);
+        cluster.sync();
+        if (rank == 0) for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog_own[i] = 0;
+        cluster.sync();
+        sweep_pair_fast<-1, WIDE>(T, sm[w].rings, sm[w].dstage, lane, g, G, prog);
         cp_async_wait_all();
     }
+    cluster.sync();                                          // nobody leaves while a neighbour may still read its shared memory
 }
 
 // Warps that share one pair in the sweep of a sub-batch.  From sms * 16 pairs on, one warp per pair fills the GPU (the
-// persistent kernel).  Below that each pair is shared by nw = 2 .. 16 warps of one CTA (age_sweep_long_kernel, 16 / nw CTAs
-// per SM): the nw is taken that keeps most of the SMs' warp slots busy -- pairs in flight x nw over the slots of the waves
-// they need, times the share of a pair's strip rounds that all nw warps work in; ties go to the smaller nw, whose pipeline
-// has fewer fill and drain steps.
-int sweep_warps_per_pair(int n_pairs, int max_strips)
+// persistent kernel).  Below that each pair is shared by nw = 2 .. 16 warps of one CTA, times cs = 1, 2 or 4 CTAs of a
+// cluster (age_sweep_long_kernel): the combination is taken that keeps most of the SMs' warp slots busy -- pairs in flight
+// x warps over the slots of the waves they need, times the share of a pair's strip rounds that all its warps work in; ties
+// go to the smaller group, whose pipeline has fewer fill and drain steps.
+void sweep_plan(int n_pairs, int max_strips, int *nw_out, int *cs_out)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;   // test knob: 1 = one warp per pair, 2..16 = pipelined
-    if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) return max_strips > MAX_STRIPS_LONG ? 1 : force_nw;
-    if (n_pairs <= 0 || n_pairs >= sms * 16 || max_strips > MAX_STRIPS_LONG) return 1;
-    int best = 1;
-    double best_score = 0;
-    for (int nw = 1; nw <= 16 && nw <= std::max(1, max_strips); nw *= 2) {
-        const int cap = sms * (16 / nw);                                  // CTAs (pairs) in flight
-        const int waves = (n_pairs + cap - 1) / cap, rounds = (max_strips + nw - 1) / nw;
-        const double score = (double)n_pairs / ((double)waves * cap) * ((double)max_strips / ((double)rounds * nw));
-        if (score > best_score * 1.0001) { best_score = score; best = nw; }
+    *nw_out = 1; *cs_out = 1;
+    const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;   // test knobs: 1 = one warp per pair, 2..16 = pipelined,
+    const int force_cs = getenv("AGE_LONG_CS") ? atoi(getenv("AGE_LONG_CS")) : 0;   // clusters of 2 / 4 CTAs
+    if (max_strips > MAX_STRIPS_LONG) return;
+    if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) {
+        *nw_out = force_nw;
+        if (force_nw > 1 && (force_cs == 2 || force_cs == 4)) *cs_out = force_cs;
+        return;
     }
-    return best;
+    if (n_pairs <= 0 || n_pairs >= sms * 16) return;
+    double best_score = 0;
+    for (int cs = 1; cs <= 4; cs *= 2)
+        for (int nw = 1; nw <= 16; nw *= 2) {
+            const int G = nw * cs;
+            if ((G > 1 && G / 2 >= std::max(1, max_strips)) || (cs > 1 && nw < 8)) continue;     // clusters only of large CTAs
+            const int cap = std::max(1, sms * (16 / nw) / cs);                                     // pairs in flight
+            const int waves = (n_pairs + cap - 1) / cap, rounds = (max_strips + G - 1) / G;
+            const double score = (double)n_pairs / ((double)waves * cap) * ((double)max_strips / ((double)rounds * G));
+            if (score > best_score * 1.0001) { best_score = score; *nw_out = nw; *cs_out = cs; }
+        }
 }
 
 template <bool WIDE>
-static void launch_sweeps_t(const PairTask *d_pairs, int n_pairs, int nw, int32_t *d_counter, cudaStream_t st)
+static void launch_sweeps_t(const PairTask *d_pairs, int n_pairs, int nw, int cs, int32_t *d_counter, cudaStream_t st)
 {
     if (n_pairs <= 0) return;
-    if (nw > 1) {
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int smem = nw * (int)sizeof(SweepSmem);
-        cudaFuncSetAttribute(age_sweep_long_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        age_sweep_long_kernel<WIDE><<<std::min(n_pairs, sms * (16 / nw)), nw * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
-        return;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (nw > 1) {
+        const int smem = nw * (int)sizeof(SweepSmem);
+        cudaFuncSetAttribute(age_sweep_long_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = (unsigned)cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.blockDim = dim3((unsigned)nw * 32); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int groups = sms * (16 / nw) / cs;                                 // resident groups: persistent, the counter feeds them
+        if (cs > 1) {
+            cfg.gridDim = dim3((unsigned)(sms * (16 / nw)));
+            int fit = 0;
+            if (cudaOccupancyMaxActiveClusters(&fit, age_sweep_long_kernel<WIDE>, &cfg) == cudaSuccess && fit > 0) groups = std::min(groups, fit);
+            else cudaGetLastError();
+        }
+        cfg.gridDim = dim3((unsigned)(std::min(n_pairs, std::max(1, groups)) * cs));
+        cudaLaunchKernelEx(&cfg, age_sweep_long_kernel<WIDE>, d_pairs, n_pairs, d_counter);
+        return;
+    }
     const int blocks = std::min((n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * SWEEP_OCC);   // persistent: the work counter feeds the warps
     const int smem = SWEEP_WARPS * (int)sizeof(SweepSmem);
     cudaFuncSetAttribute(age_sweep_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -224,8 +256,8 @@ template <bool WIDE> static void launch_pass2_t(const Pass2Params &p, cudaStream
 void launch_sweeps(const BatchLaunch &b, cudaStream_t st)
 {
     cudaMemsetAsync(b.counters, 0, 32 * sizeof(int32_t), st);
-    if (b.n_wide > 0) launch_sweeps_t<true>(b.pairs, b.n_wide, b.nw_wide, b.counters + 16, st);
-    if (b.n_pairs > b.n_wide) launch_sweeps_t<false>(b.pairs + b.n_wide, b.n_pairs - b.n_wide, b.nw, b.counters + 0, st);
+    if (b.n_wide > 0) launch_sweeps_t<true>(b.pairs, b.n_wide, b.nw_wide, b.cs_wide, b.counters + 16, st);
+    if (b.n_pairs > b.n_wide) launch_sweeps_t<false>(b.pairs + b.n_wide, b.n_pairs - b.n_wide, b.nw, b.cs, b.counters + 0, st);
 }
 
 // Pass 2 of a sub-batch on `st`: select -> pre-sweep -> enumerate -> pre-sweep -> blocks, per kind of pair

@@ -65,7 +65,11 @@ def test_c4_inversions_20kb(eng, flag):
         assert not diff_summary(r, want), diff_summary(r, want)
 
 
-def test_c5_long_sv_50kb(eng):
+@pytest.mark.parametrize("knob", [{}, {"AGE_LONG_NW": "16", "AGE_LONG_CS": "2"}, {"AGE_LONG_NW": "16", "AGE_LONG_CS": "4"}])
+def test_c5_long_sv_50kb(eng, knob, monkeypatch):
+    """40 strips per pair: by default two pairs get clusters of CTAs; forced: 32 and 64 warps per pair"""
+    for k, v in knob.items():
+        monkeypatch.setenv(k, v)
     check_both_against_oracle(eng, synth.long_sv_candidates(2, seed=1005), capi.INDEL_FLAG)
 
 

@@ -181,13 +181,15 @@ def test_two_devices_same_results(eng):
 
 @pytest.mark.parametrize("knob", [{"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_DFMT": "raw"}, {"AGE_DFMT": "raw", "AGE_LONG_NW": "1"},
                                   {"AGE_QUEUE_CAP": "4"}, {"AGE_QUEUE_CAP": "4", "AGE_LONG_NW": "1"}, {"AGE_TRACE_POOL_GRANULES": "400"},
-                                  {"AGE_TRACE_POOL_GRANULES": "400", "AGE_QUEUE_CAP": "4"}])
+                                  {"AGE_TRACE_POOL_GRANULES": "400", "AGE_QUEUE_CAP": "4"}, {"AGE_LONG_NW": "8", "AGE_LONG_CS": "2"},
+                                  {"AGE_LONG_NW": "16", "AGE_LONG_CS": "4"}])
 def test_golden_records_other_kernel_paths(eng, knob, monkeypatch):
     """The same golden batch through the code paths a small batch does not take by itself: one warp per pair
     (the kernel large batches use), 16 warps per pair (long alignments), a work list too short for the
     pre-sweeps, so that pass 2 re-sweeps nearly every window on demand, the 16-bit storage format of the
     forward-maxima plane (by default only scorings with match or mismatch above 15 use it), and a trace pool far too
-    small for the batch: the engine notices the overflow and runs the batch again with a larger pool."""
+    small for the batch: the engine notices the overflow and runs the batch again with a larger pool; thread-block
+    clusters of 2 / 4 CTAs sharing one pair (what a few dozen very long pairs get)."""
     for k, v in knob.items():
         monkeypatch.setenv(k, v)
     jobs, owner = [], []

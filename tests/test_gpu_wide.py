@@ -37,7 +37,7 @@ def golden_batch_matches(eng):
     return bad
 
 
-@pytest.mark.parametrize("knob", [{}, {"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_QUEUE_CAP": "4"}, {"AGE_QUEUE_CAP": "4", "AGE_LONG_NW": "1"}, {"AGE_TRACE_POOL_GRANULES": "400"}])
+@pytest.mark.parametrize("knob", [{}, {"AGE_LONG_NW": "1"}, {"AGE_LONG_NW": "16"}, {"AGE_QUEUE_CAP": "4"}, {"AGE_QUEUE_CAP": "4", "AGE_LONG_NW": "1"}, {"AGE_TRACE_POOL_GRANULES": "400"}, {"AGE_LONG_NW": "8", "AGE_LONG_CS": "2"}])
 def test_golden_records_forced_wide(eng, knob, monkeypatch):
     """all 247 reference records through the 32-bit kernels"""
     monkeypatch.setenv("AGE_FORCE_WIDE", "1")
