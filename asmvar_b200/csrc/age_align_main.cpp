@@ -465,14 +465,14 @@ int mode_count(int flag)
     return n;
 }
 
-// candidates per batch and device: 2.5 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
+// candidates per batch and device: 3 pairs per resident warp of a B200 (148 SMs x 16 warps); see DESIGN.md
 size_t device_count()
 {
     size_t n = 0;
     if (const char *e = getenv("AGE_DEVICES")) { stringstream ss(e); string tok; while (getline(ss, tok, ',')) if (!tok.empty()) ++n; }
     return n ? n : 1;
 }
-const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 5920 * device_count()); }();
+const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 7104 * device_count()); }();
 
 // ---------------------------------------------------------------------------------------------------------
 // batch dialect (age_align.cpp)

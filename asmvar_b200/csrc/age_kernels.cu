@@ -148,7 +148,7 @@ age_sweep_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *count
 // shared memory of the cluster's first CTA and the others reach them through distributed shared memory.
 constexpr int MAX_STRIPS_LONG = 128;
 
-template <bool WIDE>
+template <bool WIDE, bool CLUSTER>
 __global__ void __launch_bounds__(512, 1)
 age_sweep_long_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *counter)
 {
@@ -157,32 +157,39 @@ age_sweep_long_kernel(const PairTask *__restrict__ pairs, int n_pairs, int32_t *
     SweepSmem *sm = reinterpret_cast<SweepSmem *>(smem_raw);
     __shared__ int prog_own[MAX_STRIPS_LONG];
     __shared__ int item_own;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();
-    int *prog = cluster.map_shared_rank(prog_own, 0);        // of the cluster's first CTA (our own when there is no cluster)
-    int *item_p = cluster.map_shared_rank(&item_own, 0);
+    // one CTA per pair: plain shared memory and __syncthreads (a cluster of one through the cluster API measured 12 % slower);
+    // a cluster per pair: counters and work item of the first CTA through distributed shared memory, cluster barriers
+    int rank = 0, cs = 1;
+    int *prog = prog_own, *item_p = &item_own;
+    if (CLUSTER) {
+        cg::cluster_group cluster = cg::this_cluster();
+        rank = (int)cluster.block_rank(); cs = (int)cluster.num_blocks();
+        prog = cluster.map_shared_rank(prog_own, 0);
+        item_p = cluster.map_shared_rank(&item_own, 0);
+    }
+    auto sync_all = [&]() { if (CLUSTER) cg::this_cluster().sync(); else __syncthreads(); };
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int g = rank * nw + w, G = nw * cs;                // this warp in the group that shares the pair
     dstage_init(sm[w].dstage, lane);
     for (;;) {
-        cluster.sync();
+        sync_all();
         if (rank == 0) {
             if (threadIdx.x == 0) item_own = atomicAdd(counter, 1);
             for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog_own[i] = 0;
         }
-        cluster.sync();
+        sync_all();
         const int item = *reinterpret_cast<volatile int *>(item_p);
         if (item >= n_pairs) break;
         const PairTask &T = pairs[item];
         sweep_pair_fast<+1, WIDE>(T, sm[w].rings, sm[w].dstage, lane, g, G, prog);
         __threadfence();
-        cluster.sync();
+        sync_all();
         if (rank == 0) for (int i = threadIdx.x; i < MAX_STRIPS_LONG; i += blockDim.x) prog_own[i] = 0;
-        cluster.sync();
+        sync_all();
         sweep_pair_fast<-1, WIDE>(T, sm[w].rings, sm[w].dstage, lane, g, G, prog);
         cp_async_wait_all();
     }
-    cluster.sync();                                          // nobody leaves while a neighbour may still read its shared memory
+    if (CLUSTER) cg::this_cluster().sync();                  // nobody leaves while a neighbour may still read its shared memory
 }
 
 // Warps that share one pair in the sweep of a sub-batch.  From sms * 16 pairs on, one warp per pair fills the GPU (the
@@ -224,9 +231,15 @@ static void launch_sweeps_t(const PairTask *d_pairs, int n_pairs, int nw, int cs
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (nw > 1 && cs == 1) {
+        const int smem = nw * (int)sizeof(SweepSmem);
+        cudaFuncSetAttribute(age_sweep_long_kernel<WIDE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        age_sweep_long_kernel<WIDE, false><<<std::min(n_pairs, sms * (16 / nw)), nw * 32, smem, st>>>(d_pairs, n_pairs, d_counter);
+        return;
+    }
     if (nw > 1) {
         const int smem = nw * (int)sizeof(SweepSmem);
-        cudaFuncSetAttribute(age_sweep_long_kernel<WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(age_sweep_long_kernel<WIDE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
@@ -234,14 +247,12 @@ static void launch_sweeps_t(const PairTask *d_pairs, int n_pairs, int nw, int cs
         cfg.blockDim = dim3((unsigned)nw * 32); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
         cfg.attrs = &attr; cfg.numAttrs = 1;
         int groups = sms * (16 / nw) / cs;                                 // resident groups: persistent, the counter feeds them
-        if (cs > 1) {
-            cfg.gridDim = dim3((unsigned)(sms * (16 / nw)));
-            int fit = 0;
-            if (cudaOccupancyMaxActiveClusters(&fit, age_sweep_long_kernel<WIDE>, &cfg) == cudaSuccess && fit > 0) groups = std::min(groups, fit);
-            else cudaGetLastError();
-        }
+        cfg.gridDim = dim3((unsigned)(sms * (16 / nw)));
+        int fit = 0;
+        if (cudaOccupancyMaxActiveClusters(&fit, age_sweep_long_kernel<WIDE, true>, &cfg) == cudaSuccess && fit > 0) groups = std::min(groups, fit);
+        else cudaGetLastError();
         cfg.gridDim = dim3((unsigned)(std::min(n_pairs, std::max(1, groups)) * cs));
-        cudaLaunchKernelEx(&cfg, age_sweep_long_kernel<WIDE>, d_pairs, n_pairs, d_counter);
+        cudaLaunchKernelEx(&cfg, age_sweep_long_kernel<WIDE, true>, d_pairs, n_pairs, d_counter);
         return;
     }
     const int blocks = std::min((n_pairs + SWEEP_WARPS - 1) / SWEEP_WARPS, sms * SWEEP_OCC);   // persistent: the work counter feeds the warps

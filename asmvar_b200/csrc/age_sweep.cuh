@@ -107,10 +107,19 @@ __device__ __forceinline__ int subst2(int xc, int yc, int m2, int mm2)
 // OFF8 format of D (age_device.cuh): the entries of one (lane, block column) are `base` (row k = 0) and Ml[0..6] (k = 1..7).
 // Word j holds rows 2j and 2j+1 as bytes {A_2j, A_2j+1, B_2j, B_2j+1} = offset(2j) + 256 * offset(2j+1) on the packed pairs:
 // one multiply-add per word on the FMA pipe (the ALU pipe is the one the recurrence saturates).
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 __device__ __forceinline__ uint4 d8_encode(uint32_t base, const uint32_t (&Ml)[RPT])
-{   // neither half can borrow: the maxima grow with the row
-    return make_uint4((Ml[0] - base) * 256u, (Ml[2] - base) * 256u + (Ml[1] - base),
-                      (Ml[4] - base) * 256u + (Ml[3] - base), (Ml[6] - base) * 256u + (Ml[5] - base));
+{   // (Ml[2j] - base) * 256 + (Ml[2j-1] - base) = Ml[2j] * 256 + Ml[2j-1] - 257 * base in the ring of 32-bit words: nothing but
+    // multiply-adds, none of them on the ALU pipe (seven packed subtractions per column before).  Neither half can borrow in
+    // the result: the maxima grow with the row, every offset is >= 0.
+    const uint32_t nb256 = base * 0xFFFFFF00u, nb257 = base * 0xFFFFFEFFu;          // -256 * base, -257 * base
+    return make_uint4(mad_u32(Ml[0], 256u, nb256), mad_u32(Ml[1], 1u, mad_u32(Ml[2], 256u, nb257)),
+                      mad_u32(Ml[3], 1u, mad_u32(Ml[4], 256u, nb257)), mad_u32(Ml[5], 1u, mad_u32(Ml[6], 256u, nb257)));
 }
 __device__ __forceinline__ uint32_t d8_offset(const uint4 &o, int k)       // packed offset of row k (0 in the upper bytes)
 {

@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
 
-A step is one pass of the hot path over one batch of B synthetic candidates of configuration C2
+A step is one pass of the hot path over one batch of B (default 7104) synthetic candidates of configuration C2
 (5 kb reference windows, 2 x 500 bp contig flanks, -indel -both, scoring 1/-1/-10/-1).
 Each rank (one process per GPU, torchrun) aligns its own shard -- candidates are independent, there is no
 data-path collective -- so scaling is weak and `value` is the candidates all ranks finished / the max time.
@@ -347,13 +347,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=5920, help="candidates per step per GPU (5920 = 2.5 pairs per resident warp: 148 SMs x 16 warps; about 137 GB of scratch)")
+    ap.add_argument("--batch", type=int, default=0, help="candidates per step per GPU (default 7104 for C2 = 3 pairs per resident warp: 148 SMs x 16 warps, about 125 GB of scratch; "
+                                                          "296 for C4, 72 for C5)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cli", action="store_true", help="skip the age_align process leg (FASTA in -> .age out)")
     ap.add_argument("--no-extra", action="store_true", help="skip the C4 / C5 legs")
     ap.add_argument("--no-inproc", action="store_true", help="skip the in-process multi-device leg")
-    ap.add_argument("--cli-candidates", type=int, default=100640, help="candidates of the age_align process leg (C2 asks for N = 100 000; 17 chunks of 5920)")
+    ap.add_argument("--cli-candidates", type=int, default=100640, help="candidates of the age_align process leg (C2 asks for N = 100 000)")
     ap.add_argument("--cpu-sample", type=int, default=1024, help="candidates of the cpu_baseline leg")
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 (default, the configuration the metric is quoted on); c4 = -inv 20 kb x 4 kb; c5 = 50 kb x 10 kb -indel -both")
@@ -377,6 +378,8 @@ def main():
         dist.barrier()
     from asmvar_b200 import capi, engine
 
+    if args.batch <= 0:
+        args.batch = {"c2": 7104, "c4": 296, "c5": 72}[args.workload]
     cands, jobs, aligners, mode_opts = workload_jobs(args.workload, args.batch, rank)
     cu = cell_updates(cands, aligners)
     eng = engine.Engine([local])
@@ -474,7 +477,7 @@ def main():
 
     if rank == 0 and not args.no_extra and args.workload == "c2":
         extra = {}
-        for name, batch in (("c4", 192), ("c5", 72)):
+        for name, batch in (("c4", 296), ("c5", 72)):
             try:
                 xc, xj, xa, xm = workload_jobs(name, batch)
                 with engine.Engine([local]) as xe:
