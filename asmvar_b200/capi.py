@@ -128,7 +128,7 @@ class AgeStats(C.Structure):
     _fields_ = [
         ("kernel_ms", C.c_double), ("fill_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
         ("cell_updates", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("launches", C.c_uint64), ("fill_launches", C.c_uint64), ("n_aligners", C.c_uint64), ("sweep_bytes", C.c_uint64),
+        ("launches", C.c_uint64), ("fill_launches", C.c_uint64), ("n_aligners", C.c_uint64), ("sweep_bytes", C.c_uint64), ("pool_reruns", C.c_uint64),
     ]
 
 

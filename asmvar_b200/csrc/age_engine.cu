@@ -110,6 +110,7 @@ struct Device {
     cudaStream_t rb = nullptr;   // device -> host read-back of the previous one
     Arena scratch;
     Slot slot[2];
+    double trace_scale = 1.0;    // grows when a batch overflowed its trace pool: later batches of the same kind get more from the start
     std::string err;
 };
 
@@ -237,7 +238,8 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
         // pages in the C2 workload), a TDUP / inversion aligner at whole strips of the tie rows (about 10 % in C4).  The pool gets
         // an eighth / a quarter of the full size; a batch that needs more is run again with a pool twice as large.
         hp.trace_full = (size_t)hp.nsets * p2_full_granules((size_t)hp.nstrips * hp.nwin, hp.k7);
-        hp.trace_share = hp.trace_full / (hp.k7 ? 4 : 8) + 8;
+        // (small matrices touch a larger part of their windows: at least 64 granules per aligner, never more than all pages)
+        hp.trace_share = std::min(hp.trace_full, std::max(hp.trace_full / (hp.k7 ? 4 : 8), (size_t)64 * hp.nsets) + 8);
         hp.cells = (double)j.len1 * j.len2;
         B->pairs.push_back(hp);
     };
@@ -389,7 +391,7 @@ bool stage_on_device(age_ctx *ctx, Batch &B, const age_job *jobs, Device &dev, S
     size_t share = 0;
     sl.tpool_full = P2_DUMP_GRANULES;
     for (size_t i = 0; i < np; ++i) { share += B.pairs[pair_ids[i]].trace_share; sl.tpool_full += B.pairs[pair_ids[i]].trace_full; }
-    size_t gran = std::min(sl.tpool_full, std::max<size_t>(share + P2_DUMP_GRANULES, (size_t)16384));          // at least 64 MB
+    size_t gran = std::min(sl.tpool_full, std::max<size_t>((size_t)((double)share * dev.trace_scale) + P2_DUMP_GRANULES, (size_t)16384));   // at least 64 MB
     if (const char *e = getenv("AGE_TRACE_POOL_GRANULES")) gran = std::max<size_t>(P2_DUMP_GRANULES + 64, (size_t)atol(e));   // test knob: a small pool forces the overflow re-run
     sl.tpool_granules = (uint32_t)std::min<size_t>(gran, 0xFFFFFFF0u);
     sl.tpool_off = align_up(sl.sc_off[np], P2_GRANULE);
@@ -484,7 +486,7 @@ bool rerun_with_pools(Batch &B, Device &dev, Slot &sl, int pool_cap, size_t tpoo
 }
 
 // wait for the slot's results and gather them into the batch
-bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
+bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st, int host_threads = 1)
 {
     CK(cudaSetDevice(dev.id));
     for (int attempt = 0; attempt < 8; ++attempt) {
@@ -494,11 +496,13 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
         if (H.counters[1] > sl.pool_cap || tneed > sl.tpool_granules) {       // a pool was too small: run again with larger ones
             const int pc = H.counters[1] > sl.pool_cap ? H.counters[1] + 4096 : sl.pool_cap;
             const size_t tg = tneed > sl.tpool_granules ? std::max(2 * (size_t)sl.tpool_granules, tneed + tneed / 4) : sl.tpool_granules;
+            if (tneed > sl.tpool_granules) dev.trace_scale = std::min(8.0, dev.trace_scale * std::max(1.5, 1.25 * (double)tneed / (double)sl.tpool_granules));
+            if (g_hprof) fprintf(stderr, "[host prof] pool overflow: blocks %d of %d, trace granules %zu of %u -> run again\n", H.counters[1], sl.pool_cap, tneed, sl.tpool_granules);
             if (!rerun_with_pools(B, dev, sl, pc, tg)) return false;
-            st.launches += 1 + sl.launches; st.fill_launches += 1;
+            st.launches += 1 + sl.launches; st.fill_launches += 1; st.pool_reruns += 1;
             continue;
         }
-        for (size_t i = 0; i < sl.pair_ids.size(); ++i) {
+        parallel_for(host_threads, sl.pair_ids.size(), [&](size_t i) {     // pairs are disjoint: gathered on all host cores
             const HostPair &hp = B.pairs[sl.pair_ids[i]];
             for (int k = 0; k < 2; ++k) {
                 if (hp.a[k] < 0) continue;
@@ -513,7 +517,7 @@ bool finish_fetch(Batch &B, Device &dev, Slot &sl, age_stats &st)
                         b.push_back(age_block{s.start1, s.start2, s.length});
                     }
             }
-        }
+        });
         float ms = 0;
         st.h2d_bytes += sl.in_bytes; st.d2h_bytes += sl.out_bytes;
         if (cudaEventElapsedTime(&ms, sl.ev[0], sl.ev[1]) == cudaSuccess) st.h2d_ms += ms;
@@ -599,14 +603,14 @@ void account(Batch &B)
     }
 }
 
-void assemble(const Batch &B, age_result *out, size_t n)
+void assemble(const Batch &B, age_result *out, size_t n, int host_threads = 1)
 {
     std::vector<int> main_of(n, -1), aux_of(n, -1);
     for (size_t a = 0; a < B.aligners.size(); ++a) {
         const Aligner &al = B.aligners[a];
         (al.role ? aux_of : main_of)[al.job] = (int)a;
     }
-    for (size_t i = 0; i < n; ++i) {
+    parallel_for(host_threads, n, [&](size_t i) {
         age_result &r = out[i];
         memset(&r, 0, offsetof(age_result, bp));          // header only: bp rows beyond n_bp are not part of the result
         memset(&r.counts, 0, sizeof(r.counts));
@@ -614,7 +618,7 @@ void assemble(const Batch &B, age_result *out, size_t n)
         r.left = r.right = r.alt_left = r.alt_right = nullptr;
         r.status = B.job_status[i];
         r.aux_score = -1;
-        if (r.status != AGE_OK) continue;
+        if (r.status != AGE_OK) return;
         const int m = main_of[i], x = aux_of[i];
         const AlignerOut &om = B.outs[m];
         r.main_score = om.score;
@@ -624,9 +628,9 @@ void assemble(const Batch &B, age_result *out, size_t n)
             if (B.outs[x].score > om.score) { pick = x; r.used_aux = 1; }       // AGEaligner.cpp:151,181-184
         }
         const AlignerOut &o = B.outs[pick];
-        if (o.status != 0) { r.status = AGE_ERR_CUDA; continue; }
+        if (o.status != 0) { r.status = AGE_ERR_CUDA; return; }
         r.score = o.score; r.flag = B.aligners[pick].flag;
-        if (o.n_bp < 0) continue;                                  // lost the -both selection: score only
+        if (o.n_bp < 0) return;                                    // lost the -both selection: score only
         r.detail = 1;
         r.n_bp = o.n_bp;
         memcpy(r.bp, o.bp, sizeof(r.bp[0]) * (size_t)std::max(o.n_bp, 0));
@@ -638,7 +642,7 @@ void assemble(const Batch &B, age_result *out, size_t n)
         for (int k = 0; k < 2; ++k) { c.n_aligned[k] = o.call[CALL_ALIGNED + k]; c.n_identic[k] = o.call[CALL_IDENTIC + k]; c.n_gap[k] = o.call[CALL_GAP + k]; }
         for (int k = 0; k < 3; ++k) { c.homo_at1[k] = o.call[CALL_AT1 + k]; c.homo_at2[k] = o.call[CALL_AT2 + k]; }
         c.homo_out1 = o.call[CALL_OUT1]; c.homo_out2 = o.call[CALL_OUT2]; c.homo_in1 = o.call[CALL_IN1]; c.homo_in2 = o.call[CALL_IN2];
-    }
+    });
     // Mutual -both partners that did not share a warp (wide jobs) both come back complete: keep the details of the one
     // age_align prints only (the lower index unless the other scores strictly higher, age_align.cpp:273), as the
     // on-device selection does.
@@ -661,7 +665,7 @@ void merge_stats(age_stats &to, const std::vector<age_stats> &per_dev)
     for (const age_stats &s : per_dev) {
         to.kernel_ms = std::max(to.kernel_ms, s.kernel_ms); to.fill_ms = std::max(to.fill_ms, s.fill_ms);
         to.h2d_ms = std::max(to.h2d_ms, s.h2d_ms); to.d2h_ms = std::max(to.d2h_ms, s.d2h_ms);
-        to.h2d_bytes += s.h2d_bytes; to.d2h_bytes += s.d2h_bytes; to.launches += s.launches; to.fill_launches += s.fill_launches;
+        to.h2d_bytes += s.h2d_bytes; to.d2h_bytes += s.d2h_bytes; to.launches += s.launches; to.fill_launches += s.fill_launches; to.pool_reruns += s.pool_reruns;
     }
 }
 
@@ -737,14 +741,14 @@ int collect(age_ctx *ctx, age_result *out, size_t n)
     if (B.state == 1) {
         const int nd = (int)ctx->devs.size();
         std::vector<age_stats> dstat(nd);
-        ok = for_each_device(ctx, [&](int d) { return !B.on_dev[d] || finish_fetch(B, ctx->devs[d], ctx->devs[d].slot[s], dstat[d]); });
+        ok = for_each_device(ctx, [&](int d) { return !B.on_dev[d] || finish_fetch(B, ctx->devs[d], ctx->devs[d].slot[s], dstat[d], std::max(1, ctx->host_threads / (int)ctx->devs.size())); });
         merge_stats(B.stats, dstat);
     }
     B.state = 0; ctx->in_flight -= 1;
     if (!ok) { for (Device &dev : ctx->devs) sync_device(dev); return AGE_ERR_CUDA; }
     const double t1 = wall_ms();
     account(B);
-    assemble(B, out, n);
+    assemble(B, out, n, ctx->host_threads);
     ctx->stats = B.stats;
     if (g_hprof) fprintf(stderr, "[host prof] collect: wait + gather %.2f ms, assemble %.2f ms; kernels %.2f ms\n", t1 - t0, wall_ms() - t1, B.stats.kernel_ms);
     return 0;

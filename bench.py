@@ -319,22 +319,25 @@ def inproc_leg(devices, single_device_results=None):
             t0 = time.perf_counter()
             pending = []
             scores = []
+            reruns = 0
             for bi, (arr, keep, n) in enumerate(prepared):
                 eng.submit(arr, n)
                 pending.append((bi, n))
                 if len(pending) == 2:
                     b0, n0 = pending.pop(0)
                     res = eng.collect(n0, outs[b0 & 1])
+                    reruns += eng.stats()["pool_reruns"]
                     if b0 == 0:
                         scores = [(res[i].status, res[i].score, res[i].n_bp, res[i].detail) for i in range(min(n0, 2048))]
             while pending:
                 b0, n0 = pending.pop(0)
                 res = eng.collect(n0, outs[b0 & 1])
+                reruns += eng.stats()["pool_reruns"]
                 if b0 == 0:
                     scores = [(res[i].status, res[i].score, res[i].n_bp, res[i].detail) for i in range(min(n0, 2048))]
             dt = time.perf_counter() - t0
             total_s += dt; total_c += len(cands); total_cu += cell_updates(cands)
-            summary[kind] = {"candidates": len(cands), "seconds": dt, "value": len(cands) / dt}
+            summary[kind] = {"candidates": len(cands), "seconds": dt, "value": len(cands) / dt, "batches": len(prepared), "pool_reruns": int(reruns)}
             checks.append((kind, scores))
     return {"value": total_c / total_s, "unit": "realignments/s", "gcups": total_cu / total_s / 1e9, "candidates": total_c, "seconds": total_s,
             "devices": nd, "per_mode": summary, "generate_s": gen_s, "scaling": "strong",

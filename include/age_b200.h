@@ -108,6 +108,8 @@ typedef struct {
     uint64_t n_aligners;       /* single-mode aligner runs executed (a -inv job is two) */
     uint64_t sweep_bytes;      /* bytes the sweep kernels of the batch move to and from HBM by construction: the D planes in the
                                 * batch's storage format written and read back, checkpoints, strip boundary rows, tile maxima */
+    uint64_t pool_reruns;      /* times (a device's part of) the batch was run again because its block pool or its trace pool
+                                * was too small (the pools of later batches start larger) */
 } age_stats;
 
 /* Replaces: process start-up of age_align (age_align.cpp:194-229).  device_ids may be NULL
