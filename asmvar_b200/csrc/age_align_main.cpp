@@ -185,6 +185,8 @@ void create_ctx()
         while (getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
     }
     if (devs.empty()) devs.push_back(0);
+    // the kernels are loaded with the context (beside the FASTA parsing) instead of at their first launch
+    if (!getenv("CUDA_MODULE_LOADING")) setenv("CUDA_MODULE_LOADING", "EAGER", 1);
     // CUDA initialises every visible GPU (0.5 s and more on an 8-GPU box): show it only the ones this run uses
     if (!getenv("CUDA_VISIBLE_DEVICES")) {
         string vis;

@@ -236,10 +236,12 @@ void build_plan(Batch *B, const age_job *jobs, size_t n)
         hp.scratch_bytes += hp.nsets * hp.set_bytes;
         // Trace pages come out of a pool of the batch: an INDEL aligner looks at a few dozen of its windows (about 5 % of all its
         // pages in the C2 workload), a TDUP / inversion aligner at whole strips of the tie rows (about 10 % in C4).  The pool gets
-        // an eighth / a quarter of the full size; a batch that needs more is run again with a pool twice as large.
+        // an eighth of the full size or what those strips take; a batch that needs more is run again with a larger pool.
         hp.trace_full = (size_t)hp.nsets * p2_full_granules((size_t)hp.nstrips * hp.nwin, hp.k7);
         // (small matrices touch a larger part of their windows: at least 64 granules per aligner, never more than all pages)
-        hp.trace_share = std::min(hp.trace_full, std::max(hp.trace_full / (hp.k7 ? 4 : 8), (size_t)64 * hp.nsets) + 8);
+        // (a TDUP / inversion aligner sweeps the whole strips of its tie rows, usually one to three: that many strips' worth of pages)
+        const size_t k7_strips = (size_t)3 * hp.nwin * 41 * hp.nsets;
+        hp.trace_share = std::min(hp.trace_full, std::max(hp.trace_full / 8, hp.k7 ? k7_strips : (size_t)64 * hp.nsets) + 8);
         hp.cells = (double)j.len1 * j.len2;
         B->pairs.push_back(hp);
     };
@@ -819,6 +821,12 @@ extern "C" int age_reserve(age_ctx *ctx, size_t scratch_bytes)
             if (cudaMalloc(&dev.scratch.ptr, want) != cudaSuccess) { cudaGetLastError(); ctx->err = "age_reserve: device allocation failed"; return AGE_ERR_CUDA; }
             dev.scratch.cap = want;
         }
+        if (!scratch_bytes)            // "all of it": the staging buffers of both slots too, sized for a batch of a few thousand candidates
+            for (Slot &sl : dev.slot) {
+                const bool ok = sl.hin.ensure((size_t)128 << 20) && sl.in.ensure((size_t)128 << 20) && sl.hout.ensure((size_t)64 << 20) &&
+                                sl.outbuf.ensure((size_t)64 << 20) && sl.aux.ensure((size_t)16 << 20);
+                if (!ok) { ctx->err = "age_reserve: staging buffer allocation failed"; return AGE_ERR_CUDA; }
+            }
     }
     return 0;
 }

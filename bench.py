@@ -516,7 +516,7 @@ def main():
             sys.path.insert(0, str(ROOT / "tools"))
             import cli_throughput
             devs = ",".join(str(i) for i in range(world))
-            m = cli_throughput.measure(args.cli_candidates * (world if world > 1 else 1), devices=devs)
+            m = cli_throughput.measure(args.cli_candidates, devices=devs, replicate=world)      # N x the candidates at N devices
             line["cli"] = {"value": m["realign_per_s"], "unit": "realignments/s", "candidates": m["candidates"], "seconds": m["seconds"],
                            "fasta_bytes": m["fasta_bytes"], "age_bytes": m["age_bytes"], "cuda_startup_s": m.get("cuda_startup_s"),
                            "steady_value": m.get("steady_realign_per_s"), "devices": devs,

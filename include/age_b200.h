@@ -118,7 +118,9 @@ age_ctx *age_create(const int *device_ids, int n_dev);
 void     age_destroy(age_ctx *ctx);
 const char *age_last_error(const age_ctx *ctx);   /* ctx may be NULL: error of the failed age_create */
 /* Allocate the scratch arena of every device now instead of with the first batches (a cudaMalloc of ~100 GB costs tens of
- * milliseconds): scratch_bytes per device, 0 = 80 % of what is free.  Optional; arenas still grow on demand. */
+ * milliseconds, pinning a ~100 MB staging buffer even more): scratch_bytes per device; 0 = 80 % of what is free plus the
+ * staging buffers of both batch slots at a size that fits batches of a few thousand candidates.  Optional; everything still
+ * grows on demand. */
 int age_reserve(age_ctx *ctx, size_t scratch_bytes);
 
 /* Replaces: the serial candidate loop of age_align.cpp:231-293 / VarUnit.cpp:271-299 --

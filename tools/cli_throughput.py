@@ -7,11 +7,21 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def measure(n: int, devices: str = "0", chunk: int = 0, keep: str = "", verbose: bool = False) -> dict:
+def measure(n: int, devices: str = "0", chunk: int = 0, keep: str = "", verbose: bool = False, replicate: int = 1) -> dict:
+    """`n` C2 candidates, written `replicate` times under different record names (several GPUs need more input than is
+    worth generating in Python)"""
     from asmvar_b200 import synth
     cands = synth.indel_candidates(n, seed=1002)
     with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as d:
         t, q, v = synth.write_files(cands, Path(d), "cli")
+        if replicate > 1:
+            with open(t, "ab") as ft, open(q, "ab") as fq, open(v, "a") as fv:
+                for rep in range(1, replicate):
+                    for i, (w, c) in enumerate(cands):
+                        ft.write(b">t%d_%d\n%s\n" % (i, rep, w))
+                        fq.write(b">q%d_%d\n%s\n" % (i, rep, c))
+                        fv.write(f"t{i}_{rep}\t1\t{len(w)}\tq{i}_{rep}\t1\t{len(c)}\tcand{i}_{rep}\n")
+            n = n * replicate
         env = dict(os.environ, AGE_DEVICES=devices, AGE_CLI_PROF="1")
         if chunk:
             env["AGE_CHUNK"] = str(chunk)
