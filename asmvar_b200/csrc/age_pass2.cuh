@@ -484,6 +484,25 @@ __device__ void indel_row_ranges(const View<WIDE> &V, int *rlo, int *rhi, int la
     __syncwarp();
 }
 
+// Smallest x in [lo, hi) with pred(x), or hi when there is none; pred is monotone (false ... false true ... true).  The 32
+// lanes probe 32 positions per round (each probe is a dependent chain of global loads: a 20 000-column row takes 3 rounds
+// instead of the 15 steps of a bisection).  Warp-collective: every lane calls it with the same arguments.
+template <class Pred>
+__device__ __forceinline__ int first_true32(int lo, int hi, int lane, Pred pred)
+{
+    while (hi - lo > 32) {
+        const int step = (hi - lo + 31) / 32;
+        const int x = min(lo + (lane + 1) * step - 1, hi - 1);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, pred(x));
+        if (!m) return hi;                                  // the last probe is hi - 1
+        const int k = __ffs(m) - 1;
+        hi = min(lo + (k + 1) * step - 1, hi - 1);          // that probe holds: the answer is it unless an earlier position does
+        lo = lo + k * step;                                 // the probe before it does not
+    }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, lo + lane < hi && pred(lo + lane));
+    return m ? lo + __ffs(m) - 1 : hi;
+}
+
 // K7 findInversionTDuplicationBPs (:472-538).  The reference walks every (j1, j2) pair; here the monotone
 // rows are binary-searched for the run of matching values, and of the start cells whose traceBackMaxima walks
 // merge (View::merges_into_next: they share the endpoint, hence the addBpoints key) only the last one is walked --
@@ -503,13 +522,10 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
         const int tv = max2 - V.F2(r, j1);
         if (tv < 0) return;
         // columns x in [1, len1+1] of row r+1, values non-increasing: first x with value <= tv
-        int lo = 1, hi = len1 + 2;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (V.R2(r + 1, mid) <= tv) hi = mid; else lo = mid + 1; }
+        const int lo = first_true32(1, len1 + 2, lane, [&](int x) { return V.R2(r + 1, x) <= tv; });
         if (V.R2(r + 1, lo) != tv) return;
         // the run of columns with value tv ends before the first x with value < tv
-        int l2 = lo, h2 = len1 + 2;
-        while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (V.R2(r + 1, mid) < tv) h2 = mid; else l2 = mid + 1; }
-        const int xhi = l2 - 1;
+        const int xhi = first_true32(lo, len1 + 2, lane, [&](int x) { return V.R2(r + 1, x) < tv; }) - 1;
         for (int xb = lo; xb <= xhi && !stop; xb += 32) {
             const int xi = xb + lane;
             const bool in = xi <= xhi;
@@ -562,13 +578,10 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
         const int tv = max2 - V.R2(i2, j2);
         if (tv < 0) return;
         // columns x in [0, len1] of row i2-1, values non-decreasing: last x with value <= tv
-        int lo = -1, hi = len1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (V.F2(i2 - 1, mid) <= tv) lo = mid; else hi = mid - 1; }
+        const int lo = first_true32(0, len1 + 1, lane, [&](int x) { return V.F2(i2 - 1, x) > tv; }) - 1;
         if (lo < 0 || V.F2(i2 - 1, lo) != tv) return;
         // the run of columns with value tv starts after the last x with value < tv
-        int l2 = -1, h2 = lo;
-        while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (V.F2(i2 - 1, mid) < tv) l2 = mid; else h2 = mid - 1; }
-        const int xlo = l2 + 1;
+        const int xlo = first_true32(0, lo + 1, lane, [&](int x) { return V.F2(i2 - 1, x) >= tv; });
         for (int xb = lo; xb >= xlo && !stop; xb -= 32) {
             const int xi = xb - lane;
             const bool in = xi >= xlo;
