@@ -90,6 +90,9 @@ template <bool WIDE> struct View {
         set_valid(plane, s, win);
         if (with_mp) set_valid(4, s, win);
         P2_PROF_ADD(4 + (plane >> 1), c0);
+#ifdef AGE_P2_PROF
+        if (lane == 0) atomicAdd(&g_prof[6 + (plane >> 1)], 1ull);
+#endif
     }
     __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)
         for (int win = 0; win < nwin; ++win) ensure(3, s, win, true);
