@@ -779,14 +779,18 @@ extern "C" age_ctx *age_create(const int *device_ids, int n_dev)
         if (d.id < 0 || d.id >= count) { g_create_error = "invalid device id"; delete ctx; return nullptr; }
         ctx->devs.push_back(d);
     }
-    for (Device &d : ctx->devs) {
+    // one host thread per device: creating a context takes a few hundred milliseconds, eight of them one after the other seconds
+    const bool all_ok = for_each_device(ctx, [&](int di) {
+        Device &d = ctx->devs[di];
         bool ok = cudaSetDevice(d.id) == cudaSuccess && cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&d.cp, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaStreamCreateWithFlags(&d.rb, cudaStreamNonBlocking) == cudaSuccess;
         for (Slot &sl : d.slot)
             for (int e = 0; ok && e < 7; ++e) ok = cudaEventCreate(&sl.ev[e]) == cudaSuccess;
-        if (!ok) { g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError()); age_destroy(ctx); return nullptr; }
-    }
+        if (!ok) d.err = std::string("CUDA initialisation failed: ") + cudaGetErrorString(cudaGetLastError());
+        return ok;
+    });
+    if (!all_ok) { g_create_error = ctx->err; age_destroy(ctx); return nullptr; }
     if (g_hprof) fprintf(stderr, "[host prof] age_create %.1f ms\n", wall_ms() - t_create);
     return ctx;
 }
@@ -811,24 +815,26 @@ extern "C" int age_reserve(age_ctx *ctx, size_t scratch_bytes)
 {
     if (!ctx) return AGE_ERR_ARG;
     if (ctx->in_flight) { ctx->err = "age_reserve: batches are in flight"; return AGE_ERR_ARG; }
-    for (Device &dev : ctx->devs) {
-        if (cudaSetDevice(dev.id) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return AGE_ERR_CUDA; }
+    const bool ok = for_each_device(ctx, [&](int di) {
+        Device &dev = ctx->devs[di];
+        if (cudaSetDevice(dev.id) != cudaSuccess) { dev.err = "cudaSetDevice failed"; return false; }
         size_t want = scratch_bytes;
         if (!want) { size_t fr = 0, tot = 0; cudaMemGetInfo(&fr, &tot); want = (size_t)(0.8 * (double)(fr + dev.scratch.cap)); }
         if (want > dev.scratch.cap) {
             cudaStreamSynchronize(dev.st);
             dev.scratch.release();
-            if (cudaMalloc(&dev.scratch.ptr, want) != cudaSuccess) { cudaGetLastError(); ctx->err = "age_reserve: device allocation failed"; return AGE_ERR_CUDA; }
+            if (cudaMalloc(&dev.scratch.ptr, want) != cudaSuccess) { cudaGetLastError(); dev.err = "age_reserve: device allocation failed"; return false; }
             dev.scratch.cap = want;
         }
         if (!scratch_bytes)            // "all of it": the staging buffers of both slots too, sized for a batch of a few thousand candidates
             for (Slot &sl : dev.slot) {
-                const bool ok = sl.hin.ensure((size_t)128 << 20) && sl.in.ensure((size_t)128 << 20) && sl.hout.ensure((size_t)64 << 20) &&
-                                sl.outbuf.ensure((size_t)64 << 20) && sl.aux.ensure((size_t)16 << 20);
-                if (!ok) { ctx->err = "age_reserve: staging buffer allocation failed"; return AGE_ERR_CUDA; }
+                const bool fine = sl.hin.ensure((size_t)128 << 20) && sl.in.ensure((size_t)128 << 20) && sl.hout.ensure((size_t)64 << 20) &&
+                                  sl.outbuf.ensure((size_t)64 << 20) && sl.aux.ensure((size_t)16 << 20);
+                if (!fine) { dev.err = "age_reserve: staging buffer allocation failed"; return false; }
             }
-    }
-    return 0;
+        return true;
+    });
+    return ok ? 0 : AGE_ERR_CUDA;
 }
 
 extern "C" const char *age_last_error(const age_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }

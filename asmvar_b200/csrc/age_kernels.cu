@@ -546,13 +546,14 @@ static void launch_pass2_t(const Pass2Params &p, cudaStream_t st)
     age_blocks_kernel<WIDE><<<std::min(nb, sms * P2_OCC), P2_WARPS * 32, 0, st>>>(p);
 #ifdef AGE_P2_PROF
     {   // cycle accounting of pass 2 (diagnostic builds only): summed over the warps of the launch
-        unsigned long long z[8];
+        unsigned long long z[16];
         cudaStreamSynchronize(st);
         cudaMemcpyFromSymbol(z, g_prof, sizeof(z));
         fprintf(stderr, "[p2 prof] pairs %d | Mcycles summed over warps: ranges / K7 forward %.1f, enumerate / K7 reverse %.1f, blocks %.1f, "
                         "on-demand re-sweeps forward %.1f reverse %.1f (counts %llu / %llu)\n",
                 p.n_pairs, z[1] / 1e6, z[2] / 1e6, z[3] / 1e6, z[4] / 1e6, z[5] / 1e6, z[6], z[7]);
-        unsigned long long zero[8] = {};
+        fprintf(stderr, "[p2 prof] on-demand windows per plane FS %llu FM %llu RS %llu RM %llu, with maxima RM %llu\n", z[8], z[9], z[10], z[11], z[15]);
+        unsigned long long zero[16] = {};
         cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
     }
 #endif

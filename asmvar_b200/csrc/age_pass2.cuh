@@ -12,7 +12,7 @@ namespace age {
 // optional cycle accounting of pass 2 (compiled in with -DAGE_P2_PROF only): 1 ranges / K7 forward, 2 enumerate / K7 reverse,
 // 3 blocks, 4 forward re-sweeps, 5 reverse re-sweeps
 #ifdef AGE_P2_PROF
-__device__ unsigned long long g_prof[8];
+__device__ unsigned long long g_prof[16];      // 8 + plane: on-demand re-sweeps per plane (FS, FM, RS, RM), 12 + plane: with the maxima (K7)
 #define P2_PROF_T0(v) long long v = clock64()
 #define P2_PROF_RESET(v) v = clock64()
 #define P2_PROF_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[i], (unsigned long long)(clock64() - (v))); } while (0)
@@ -91,7 +91,7 @@ template <bool WIDE> struct View {
         if (with_mp) set_valid(4, s, win);
         P2_PROF_ADD(4 + (plane >> 1), c0);
 #ifdef AGE_P2_PROF
-        if (lane == 0) atomicAdd(&g_prof[6 + (plane >> 1)], 1ull);
+        if (lane == 0) { atomicAdd(&g_prof[6 + (plane >> 1)], 1ull); atomicAdd(&g_prof[(with_mp ? 12 : 8) + plane], 1ull); }
 #endif
     }
     __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)

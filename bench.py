@@ -53,7 +53,8 @@ WORKLOADS = {
     "c4": "C4 synthetic inversions: 20 kb windows, 2 x 2 kb flanks, -inv, 1/-1/-10/-1",
     "c5": "C5 synthetic long deletions: 50 kb windows, 10 kb contigs, -indel -both, 1/-1/-10/-1",
 }
-INPROC_CANDIDATES = 98304            # fixed C3-style set of the in-process multi-device leg (strong scaling over N)
+INPROC_CANDIDATES = 98304            # C3-style set of the in-process multi-device leg, generated once ...
+INPROC_REPEAT = 4                    # ... and aligned this many times over: 393 216 candidates at every N (strong scaling)
 
 
 def measured_peaks():
@@ -312,7 +313,7 @@ def inproc_leg(devices, single_device_results=None):
             # others run out of short ones (the caller owns the order of its results; nothing is printed here)
             cands.sort(key=lambda c: len(c[0]) * len(c[1]), reverse=True)
             batches = [cands[i:i + per_batch] for i in range(0, len(cands), per_batch)]
-            prepared = [eng.make_jobs(both_jobs(b, flag)) for b in batches]
+            prepared = [eng.make_jobs(both_jobs(b, flag)) for b in batches] * INPROC_REPEAT      # the same job arrays again: nothing is cached between batches
             outs = [(capi.AgeResult * max(1, p[2]))() for p in prepared[:2]]
             # warm-up: first batch once (arena allocation, clocks)
             eng.align_raw(prepared[0][0], prepared[0][2], outs[0])
@@ -336,13 +337,13 @@ def inproc_leg(devices, single_device_results=None):
                 if b0 == 0:
                     scores = [(res[i].status, res[i].score, res[i].n_bp, res[i].detail) for i in range(min(n0, 2048))]
             dt = time.perf_counter() - t0
-            total_s += dt; total_c += len(cands); total_cu += cell_updates(cands)
-            summary[kind] = {"candidates": len(cands), "seconds": dt, "value": len(cands) / dt, "batches": len(prepared), "pool_reruns": int(reruns)}
+            total_s += dt; total_c += len(cands) * INPROC_REPEAT; total_cu += cell_updates(cands) * INPROC_REPEAT
+            summary[kind] = {"candidates": len(cands) * INPROC_REPEAT, "seconds": dt, "value": len(cands) * INPROC_REPEAT / dt, "batches": len(prepared), "pool_reruns": int(reruns)}
             checks.append((kind, scores))
     return {"value": total_c / total_s, "unit": "realignments/s", "gcups": total_cu / total_s / 1e9, "candidates": total_c, "seconds": total_s,
             "devices": nd, "per_mode": summary, "generate_s": gen_s, "scaling": "strong",
             "api": f"one age_create over {nd} device(s); age_submit/age_collect, length-binned batches of {per_batch} candidates, two in flight",
-            "workload": "C3-style fixed set: len1 in {1,2,4,8} kb x len2 in {0.5,1,2} kb, 70 % indel / 30 % tdup, -both"}, checks
+            "workload": f"C3-style fixed set ({INPROC_CANDIDATES} candidates x {INPROC_REPEAT}): len1 in {{1,2,4,8}} kb x len2 in {{0.5,1,2}} kb, 70 % indel / 30 % tdup, -both"}, checks
 
 
 def main():
@@ -516,7 +517,11 @@ def main():
             sys.path.insert(0, str(ROOT / "tools"))
             import cli_throughput
             devs = ",".join(str(i) for i in range(world))
-            m = cli_throughput.measure(args.cli_candidates, devices=devs, replicate=world)      # N x the candidates at N devices
+            m = cli_throughput.measure(args.cli_candidates, devices=devs, replicate=world, also_binary=True)      # N x the candidates at N devices
+            mb = m["binary"]
+            line["cli_binary"] = {"value": mb["realign_per_s"], "unit": "realignments/s", "candidates": mb["candidates"], "seconds": mb["seconds"],
+                                  "record_bytes": mb["age_bytes"], "steady_value": mb.get("steady_realign_per_s"), "devices": devs,
+                                  "note": "the same process with --binary-out: compact records instead of text (age2text prints the text from them later)"}
             line["cli"] = {"value": m["realign_per_s"], "unit": "realignments/s", "candidates": m["candidates"], "seconds": m["seconds"],
                            "fasta_bytes": m["fasta_bytes"], "age_bytes": m["age_bytes"], "cuda_startup_s": m.get("cuda_startup_s"),
                            "steady_value": m.get("steady_realign_per_s"), "devices": devs,
