@@ -208,7 +208,7 @@ void sweep_plan(int n_pairs, int max_strips, int *nw_out, int *cs_out)
     if (max_strips > MAX_STRIPS_LONG) return;
     if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) {
         *nw_out = force_nw;
-        if (force_nw > 1 && (force_cs == 2 || force_cs == 4)) *cs_out = force_cs;
+        if (force_nw > 1 && (force_cs == 2 || force_cs == 4)) *cs_out = force_cs;     // (AGE_LONG_CS=1 or unset: one CTA per pair)
         return;
     }
     if (n_pairs <= 0 || n_pairs >= sms * 16) return;
