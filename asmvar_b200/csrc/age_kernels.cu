@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <algorithm>
+#include <vector>
 
 namespace age {
 
@@ -481,10 +482,20 @@ age_enum_kernel(Pass2Params prm)
         for (int h = 0; h < 2; ++h) {
             if (!hd.need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
+#ifdef AGE_P2_PROF
+            __shared__ unsigned int od_s[P2_WARPS];
+            if (lane == 0) od_s[w] = 0;
+            __syncwarp();
+            const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords, &od_s[w]};
+#else
             const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
+#endif
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{0, bp_s[w]};
+            P2_PROF_T0(pc_pair);
             enumerate_aligner(V, T.flag[h], L, O, lane);
+            P2_PROF_PAIR(0, item, pc_pair);
+            P2_PROF_RESET(pc_pair);
             // the tracebacks of bpoint 0 and of the alternative printAlignment shows (the last one, normally)
             for (int which = 0; which < 2; ++which) {
                 const int idx = which == 0 ? 0 : L.n - 1;
@@ -494,6 +505,10 @@ age_enum_kernel(Pass2Params prm)
                 queue_path(prm, V, item, 0, lg2, lg1, -1, fl + fl / 4 + 64);
                 queue_path(prm, V, item, 2, rg2, rg1, +1, fr + fr / 4 + 64);
             }
+            P2_PROF_PAIR(1, item, pc_pair);
+#ifdef AGE_P2_PROF
+            if (lane == 0 && item < PROF_PAIRS) g_pair_cycles[3][item] += od_s[w];
+#endif
             __syncwarp();
         }
     }
@@ -519,13 +534,25 @@ age_blocks_kernel(Pass2Params prm)
         for (int h = 0; h < 2; ++h) {
             if (!hd.need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
+#ifdef AGE_P2_PROF
+            __shared__ unsigned int od_s[P2_WARPS];
+            if (lane == 0) od_s[w] = 0;
+            __syncwarp();
+            const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords, &od_s[w]};
+#else
             const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
+#endif
             AlignerOut &O = prm.outs[T.out[h]];
             BpList L{O.n_bp, bp_s[w]};
             __syncwarp();
             for (int i = lane; i < L.n * 4; i += 32) L.bp[i >> 2][i & 3] = O.bp[i >> 2][i & 3];
             __syncwarp();
+            P2_PROF_T0(pc_pair);
             emit_blocks(V, T.flag[h], L, O, prm.pool, prm.pool_cap, prm.pool_used, lane);
+            P2_PROF_PAIR(2, item, pc_pair);
+#ifdef AGE_P2_PROF
+            if (lane == 0 && item < PROF_PAIRS) g_pair_cycles[4][item] += od_s[w];
+#endif
         }
     }
 }
@@ -555,6 +582,30 @@ static void launch_pass2_t(const Pass2Params &p, cudaStream_t st)
         fprintf(stderr, "[p2 prof] on-demand windows per plane FS %llu FM %llu RS %llu RM %llu, with maxima RM %llu\n", z[8], z[9], z[10], z[11], z[15]);
         unsigned long long zero[16] = {};
         cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
+        // the slowest pairs of the launch (the enumerate / blocks kernels last as long as their slowest warp)
+        const int n = std::min(p.n_pairs, (int)PROF_PAIRS);
+        std::vector<unsigned int> cyc(5 * (size_t)PROF_PAIRS);
+        cudaMemcpyFromSymbol(cyc.data(), g_pair_cycles, cyc.size() * sizeof(unsigned int));
+        std::vector<PairTask> pt(n);
+        cudaMemcpy(pt.data(), p.pairs, n * sizeof(PairTask), cudaMemcpyDeviceToHost);
+        std::vector<int> order(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        auto tot = [&](int i) { return (unsigned long long)cyc[i] + cyc[PROF_PAIRS + i]; };
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return tot(a) > tot(b); });
+        unsigned long long sum = 0, od_e = 0, od_b = 0;
+        for (int i = 0; i < n; ++i) { sum += tot(i); od_e += cyc[3 * PROF_PAIRS + i]; od_b += cyc[4 * PROF_PAIRS + i]; }
+        fprintf(stderr, "[p2 prof] enumerate kernel, cycles per pair: mean %.2f M, median %.2f M, p90 %.2f M, p99 %.2f M; windows re-swept on demand: %llu enumerate, %llu blocks\n",
+                sum / 1e6 / std::max(n, 1), n ? tot(order[n / 2]) / 1e6 : 0.0, n ? tot(order[n / 10]) / 1e6 : 0.0, n ? tot(order[n / 100]) / 1e6 : 0.0, od_e, od_b);
+        for (int k = 0; k < std::min(n, 12); ++k) {
+            const int i = order[k];
+            AlignerOut ao[2] = {};
+            for (int h = 0; h < 2; ++h) if (pt[i].out[h] >= 0) cudaMemcpy(&ao[h], p.outs + pt[i].out[h], 32, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[p2 prof]   pair %5d: len1 %d len2 %d, enumerate %.2f M + path queueing %.2f M, blocks %.2f M cycles; on demand %u + %u windows; n_bp %d / %d, score %d / %d\n",
+                    i, pt[i].len1, pt[i].len2, cyc[i] / 1e6, cyc[PROF_PAIRS + i] / 1e6, cyc[2 * PROF_PAIRS + i] / 1e6, cyc[3 * PROF_PAIRS + i], cyc[4 * PROF_PAIRS + i],
+                    ao[0].n_bp, ao[1].n_bp, ao[0].score, ao[1].score);
+        }
+        std::fill(cyc.begin(), cyc.end(), 0u);
+        cudaMemcpyToSymbol(g_pair_cycles, cyc.data(), cyc.size() * sizeof(unsigned int));
     }
 #endif
 }

@@ -7,12 +7,22 @@
 #pragma once
 #include "age_sweep.cuh"
 
+// AGE_V_WIDERUN (build switch for A/B measurements): 1 = straight runs of the maxima planes are read 256 cells per pass, 0 = 32
+#ifndef AGE_V_WIDERUN
+#define AGE_V_WIDERUN 1
+#endif
+
 namespace age {
 
 // optional cycle accounting of pass 2 (compiled in with -DAGE_P2_PROF only): 1 ranges / K7 forward, 2 enumerate / K7 reverse,
 // 3 blocks, 4 forward re-sweeps, 5 reverse re-sweeps
 #ifdef AGE_P2_PROF
 __device__ unsigned long long g_prof[16];      // 8 + plane: on-demand re-sweeps per plane (FS, FM, RS, RM), 12 + plane: with the maxima (K7)
+constexpr int PROF_PAIRS = 1 << 15;
+// per pair of the launch: cycles in the enumeration, in the queueing of the traceback paths, in the blocks kernel; windows re-swept
+// on demand by the enumerate / by the blocks kernel
+__device__ unsigned int g_pair_cycles[5][PROF_PAIRS];
+#define P2_PROF_PAIR(i, item, v) do { if ((threadIdx.x & 31) == 0 && (item) < PROF_PAIRS) g_pair_cycles[i][item] += (unsigned int)(clock64() - (v)); } while (0)
 #define P2_PROF_T0(v) long long v = clock64()
 #define P2_PROF_RESET(v) v = clock64()
 #define P2_PROF_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[i], (unsigned long long)(clock64() - (v))); } while (0)
@@ -20,6 +30,7 @@ __device__ unsigned long long g_prof[16];      // 8 + plane: on-demand re-sweeps
 #define P2_PROF_T0(v) do { } while (0)
 #define P2_PROF_RESET(v) do { } while (0)
 #define P2_PROF_ADD(i, v) do { } while (0)
+#define P2_PROF_PAIR(i, item, v) do { } while (0)
 #endif
 
 template <bool WIDE> struct View {
@@ -28,6 +39,9 @@ template <bool WIDE> struct View {
     WarpRings *R;
     TraceSmem *X;
     int len1, len2, nb, nsteps, nwin, nstrips, half, lane, max2, vwords;
+#ifdef AGE_P2_PROF
+    unsigned int *od = nullptr;                  // windows this warp re-swept on demand for the pair at hand
+#endif
     __device__ __forceinline__ int sh() const { return WIDE ? 0 : 16 * half; }                                  // the aligner's half of a packed word
     __device__ __forceinline__ int pick(uint32_t w) const { return WIDE ? (int)w : (int)((w >> (16 * half)) & 0xFFFFu); }
 
@@ -91,7 +105,7 @@ template <bool WIDE> struct View {
         if (with_mp) set_valid(4, s, win);
         P2_PROF_ADD(4 + (plane >> 1), c0);
 #ifdef AGE_P2_PROF
-        if (lane == 0) { atomicAdd(&g_prof[6 + (plane >> 1)], 1ull); atomicAdd(&g_prof[(with_mp ? 12 : 8) + plane], 1ull); }
+        if (lane == 0) { atomicAdd(&g_prof[6 + (plane >> 1)], 1ull); atomicAdd(&g_prof[(with_mp ? 12 : 8) + plane], 1ull); if (od) ++*od; }
 #endif
     }
     __device__ void ensure_rm(int s) const {                 // reverse maxima of a whole strip (K7 rows)
@@ -172,15 +186,82 @@ template <bool WIDE> struct View {
     __device__ __forceinline__ uint32_t rev_codes(int plane, int r, int c1) const { return word_codes(code_word(plane, r - 1, rstep(r - 1, c1)), r - 1); }
     __device__ __forceinline__ uint32_t hot_word(int r, int c) const { return hot_at(r - 1, rstep(r - 1, c)); }     // of reverse cell (r, c)'s slot
 
-    // Starting at (r, c) and stepping by (dr, dc): how many consecutive cells (at most 32) carry code t, and the
-    // code of the first cell that does not (meaningful when the result is < 32).
+    // Starting at (r, c) and stepping by (dr, dc): how many consecutive cells carry code t, and the code of the first cell
+    // that does not -- or RUN_ON when the look-ahead ended without finding one (the caller reads on from the cell behind it).
+    // Only the cell the walk stands on forces its window to be swept; cells further along are read when their window is
+    // resident and end the look-ahead otherwise: a walk that stops a few cells short of a window border must not pay a
+    // whole re-sweep (hundreds of thousands of cycles inside this latency-bound kernel) for cells it never reaches.
+    // Straight runs of the maxima planes (FM / RM: a walk crosses the whole excised stretch along one row or column) read
+    // one trace word per lane and word instead of one cell: along a row two blocks of four columns per lane = 256 cells a
+    // pass, along a column the eight rows a word holds = 256 cells; everything else, and anything near the border, 32 cells.
+    static constexpr uint32_t RUN_ON = 0xFFu;
+    __device__ __forceinline__ bool resident(int plane, int r, int c) const { return valid(plane, (r - 1) >> 8, win_of(plane, r, c)); }   // interior (r, c)
     __device__ int run_len(int plane, int r, int c, int dr, int dc, uint32_t t, uint32_t &tnext) const {
+        const int rev = plane >> 1;
+        if (interior(r, c)) ensure(plane, (r - 1) >> 8, win_of(plane, r, c));
+#if AGE_V_WIDERUN
+        if ((plane & 1) && dr == 0 && r >= 1 && r <= len2 && c >= 1 && c <= len1) {      // along row r: blocks m0, m0 + dc, ... (columns 4m+1 .. 4m+4)
+            const int m0 = (c - 1) >> 2, mlast = m0 + dc * 63;
+            if (mlast >= 0 && 4 * mlast + 4 <= len1) {
+                const int q = r - 1;
+                const int first = dc > 0 ? 4 - ((c - 1) & 3) : ((c - 1) & 3) + 1;       // cells of the run in block m0
+                int brk = -1; uint32_t bcode = RUN_ON;                                // first cell of this lane that ends the look-ahead
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    const int i = 2 * lane + g, m = m0 + dc * i, c1 = 4 * m + 1;
+                    const int before = i == 0 ? 0 : first + 4 * (i - 1), cnt = i == 0 ? first : 4;
+                    if (brk >= 0) continue;
+                    if (!resident(plane, r, c1)) { brk = before; continue; }           // (bcode stays RUN_ON)
+                    const uint32_t codes = word_codes(code_word(plane, q, rev ? rstep(q, c1) : fstep(q, c1)), q);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // k-th cell of the block in walking order: column offset j; reverse planes count block columns from the right
+                        const int j = dc > 0 ? (i == 0 ? 4 - first + k : k) : (i == 0 ? first - 1 - k : 3 - k);
+                        const uint32_t code = (codes >> (2 * (rev ? 3 - j : j))) & 3u;
+                        if (k < cnt && brk < 0 && code != t) { brk = before + k; bcode = code; }
+                    }
+                }
+                const unsigned mk = __ballot_sync(0xFFFFFFFFu, brk >= 0);
+                if (!mk) { tnext = RUN_ON; return first + 4 * 63; }
+                const int src = __ffs(mk) - 1;
+                tnext = __shfl_sync(0xFFFFFFFFu, bcode, src);
+                return __shfl_sync(0xFFFFFFFFu, brk, src);
+            }
+        }
+        if ((plane & 1) && dc == 0 && c >= 1 && c <= len1 && r >= 1 && r <= len2) {      // along column c: groups of the eight rows one word holds
+            const int q0 = r - 1, g0 = q0 >> 3, glast = g0 + dr * 31;
+            if (glast >= 0 && 8 * glast + 8 <= len2) {
+                const int first = dr > 0 ? 8 - (q0 & 7) : (q0 & 7) + 1;
+                const int qg = 8 * (g0 + dr * lane);                                  // first row (0-based) of this lane's group
+                const int before = lane == 0 ? 0 : first + 8 * (lane - 1), cnt = lane == 0 ? first : 8;
+                int brk = -1; uint32_t bcode = RUN_ON;
+                if (!resident(plane, qg + 1, c)) brk = before;
+                else {
+                    const uint2 v = code_word(plane, qg, rev ? rstep(qg, c) : fstep(qg, c));
+                    const int w = rev ? W * ((c - 1) / W + 1) - c : (c - 1) % W;
+                    const uint32_t codes = ((w < 2 ? v.x : v.y) >> (16 * (w & 1))) & 0xFFFFu;    // 2 bits per row of the group
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int j = dr > 0 ? (lane == 0 ? 8 - first + k : k) : (lane == 0 ? first - 1 - k : 7 - k);
+                        const uint32_t code = (codes >> (2 * j)) & 3u;
+                        if (k < cnt && brk < 0 && code != t) { brk = before + k; bcode = code; }
+                    }
+                }
+                const unsigned mk = __ballot_sync(0xFFFFFFFFu, brk >= 0);
+                if (!mk) { tnext = RUN_ON; return first + 8 * 31; }
+                const int src = __ffs(mk) - 1;
+                tnext = __shfl_sync(0xFFFFFFFFu, bcode, src);
+                return __shfl_sync(0xFFFFFFFFu, brk, src);
+            }
+        }
+#endif
         const int rr = r + lane * dr, cc = c + lane * dc;
-        ensure_lanes(plane, rr, cc);
-        const uint32_t code = code_nc(plane, rr, cc);
+        const bool known = !interior(rr, cc) || resident(plane, rr, cc);
+        const uint32_t code = known ? code_nc(plane, rr, cc) : RUN_ON;
         const unsigned m = __ballot_sync(0xFFFFFFFFu, code != t);
-        const int n = m ? __ffs(m) - 1 : 32;
-        tnext = __shfl_sync(0xFFFFFFFFu, code, n & 31);
+        if (!m) { tnext = RUN_ON; return 32; }
+        const int n = __ffs(m) - 1;
+        tnext = __shfl_sync(0xFFFFFFFFu, code, n);
         return n;
     }
     // K7 helper.  A maxima-trace walk (plane 1 = FM stepping by -1, plane 3 = RM stepping by +1) that starts at (r, x)
@@ -230,7 +311,7 @@ __device__ void walk_chain(const View<WIDE> &V, int plane, int sign, int &c, int
         uint32_t tn;
         const int n = V.run_len(plane, r, c, dr, dc, t, tn);
         r += n * dr; c += n * dc;
-        t = n < 32 ? tn : V.code_at(plane, r, c);
+        t = tn != View<WIDE>::RUN_ON ? tn : V.code_at(plane, r, c);
     }
 }
 template <bool WIDE>
@@ -323,7 +404,7 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
             if (lo < a) slow(lo, a - 1);
             for (int g0 = (a - 1) >> 2; g0 <= (b - 1) >> 2 && !stop; g0 += 32) {
                 const int m = g0 + lane, c1 = 4 * m + 1;
-                const bool act = m <= (b - 1) >> 2, fourth = act && c1 + 4 <= V.len1;
+                const bool act = m <= (b - 1) >> 2, fourth = act && c1 + 4 <= V.len1 && c1 + 3 >= a && c1 + 3 <= b;      // (its hot word is only read for cell c1 + 3)
                 V.ensure_lanes(1, act ? r : -1, c1);
                 V.ensure_lanes(3, act ? r + 1 : -1, c1 + 1);
                 V.ensure_lanes(3, fourth ? r + 1 : -1, c1 + 4);
@@ -647,7 +728,7 @@ __device__ int left_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_
         r += len * dr; c += len * dc;
         if (t == T_DIAG) run += len;
         else if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n_total - 1 - n] = Block{c - len * dc + 1, r - len * dr + 1, run}; ++n; run = 0; }
-        t = len < 32 ? tn : V.code_at(0, r, c);
+        t = tn != View<WIDE>::RUN_ON ? tn : V.code_at(0, r, c);
     }
     if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n_total - 1 - n] = Block{c + 1, r + 1, run}; ++n; }
     return n;       // (n <= n_total unless the trace pool overflowed between the counting and the writing pass: the batch is run again then)
@@ -666,7 +747,7 @@ __device__ int right_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n
         if (t == T_DIAG) { if (run == 0) { s1 = c; s2 = r; } run += len; }     // interior cells only (:820 always holds)
         else if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
         r += len * dr; c += len * dc;
-        t = len < 32 ? tn : V.code_at(2, r, c);
+        t = tn != View<WIDE>::RUN_ON ? tn : V.code_at(2, r, c);
     }
     if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n] = Block{s1, s2, run}; ++n; }
     return n;
