@@ -483,10 +483,10 @@ age_enum_kernel(Pass2Params prm)
             if (!hd.need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
 #ifdef AGE_P2_PROF
-            __shared__ unsigned int od_s[P2_WARPS];
-            if (lane == 0) od_s[w] = 0;
+            __shared__ unsigned int od_s[P2_WARPS][8];
+            if (lane < 8) od_s[w][lane] = 0;
             __syncwarp();
-            const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords, &od_s[w]};
+            const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords, od_s[w]};
 #else
             const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
 #endif
@@ -507,7 +507,7 @@ age_enum_kernel(Pass2Params prm)
             }
             P2_PROF_PAIR(1, item, pc_pair);
 #ifdef AGE_P2_PROF
-            if (lane == 0 && item < PROF_PAIRS) g_pair_cycles[3][item] += od_s[w];
+            if (lane == 0 && item < PROF_PAIRS) { g_pair_cycles[3][item] += od_s[w][0]; g_pair_cycles[5][item] += od_s[w][1]; g_pair_cycles[6][item] += od_s[w][2]; g_pair_cycles[7][item] += od_s[w][3]; for (int q = 4; q < 8; ++q) g_pair_cycles[4 + q][item] += od_s[w][q]; }
 #endif
             __syncwarp();
         }
@@ -535,10 +535,10 @@ age_blocks_kernel(Pass2Params prm)
             if (!hd.need[h]) continue;
             const P2Scratch sc = carve_set(T, T.select ? 0 : h, prm);
 #ifdef AGE_P2_PROF
-            __shared__ unsigned int od_s[P2_WARPS];
-            if (lane == 0) od_s[w] = 0;
+            __shared__ unsigned int od_s[P2_WARPS][8];
+            if (lane < 8) od_s[w][lane] = 0;
             __syncwarp();
-            const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords, &od_s[w]};
+            const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords, od_s[w]};
 #else
             const View<WIDE> V{&T, sc, &rings[w], &tsm[w], T.len1, T.len2, T.nb, T.nsteps, T.nwin, T.nstrips, h, lane, hd.max2[h], sc.vwords};
 #endif
@@ -551,7 +551,7 @@ age_blocks_kernel(Pass2Params prm)
             emit_blocks(V, T.flag[h], L, O, prm.pool, prm.pool_cap, prm.pool_used, lane);
             P2_PROF_PAIR(2, item, pc_pair);
 #ifdef AGE_P2_PROF
-            if (lane == 0 && item < PROF_PAIRS) g_pair_cycles[4][item] += od_s[w];
+            if (lane == 0 && item < PROF_PAIRS) g_pair_cycles[4][item] += od_s[w][0];
 #endif
         }
     }
@@ -582,9 +582,14 @@ static void launch_pass2_t(const Pass2Params &p, cudaStream_t st)
         fprintf(stderr, "[p2 prof] on-demand windows per plane FS %llu FM %llu RS %llu RM %llu, with maxima RM %llu\n", z[8], z[9], z[10], z[11], z[15]);
         unsigned long long zero[16] = {};
         cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
+        unsigned long long z2[8];
+        cudaMemcpyFromSymbol(z2, g_prof2, sizeof(z2));
+        if (z2[0]) fprintf(stderr, "[p2 prof] K7: %llu tie rows, %llu forward / %llu reverse start cells taking %.1f / %.1f Mcycles, ensure_rm %.1f Mcycles\n",
+                           z2[0], z2[1], z2[2], z2[3] / 1e6, z2[4] / 1e6, z2[5] / 1e6);
+        cudaMemcpyToSymbol(g_prof2, zero, sizeof(z2));
         // the slowest pairs of the launch (the enumerate / blocks kernels last as long as their slowest warp)
         const int n = std::min(p.n_pairs, (int)PROF_PAIRS);
-        std::vector<unsigned int> cyc(5 * (size_t)PROF_PAIRS);
+        std::vector<unsigned int> cyc(12 * (size_t)PROF_PAIRS);
         cudaMemcpyFromSymbol(cyc.data(), g_pair_cycles, cyc.size() * sizeof(unsigned int));
         std::vector<PairTask> pt(n);
         cudaMemcpy(pt.data(), p.pairs, n * sizeof(PairTask), cudaMemcpyDeviceToHost);
@@ -600,8 +605,9 @@ static void launch_pass2_t(const Pass2Params &p, cudaStream_t st)
             const int i = order[k];
             AlignerOut ao[2] = {};
             for (int h = 0; h < 2; ++h) if (pt[i].out[h] >= 0) cudaMemcpy(&ao[h], p.outs + pt[i].out[h], 32, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[p2 prof]   pair %5d: len1 %d len2 %d, enumerate %.2f M + path queueing %.2f M, blocks %.2f M cycles; on demand %u + %u windows; n_bp %d / %d, score %d / %d\n",
-                    i, pt[i].len1, pt[i].len2, cyc[i] / 1e6, cyc[PROF_PAIRS + i] / 1e6, cyc[2 * PROF_PAIRS + i] / 1e6, cyc[3 * PROF_PAIRS + i], cyc[4 * PROF_PAIRS + i],
+            fprintf(stderr, "[p2 prof]   pair %5d: len1 %d len2 %d, enumerate %.2f M + path queueing %.2f M, blocks %.2f M cycles; K6: %u hot windows, ranges %.2f M, forward scan %.2f M, %u narrow passes, %u wide rows, %u walks taking %.2f M; on demand %u + %u windows; n_bp %d / %d, score %d / %d\n",
+                    i, pt[i].len1, pt[i].len2, cyc[i] / 1e6, cyc[PROF_PAIRS + i] / 1e6, cyc[2 * PROF_PAIRS + i] / 1e6, cyc[6 * PROF_PAIRS + i], cyc[5 * PROF_PAIRS + i] / 1e6, cyc[7 * PROF_PAIRS + i] / 1e6, cyc[8 * PROF_PAIRS + i], cyc[9 * PROF_PAIRS + i], cyc[10 * PROF_PAIRS + i], cyc[11 * PROF_PAIRS + i] / 1e6,
+                    cyc[3 * PROF_PAIRS + i], cyc[4 * PROF_PAIRS + i],
                     ao[0].n_bp, ao[1].n_bp, ao[0].score, ao[1].score);
         }
         std::fill(cyc.begin(), cyc.end(), 0u);

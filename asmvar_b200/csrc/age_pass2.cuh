@@ -21,9 +21,12 @@ __device__ unsigned long long g_prof[16];      // 8 + plane: on-demand re-sweeps
 constexpr int PROF_PAIRS = 1 << 15;
 // per pair of the launch: cycles in the enumeration, in the queueing of the traceback paths, in the blocks kernel; windows re-swept
 // on demand by the enumerate / by the blocks kernel
-__device__ unsigned int g_pair_cycles[5][PROF_PAIRS];
+__device__ unsigned int g_pair_cycles[12][PROF_PAIRS];    // + 5: cycles in the row ranges, 6: hot windows, 7: cycles in the forward scan (K6)
 #define P2_PROF_PAIR(i, item, v) do { if ((threadIdx.x & 31) == 0 && (item) < PROF_PAIRS) g_pair_cycles[i][item] += (unsigned int)(clock64() - (v)); } while (0)
+__device__ unsigned long long g_prof2[8];      // K7: 0 tie rows, 1 / 2 forward / reverse start cells, 3 / 4 cycles spent in them, 5 cycles in ensure_rm
+#define P2_PROF2_ADD(i, val) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof2[i], (unsigned long long)(val)); } while (0)
 #define P2_PROF_T0(v) long long v = clock64()
+#define P2_OD(V, i, val) do { if ((threadIdx.x & 31) == 0 && (V).od) (V).od[i] += (unsigned int)(val); } while (0)
 #define P2_PROF_RESET(v) v = clock64()
 #define P2_PROF_ADD(i, v) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_prof[i], (unsigned long long)(clock64() - (v))); } while (0)
 #else
@@ -31,6 +34,8 @@ __device__ unsigned int g_pair_cycles[5][PROF_PAIRS];
 #define P2_PROF_RESET(v) do { } while (0)
 #define P2_PROF_ADD(i, v) do { } while (0)
 #define P2_PROF_PAIR(i, item, v) do { } while (0)
+#define P2_PROF2_ADD(i, val) do { } while (0)
+#define P2_OD(V, i, val) do { } while (0)
 #endif
 
 template <bool WIDE> struct View {
@@ -40,7 +45,7 @@ template <bool WIDE> struct View {
     TraceSmem *X;
     int len1, len2, nb, nsteps, nwin, nstrips, half, lane, max2, vwords;
 #ifdef AGE_P2_PROF
-    unsigned int *od = nullptr;                  // windows this warp re-swept on demand for the pair at hand
+    unsigned int *od = nullptr;                  // [4] of the pair at hand: windows re-swept on demand, cycles in the row ranges, hot windows, cycles in the forward scan
 #endif
     __device__ __forceinline__ int sh() const { return WIDE ? 0 : 16 * half; }                                  // the aligner's half of a packed word
     __device__ __forceinline__ int pick(uint32_t w) const { return WIDE ? (int)w : (int)((w >> (16 * half)) & 0xFFFFu); }
@@ -264,6 +269,41 @@ template <bool WIDE> struct View {
         tnext = __shfl_sync(0xFFFFFFFFu, code, n);
         return n;
     }
+    // K7 helper.  Of the cells x0, x0 + dir, ..., x1 (at most 480) of row r of a maxima plane (1 = FM, 3 = RM): which 32-cell groups
+    // (bit g: cells x0 + 32 g dir ... x0 + (32 g + 31) dir) hold a cell whose code is not HORIZONTAL.  A HORIZONTAL cell merges into
+    // its neighbour's walk whatever that one does (merges_into_next with d = 0), and on the long plateaus of the maxima nearly
+    // every cell is one: four trace words per lane classify 480 cells in one pass.  Rows outside the matrix: every group.
+    __device__ unsigned groups_not_horizontal(int plane, int r, int x0, int x1, int dir) const {
+        const int n = (dir > 0 ? x1 - x0 : x0 - x1) + 1;
+        const unsigned all = (1u << ((n + 31) >> 5)) - 1u;
+        if (r < 1 || r > len2) return all;
+        const int lowcol = max(min(x0, x1), 1), highcol = min(max(x0, x1), len1);
+        auto group = [&](int x) { return (dir > 0 ? x - x0 : x0 - x) >> 5; };
+        unsigned need = 0;
+        if (min(x0, x1) < 1) need |= 1u << group(0);                       // border cells carry no HORIZONTAL code that would merge
+        if (max(x0, x1) > len1) need |= 1u << group(len1 + 1);
+        const int mlo = (lowcol - 1) >> 2;
+        bool ok = true;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { const int c1 = 4 * (mlo + 4 * lane + g) + 1; if (c1 <= highcol && !resident(plane, r, c1)) ok = false; }
+        if (!__all_sync(0xFFFFFFFFu, ok)) {
+#pragma unroll 1
+            for (int g = 0; g < 4; ++g) { const int c1 = 4 * (mlo + 4 * lane + g) + 1; ensure_lanes(plane, c1 <= highcol ? r : -1, c1); }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int c1 = 4 * (mlo + 4 * lane + g) + 1;
+            if (c1 > highcol) continue;
+            const uint32_t codes = (plane >> 1) ? rev_codes(plane, r, c1) : fwd_codes(plane, r, c1);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = c1 + j;
+                const uint32_t code = (codes >> (2 * ((plane >> 1) ? 3 - j : j))) & 3u;
+                if (x >= lowcol && x <= highcol && code != T_HORI) need |= 1u << group(x);
+            }
+        }
+        return __reduce_or_sync(0xFFFFFFFFu, need);
+    }
     // K7 helper.  A maxima-trace walk (plane 1 = FM stepping by -1, plane 3 = RM stepping by +1) that starts at (r, x)
     // merges into the walk that starts at the next cell (r, x + dir) when it makes d >= 0 VERTICAL steps followed by a
     // HORIZONTAL one and the neighbour's walk makes the same d VERTICAL steps first.  Both walks then share their
@@ -315,9 +355,9 @@ __device__ void walk_chain(const View<WIDE> &V, int plane, int sign, int &c, int
     }
 }
 template <bool WIDE>
-__device__ void walk_left(const View<WIDE> &V, int &lg1, int &lg2) { walk_chain(V, 1, -1, lg1, lg2); }
+__device__ void walk_left(const View<WIDE> &V, int &lg1, int &lg2) { P2_PROF_T0(wc); walk_chain(V, 1, -1, lg1, lg2); P2_OD(V, 6, 1); P2_OD(V, 7, clock64() - wc); }
 template <bool WIDE>
-__device__ void walk_right(const View<WIDE> &V, int &rg1, int &rg2) { walk_chain(V, 3, +1, rg1, rg2); }
+__device__ void walk_right(const View<WIDE> &V, int &rg1, int &rg2) { P2_PROF_T0(wc); walk_chain(V, 3, +1, rg1, rg2); P2_OD(V, 6, 1); P2_OD(V, 7, clock64() - wc); }
 
 // K9 addBpoints (:644-668); executed redundantly by every lane on the shared list, lane 0 writes
 template <bool WIDE>
@@ -336,6 +376,14 @@ __device__ int add_bp(const View<WIDE> &V, BpList &L, int lg1, int lg2, int rg1,
     return -1;
 }
 
+// Rows with at most 32 candidate columns each: log2 of the columns tested per row and pass (1, 2, 4, ..., 32), from the widest
+// of the 32 rows
+__device__ __forceinline__ int narrow_shift(int my_width_minus_1)
+{
+    const unsigned w = __reduce_max_sync(0xFFFFFFFFu, (unsigned)my_width_minus_1);
+    return w == 0 ? 0 : 32 - __clz(w);
+}
+
 // K6 findIndelBPs, ordered part (:552-610).  rlo/rhi bound, per row, the columns that can hold a cell with
 // Fmax + Rmax == max (from the hot windows of the reverse sweep and the border rule); rows with rhi < rlo are skipped.
 template <bool WIDE>
@@ -344,20 +392,24 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
     const int len2 = V.len2;
     int n_add = 0;
     bool stop = false;
+    P2_PROF_T0(fc0);
     // Most rows hold no candidate: the per-row column ranges are inspected 32 rows at a time (one per lane) and only the
     // non-empty rows are visited, in the reference's order.
     for (int rb = 0; rb <= len2 && !stop; rb += 32) {                     // forward scan (:552-573)
       const int myr = min(rb + lane, len2), mylo = rlo[myr], myhi = rhi[myr];
       const bool mine = rb + lane <= len2 && myhi >= mylo;
       unsigned rows = __ballot_sync(0xFFFFFFFFu, mine);
-      if (rows && __all_sync(0xFFFFFFFFu, !mine || myhi - mylo < 4)) {
-        // at most four candidate columns per row (the split runs along a column: insertions): 8 rows x 4 columns are tested
-        // side by side, lane order = row-major order, hits are taken in that order
-        for (int sub = 0; sub < 32 && !stop; sub += 8) {
-            if (!((rows >> sub) & 0xFFu)) continue;
-            const int src = sub + (lane >> 2);
+      if (rows && __all_sync(0xFFFFFFFFu, !mine || myhi - mylo < 32)) {
+        // at most 32 candidate columns per row (the split runs along a column: insertions; a few columns wide when the flank next
+        // to it can end in more than one place): the rows are tested side by side, 32 rows x 1 column, 16 x 2, ... or 1 x 32 per
+        // pass; lane order = row-major order, hits are taken in that order
+        const int sh = narrow_shift(mine ? myhi - mylo : 0), rp = 32 >> sh;
+        for (int sub = 0; sub < 32 && !stop; sub += rp) {
+            if (!((rows >> sub) & (0xFFFFFFFFu >> (32 - rp)))) continue;
+            P2_OD(V, 4, 1);
+            const int src = sub + (lane >> sh);
             const int r = rb + src, lo = __shfl_sync(0xFFFFFFFFu, mylo, src), hi = __shfl_sync(0xFFFFFFFFu, myhi, src);
-            const int c = lo + (lane & 3);
+            const int c = lo + (lane & ((1 << sh) - 1));
             const bool in = ((rows >> src) & 1u) && c <= hi;
             V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
             const bool tie = in && V.tie_nc(r, c);
@@ -365,7 +417,7 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
             unsigned m = __ballot_sync(0xFFFFFFFFu, tie && V.code_nc(1, r, c) == T_STOP);
             while (m && !stop) {
                 const int b = __ffs(m) - 1; m &= m - 1;
-                const int cc = __shfl_sync(0xFFFFFFFFu, c, b), rr = rb + sub + (b >> 2);
+                const int cc = __shfl_sync(0xFFFFFFFFu, c, b), rr = rb + sub + (b >> sh);
                 int lg1 = cc, lg2 = rr, rg1 = cc + 1, rg2 = rr + 1;
                 walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
                 const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
@@ -378,6 +430,7 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
       while (rows && !stop) {
         const int r = rb + __ffs(rows) - 1; rows &= rows - 1;
         const int lo = rlo[r], hi = rhi[r];
+        P2_OD(V, 5, 1);
         auto candidate = [&](int c) {                                   // cell (r, c) ties at the maximum and starts a maxima chain
             int lg1 = c, lg2 = r, rg1 = c + 1, rg2 = r + 1;
             walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
@@ -429,23 +482,28 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
         } else slow(lo, hi);
       }
     }
+#ifdef AGE_P2_PROF
+    if (lane == 0 && V.od) V.od[3] += (unsigned int)(clock64() - fc0);
+#endif
     n_add = 0; stop = false;
     for (int rb = len2 & ~31; rb >= 0 && !stop; rb -= 32) {               // reverse scan (:586-610)
       const int myr = min(rb + lane, len2), mylo = rlo[myr], myhi = rhi[myr];
       const bool mine = rb + lane <= len2 && myhi >= mylo;
       unsigned rows = __ballot_sync(0xFFFFFFFFu, mine);
-      if (rows && __all_sync(0xFFFFFFFFu, !mine || myhi - mylo < 4)) {
-        for (int sub = 24; sub >= 0 && !stop; sub -= 8) {
-            if (!((rows >> sub) & 0xFFu)) continue;
-            const int src = sub + (lane >> 2);
+      if (rows && __all_sync(0xFFFFFFFFu, !mine || myhi - mylo < 32)) {
+        const int sh = narrow_shift(mine ? myhi - mylo : 0), rp = 32 >> sh;
+        for (int sub = 32 - rp; sub >= 0 && !stop; sub -= rp) {
+            if (!((rows >> sub) & (0xFFFFFFFFu >> (32 - rp)))) continue;
+            P2_OD(V, 4, 1);
+            const int src = sub + (lane >> sh);
             const int r = rb + src, lo = __shfl_sync(0xFFFFFFFFu, mylo, src), hi = __shfl_sync(0xFFFFFFFFu, myhi, src);
-            const int c = lo + (lane & 3);
+            const int c = lo + (lane & ((1 << sh) - 1));
             const bool in = ((rows >> src) & 1u) && c <= hi;
             V.ensure_lanes(3, in ? r + 1 : -1, c + 1);
             unsigned m = __ballot_sync(0xFFFFFFFFu, in && V.tie_nc(r, c) && V.code_nc(3, r + 1, c + 1) == T_STOP);
             while (m && !stop) {
                 const int b = 31 - __clz(m); m &= ~(1u << b);
-                const int cc = __shfl_sync(0xFFFFFFFFu, c, b), rr = rb + sub + (b >> 2);
+                const int cc = __shfl_sync(0xFFFFFFFFu, c, b), rr = rb + sub + (b >> sh);
                 int lg1 = cc, lg2 = rr, rg1 = cc + 1, rg2 = rr + 1;
                 walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
                 const int res = add_bp(V, L, lg1, lg2, rg1, rg2, lane);
@@ -458,6 +516,7 @@ __device__ void indel_enumerate(const View<WIDE> &V, BpList &L, const int *rlo, 
       while (rows && !stop) {
         const int r = rb + 31 - __clz(rows); rows &= ~(1u << (r - rb));
         const int lo = rlo[r], hi = rhi[r];
+        P2_OD(V, 5, 1);
         auto candidate = [&](int c) {
             int lg1 = c, lg2 = r, rg1 = c + 1, rg2 = r + 1;
             walk_left(V, lg1, lg2); walk_right(V, rg1, rg2);
@@ -519,41 +578,67 @@ __device__ void indel_row_ranges(const View<WIDE> &V, int *rlo, int *rhi, int la
         return;
     }
     const int nhot = V.sc.hotlist[0];                                 // written by the select kernel
+    // Scratch in the warp's shared memory (the rings and the trace staging are only used while a window is re-swept): the
+    // hot words of the window [step][lane] and the column range of each of the lane's rows.  The scan below is a pair of
+    // short rolled loops: unrolled over the 32 words x 4 columns x 8 rows it was 3 400 instructions that every hot window
+    // (hundreds per long deletion) streamed through the instruction cache.
+    uint32_t *hs = reinterpret_cast<uint32_t *>(V.R);                 // [CKS][32]
+    int *lo8 = reinterpret_cast<int *>(V.X), *hi8 = lo8 + RPT * 32;   // [RPT][32]
+    static_assert(sizeof(WarpRings) >= CKS * 32 * 4 && sizeof(TraceSmem) >= 2 * RPT * 32 * 4, "scratch of indel_row_ranges");
     for (int hi = 0; hi < nhot; ++hi) {
         const int wi = V.sc.hotlist[1 + hi];
         const int s = wi / T.nwin, win = wi % T.nwin;
         V.ensure(3, s, win);
+        __syncwarp();
         const int t0 = CKS * win + 1, t1 = min(CKS * win + CKS, T.nsteps);
         const uint32_t *hotpage = reinterpret_cast<const uint32_t *>(V.page(3, s * STRIP, t0) + 2 * P2_GRANULE);   // [step in window][lane]
-        uint32_t hw[CKS];
 #pragma unroll
         for (int i = 0; i < CKS; ++i) {                               // the lane's hot words of all steps of the window, in flight together
             const int t = t0 + i, bq = t - 31 + lane;                 // logical reverse block of this lane in step t
-            hw[i] = (t <= t1 && bq >= 1 && bq <= nb) ? __ldcg(hotpage + i * 32 + lane) : 0u;
+            hs[i * 32 + lane] = (t <= t1 && bq >= 1 && bq <= nb) ? __ldcg(hotpage + i * 32 + lane) : 0u;
         }
-        // the hot cells of a lane lie in its own 8 rows: column ranges are gathered in registers, no atomics
-        int lo8[RPT], hi8[RPT];
 #pragma unroll
-        for (int k = 0; k < RPT; ++k) { lo8[k] = 0x7FFFFFFF; hi8[k] = -1; }
-#pragma unroll
+        for (int k = 0; k < RPT; ++k) { lo8[k * 32 + lane] = 0x7FFFFFFF; hi8[k * 32 + lane] = -1; }
+        // The hot cells of a lane lie in its own 8 rows.  The columns of step i are cb - 3 .. cb with cb = cb0 - 4 i: the first step
+        // that shows a row holds the row's largest column, the last one its smallest.
+        const int cb0 = W * (nb + 1 - (t0 - 31 + lane));              // reverse cell column of block column w in step i: cb0 - W i - w
+        auto word = [&](int i, int &cb) {                             // hot word of step i without the padding columns behind len1
+            const uint32_t x = hs[i * 32 + lane];
+            cb = cb0 - W * i;
+            const int pad = min(max(cb - len1, 0), W);
+            return pad >= W ? 0u : x & (0xFFFFFFFFu << (8 * pad));
+        };
+        uint32_t seen = 0;
+#pragma unroll 1
         for (int i = 0; i < CKS; ++i) {
-            const uint32_t x = hw[i];
-            if (x == 0) continue;
-            const int cb = W * (nb + 1 - (t0 + i - 31 + lane));       // reverse cell column of block column w is cb - w
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const int c = cb - w;
-                if (c > len1) continue;                               // padding
-                const uint32_t byte = (x >> (8 * w)) & 0xFFu;
-#pragma unroll
-                for (int k = 0; k < RPT; ++k)
-                    if ((byte >> k) & 1u) { lo8[k] = min(lo8[k], c - 1); hi8[k] = max(hi8[k], c - 1); }
+            int cb;
+            const uint32_t x = word(i, cb);
+            uint32_t nw = ((x | (x >> 8) | (x >> 16) | (x >> 24)) & 0xFFu) & ~seen;     // rows seen for the first time
+            seen |= nw;
+            while (nw) {
+                const int k = __ffs(nw) - 1; nw &= nw - 1;
+                const uint32_t mk = (x >> k) & 0x01010101u;           // bit 8 w: cell (row k, block column w) is hot
+                hi8[k * 32 + lane] = cb - ((__ffs(mk) - 1) >> 3) - 1;
+            }
+        }
+        seen = 0;
+#pragma unroll 1
+        for (int i = CKS - 1; i >= 0; --i) {
+            int cb;
+            const uint32_t x = word(i, cb);
+            uint32_t nw = ((x | (x >> 8) | (x >> 16) | (x >> 24)) & 0xFFu) & ~seen;
+            seen |= nw;
+            while (nw) {
+                const int k = __ffs(nw) - 1; nw &= nw - 1;
+                const uint32_t mk = (x >> k) & 0x01010101u;
+                lo8[k * 32 + lane] = cb - ((31 - __clz(mk)) >> 3) - 1;
             }
         }
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const int r = s * STRIP + lane * RPT + k + 1;             // reverse cell row; K6 row r - 1
-            if (hi8[k] >= 0 && r <= len2) { rlo[r - 1] = min(rlo[r - 1], lo8[k]); rhi[r - 1] = max(rhi[r - 1], hi8[k]); }
+            const int h8 = hi8[k * 32 + lane];
+            if (h8 >= 0 && r <= len2) { rlo[r - 1] = min(rlo[r - 1], lo8[k * 32 + lane]); rhi[r - 1] = max(rhi[r - 1], h8); }
         }
     }
     __syncwarp();
@@ -610,7 +695,10 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
         if (V.R2(r + 1, lo) != tv) return;
         // the run of columns with value tv ends before the first x with value < tv
         const int xhi = first_true32(lo, len1 + 2, lane, [&](int x) { return V.R2(r + 1, x) < tv; }) - 1;
-        for (int xb = lo; xb <= xhi && !stop; xb += 32) {
+        for (int xb0 = lo; xb0 <= xhi && !stop; xb0 += 480) {
+          unsigned need = V.groups_not_horizontal(3, r + 1, xb0, min(xhi, xb0 + 479), +1);
+          while (need && !stop) {                                  // the 32-cell groups that hold anything but HORIZONTAL codes
+            const int xb = xb0 + 32 * (__ffs(need) - 1); need &= need - 1;
             const int xi = xb + lane;
             const bool in = xi <= xhi;
             const bool mg = V.merges_into_next(3, r + 1, xi, +1, in);      // warp-collective: every lane calls it
@@ -623,33 +711,51 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
                 if (res > 0) ++n_add;
                 if (n_add >= MAX_BP / 2 || res < 0) stop = true;
             }
+          }
         }
     };
     for (int rb = 0; rb <= len2 && !stop; rb += 32) {                     // forward (:485-504): the tie rows, 32 rows per look
       unsigned tie_rows = __ballot_sync(0xFFFFFFFFu, rb + lane <= len2 && A(rb + lane) + B(rb + lane + 1) == max2);
       while (tie_rows && !stop) {
         const int r = rb + __ffs(tie_rows) - 1; tie_rows &= tie_rows - 1;
+        P2_PROF2_ADD(0, 1);
+        P2_PROF_T0(ec);
         if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
+        P2_PROF2_ADD(5, clock64() - ec);
         if (r == 0) {                                                     // border row: only (0, 0) has FM = 0 (:874-882)
             fwd_start(0, 0);
             continue;
         }
-        // interior row: column 0 carries FM = VERTICAL; columns 1 .. len1 one forward block per lane, 128 cells per pass
-        for (int g0 = 0; g0 <= (len1 - 1) >> 2 && !stop; g0 += 32) {
-            const int m = g0 + lane, c1 = 4 * m + 1;
-            const bool act = c1 <= len1;
-            V.ensure_lanes(1, act ? r : -1, c1);
-            uint32_t hits = 0;
-            if (act) {
-                const uint32_t fm = V.fwd_codes(1, r, c1);
+        // interior row: column 0 carries FM = VERTICAL; columns 1 .. len1 four forward blocks per lane, 512 cells per pass (a pass
+        // is one chain of dependent loads -- window bit, page table, trace word -- whatever the number of words it fetches)
+        for (int g0 = 0; g0 <= (len1 - 1) >> 2 && !stop; g0 += 128) {
+            bool ok = true;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (c1 + j <= len1 && ((fm >> (2 * j)) & 3u) == T_STOP) hits |= 1u << j;
+            for (int g = 0; g < 4; ++g) { const int c1 = 4 * (g0 + 4 * lane + g) + 1; if (c1 <= len1 && !V.resident(1, r, c1)) ok = false; }
+            if (!__all_sync(0xFFFFFFFFu, ok)) {
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) { const int c1 = 4 * (g0 + 4 * lane + g) + 1; V.ensure_lanes(1, c1 <= len1 ? r : -1, c1); }
+            }
+            uint32_t hits = 0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int c1 = 4 * (g0 + 4 * lane + g) + 1;
+                if (c1 <= len1) {
+                    const uint32_t fm = V.fwd_codes(1, r, c1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (c1 + j <= len1 && ((fm >> (2 * j)) & 3u) == T_STOP) hits |= 1u << (4 * g + j);
+                }
             }
             unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
             while (lanes && !stop) {
                 const int src = __ffs(lanes) - 1; lanes &= lanes - 1;
                 uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
-                while (h && !stop) { const int j = __ffs(h) - 1; h &= h - 1; fwd_start(r, 4 * (g0 + src) + 1 + j); }
+                while (h && !stop) {
+                    const int b = __ffs(h) - 1; h &= h - 1;
+                    P2_PROF_T0(sc0);
+                    fwd_start(r, 4 * (g0 + 4 * src + (b >> 2)) + 1 + (b & 3));
+                    P2_PROF2_ADD(1, 1); P2_PROF2_ADD(3, clock64() - sc0);
+                }
             }
         }
       }
@@ -666,7 +772,10 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
         if (lo < 0 || V.F2(i2 - 1, lo) != tv) return;
         // the run of columns with value tv starts after the last x with value < tv
         const int xlo = first_true32(0, lo + 1, lane, [&](int x) { return V.F2(i2 - 1, x) >= tv; });
-        for (int xb = lo; xb >= xlo && !stop; xb -= 32) {
+        for (int xb0 = lo; xb0 >= xlo && !stop; xb0 -= 480) {
+          unsigned need = V.groups_not_horizontal(1, i2 - 1, xb0, max(xlo, xb0 - 479), -1);
+          while (need && !stop) {
+            const int xb = xb0 - 32 * (__ffs(need) - 1); need &= need - 1;
             const int xi = xb - lane;
             const bool in = xi >= xlo;
             const bool mg = V.merges_into_next(1, i2 - 1, xi, -1, in);
@@ -679,6 +788,7 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
                 if (res > 0) ++n_add;
                 if (n_add >= MAX_BP / 2 || res < 0) stop = true;
             }
+          }
         }
     };
     for (int rb = (len2 + 1) & ~31; rb >= 0 && !stop; rb -= 32) {          // reverse (:515-534): the tie rows from the last one
@@ -691,22 +801,35 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
             continue;
         }
         rev_start(i2, len1 + 1);                                          // border column
-        // columns len1 .. 1, one reverse block per lane, the block with the largest columns first
-        for (int g0 = (len1 - 1) >> 2; g0 >= 0 && !stop; g0 -= 32) {
-            const int m = g0 - lane, c1 = 4 * m + 1;
-            const bool act = m >= 0;
-            V.ensure_lanes(3, act ? i2 : -1, c1);
-            uint32_t hits = 0;
-            if (act) {
-                const uint32_t rm = V.rev_codes(3, i2, c1);
+        // columns len1 .. 1, four reverse blocks per lane, the block with the largest columns first
+        for (int g0 = (len1 - 1) >> 2; g0 >= 0 && !stop; g0 -= 128) {
+            bool ok = true;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (c1 + j <= len1 && ((rm >> (2 * (3 - j))) & 3u) == T_STOP) hits |= 1u << j;
+            for (int g = 0; g < 4; ++g) { const int m = g0 - (4 * lane + g); if (m >= 0 && !V.resident(3, i2, 4 * m + 1)) ok = false; }
+            if (!__all_sync(0xFFFFFFFFu, ok)) {
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) { const int m = g0 - (4 * lane + g); V.ensure_lanes(3, m >= 0 ? i2 : -1, 4 * m + 1); }
+            }
+            uint32_t hits = 0;                                            // bit 4 * (3 - g) + j: column offset j of the lane's g-th block
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int m = g0 - (4 * lane + g), c1 = 4 * m + 1;
+                if (m >= 0) {
+                    const uint32_t rm = V.rev_codes(3, i2, c1);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (c1 + j <= len1 && ((rm >> (2 * (3 - j))) & 3u) == T_STOP) hits |= 1u << (4 * (3 - g) + j);
+                }
             }
             unsigned lanes = __ballot_sync(0xFFFFFFFFu, hits != 0);
             while (lanes && !stop) {
                 const int src = __ffs(lanes) - 1; lanes &= lanes - 1;
                 uint32_t h = __shfl_sync(0xFFFFFFFFu, hits, src);
-                while (h && !stop) { const int j = 31 - __clz(h); h &= ~(1u << j); rev_start(i2, 4 * (g0 - src) + 1 + j); }
+                while (h && !stop) {
+                    const int b = 31 - __clz(h); h &= ~(1u << b);
+                    P2_PROF_T0(sc0);
+                    rev_start(i2, 4 * (g0 - 4 * src - (3 - (b >> 2))) + 1 + (b & 3));
+                    P2_PROF2_ADD(2, 1); P2_PROF2_ADD(4, clock64() - sc0);
+                }
             }
         }
       }
@@ -860,6 +983,9 @@ __device__ void enumerate_aligner(const View<WIDE> &V, int flag, BpList &L, Alig
         int *rlo = V.sc.rowrange, *rhi = V.sc.rowrange + (V.len2 + 2);
         P2_PROF_T0(pc);
         indel_row_ranges(V, rlo, rhi, lane);
+#ifdef AGE_P2_PROF
+        if (lane == 0 && V.od) { V.od[1] += (unsigned int)(clock64() - pc); V.od[2] += (unsigned int)V.sc.hotlist[0]; }
+#endif
         P2_PROF_ADD(1, pc);
         P2_PROF_RESET(pc);
         indel_enumerate(V, L, rlo, rhi, lane);
