@@ -523,6 +523,7 @@ age_blocks_kernel(Pass2Params prm)
     __shared__ int bp_s[P2_WARPS][MAX_BP][4];
     __shared__ WarpRings rings[P2_WARPS];
     __shared__ TraceSmem tsm[P2_WARPS];
+    __shared__ Block blk_s[P2_WARPS][2 * BLK_STAGE];      // blocks of the traceback at hand (emit_blocks)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (;;) {
         int item = 0;
@@ -548,7 +549,7 @@ age_blocks_kernel(Pass2Params prm)
             for (int i = lane; i < L.n * 4; i += 32) L.bp[i >> 2][i & 3] = O.bp[i >> 2][i & 3];
             __syncwarp();
             P2_PROF_T0(pc_pair);
-            emit_blocks(V, T.flag[h], L, O, prm.pool, prm.pool_cap, prm.pool_used, lane);
+            emit_blocks(V, T.flag[h], L, O, prm.pool, prm.pool_cap, prm.pool_used, lane, blk_s[w]);
             P2_PROF_PAIR(2, item, pc_pair);
 #ifdef AGE_P2_PROF
             if (lane == 0 && item < PROF_PAIRS) g_pair_cycles[4][item] += od_s[w][0];

@@ -837,12 +837,20 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
     P2_PROF_ADD(2, kc);
 }
 
-// K11 findLeftBlocks (:752-808).  dst == nullptr: count only.  Blocks are produced last-first; a block is a maximal
-// run of DIAGONAL codes (any H / V step in between starts a new block, :774-790).
+// K11 findLeftBlocks (:752-808).  dst == nullptr: count only -- the blocks found are left in `buf` (shared memory, walking
+// order, at most `cap` of them) so that the caller need not walk the path a second time once it has room for them.  Blocks are
+// produced last-first; a block is a maximal run of DIAGONAL codes (any H / V step in between starts a new block, :774-790).
 template <bool WIDE>
-__device__ int left_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_total, int lane)
+__device__ int left_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_total, int lane, Block *buf = nullptr, int cap = 0)
 {
     int n = 0, run = 0;
+    auto put = [&](const Block &b) {
+        if (lane == 0) {
+            if (dst && n < n_total) dst[n_total - 1 - n] = b;
+            if (buf && n < cap) buf[n] = b;
+        }
+        ++n;
+    };
     uint32_t t = V.code_at(0, r, c);
     while (t != T_STOP) {
         const int dr = t == T_HORI ? 0 : -1, dc = t == T_VERT ? 0 : -1;
@@ -850,29 +858,36 @@ __device__ int left_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_
         const int len = V.run_len(0, r, c, dr, dc, t, tn);
         r += len * dr; c += len * dc;
         if (t == T_DIAG) run += len;
-        else if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n_total - 1 - n] = Block{c - len * dc + 1, r - len * dr + 1, run}; ++n; run = 0; }
+        else if (run > 0) { put(Block{c - len * dc + 1, r - len * dr + 1, run}); run = 0; }
         t = tn != View<WIDE>::RUN_ON ? tn : V.code_at(0, r, c);
     }
-    if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n_total - 1 - n] = Block{c + 1, r + 1, run}; ++n; }
+    if (run > 0) put(Block{c + 1, r + 1, run});
     return n;       // (n <= n_total unless the trace pool overflowed between the counting and the writing pass: the batch is run again then)
 }
 
 // K12 findRightBlocks (:810-860)
 template <bool WIDE>
-__device__ int right_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_total, int lane)
+__device__ int right_blocks(const View<WIDE> &V, int c, int r, Block *dst, int n_total, int lane, Block *buf = nullptr, int cap = 0)
 {
     int n = 0, run = 0, s1 = 0, s2 = 0;
+    auto put = [&](const Block &b) {
+        if (lane == 0) {
+            if (dst && n < n_total) dst[n] = b;
+            if (buf && n < cap) buf[n] = b;
+        }
+        ++n;
+    };
     uint32_t t = V.code_at(2, r, c);
     while (t != T_STOP) {
         const int dr = t == T_HORI ? 0 : 1, dc = t == T_VERT ? 0 : 1;
         uint32_t tn;
         const int len = V.run_len(2, r, c, dr, dc, t, tn);
         if (t == T_DIAG) { if (run == 0) { s1 = c; s2 = r; } run += len; }     // interior cells only (:820 always holds)
-        else if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n] = Block{s1, s2, run}; ++n; run = 0; }
+        else if (run > 0) { put(Block{s1, s2, run}); run = 0; }
         r += len * dr; c += len * dc;
         t = tn != View<WIDE>::RUN_ON ? tn : V.code_at(2, r, c);
     }
-    if (run > 0) { if (dst && lane == 0 && n < n_total) dst[n] = Block{s1, s2, run}; ++n; }
+    if (run > 0) put(Block{s1, s2, run});
     return n;
 }
 
@@ -1128,21 +1143,25 @@ __device__ void alignment_numbers(const View<WIDE> &V, int flag, const Block *le
     }
 }
 
-// K10-K12: the tracebacks of bpoint 0 and of the alternative printAlignment shows (:287-306) into the block pool
+// K10-K12: the tracebacks of bpoint 0 and of the alternative printAlignment shows (:287-306) into the block pool.  A traceback
+// is a latency-bound walk: the counting walk leaves its blocks in shared memory (`stage`: 2 x BLK_STAGE blocks of this warp) and
+// they are copied into the pool once their place is known; only alignments with more blocks than that are walked twice.
+constexpr int BLK_STAGE = 64;
 template <bool WIDE>
-__device__ void emit_blocks(const View<WIDE> &V, int flag, const BpList &L, AlignerOut &O, Block *pool, int pool_cap, int32_t *pool_used, int lane)
+__device__ void emit_blocks(const View<WIDE> &V, int flag, const BpList &L, AlignerOut &O, Block *pool, int pool_cap, int32_t *pool_used, int lane, Block *stage)
 {
     int alt = -1;
     P2_PROF_T0(pc);
+    Block *sl = stage, *sr = stage + BLK_STAGE;
     for (int which = 0; which < 2; ++which) {
         int idx = 0, nl = 0, nr = 0;
         if (which == 0) {
-            nl = left_blocks(V, L.bp[0][0], L.bp[0][1], nullptr, 0, lane);
-            nr = right_blocks(V, L.bp[0][2], L.bp[0][3], nullptr, 0, lane);
+            nl = left_blocks(V, L.bp[0][0], L.bp[0][1], nullptr, 0, lane, sl, BLK_STAGE);
+            nr = right_blocks(V, L.bp[0][2], L.bp[0][3], nullptr, 0, lane, sr, BLK_STAGE);
         } else {
             for (idx = L.n - 1; idx >= 1; --idx) {
-                nl = left_blocks(V, L.bp[idx][0], L.bp[idx][1], nullptr, 0, lane);
-                nr = right_blocks(V, L.bp[idx][2], L.bp[idx][3], nullptr, 0, lane);
+                nl = left_blocks(V, L.bp[idx][0], L.bp[idx][1], nullptr, 0, lane, sl, BLK_STAGE);
+                nr = right_blocks(V, L.bp[idx][2], L.bp[idx][3], nullptr, 0, lane, sr, BLK_STAGE);
                 if (nl + nr > 0) break;
             }
             if (idx < 1) { nl = nr = 0; idx = -1; }
@@ -1153,8 +1172,12 @@ __device__ void emit_blocks(const View<WIDE> &V, int flag, const BpList &L, Alig
             if (lane == 0) off = atomicAdd(pool_used, nl + nr);
             off = __shfl_sync(0xFFFFFFFFu, off, 0);
             if (off + nl + nr <= pool_cap) {
-                left_blocks(V, L.bp[idx][0], L.bp[idx][1], pool + off, nl, lane);
-                right_blocks(V, L.bp[idx][2], L.bp[idx][3], pool + off + nl, nr, lane);
+                __syncwarp();                                                     // the staged blocks were written by lane 0
+                if (nl <= BLK_STAGE) { for (int i = lane; i < nl; i += 32) pool[off + nl - 1 - i] = sl[i]; }
+                else left_blocks(V, L.bp[idx][0], L.bp[idx][1], pool + off, nl, lane);
+                if (nr <= BLK_STAGE) { for (int i = lane; i < nr; i += 32) pool[off + nl + i] = sr[i]; }
+                else right_blocks(V, L.bp[idx][2], L.bp[idx][3], pool + off + nl, nr, lane);
+                __syncwarp();
                 if (which == 0) alignment_numbers(V, flag, pool + off, nl, pool + off + nl, nr, O, lane);
             } else if (lane == 0) O.status = -4;          // pool overflow: host retries with a larger pool
         } else if (which == 0 && lane < CALL_N) O.call[lane] = 0;

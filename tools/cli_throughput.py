@@ -50,6 +50,7 @@ def measure(n: int, devices: str = "0", chunk: int = 0, keep: str = "", verbose:
         res = run_once(cmd, out, env, n, False, verbose)
         res["fasta_bytes"] = sum(os.path.getsize(x) for x in (t, q, v))
         if also_binary:
+            time.sleep(2.0)      # the driver is still tearing down the first process's > 100 GB context: a start right behind it waits for that
             agb = os.path.join(d, "out.agb")
             res["binary"] = run_once(cmd[:1] + ["--binary-out", agb] + cmd[1:], agb, env, n, True, verbose)
     return res
