@@ -207,9 +207,9 @@ void sweep_plan(int n_pairs, int max_strips, int *nw_out, int *cs_out)
     const int force_nw = getenv("AGE_LONG_NW") ? atoi(getenv("AGE_LONG_NW")) : 0;   // test knobs: 1 = one warp per pair, 2..16 = pipelined,
     const int force_cs = getenv("AGE_LONG_CS") ? atoi(getenv("AGE_LONG_CS")) : 0;   // clusters of 2 / 4 CTAs
     if (max_strips > MAX_STRIPS_LONG) return;
-    if (force_nw >= 1 && force_nw <= 16 && (force_nw & (force_nw - 1)) == 0) {
+    if (force_nw >= 1 && force_nw <= 16) {
         *nw_out = force_nw;
-        if (force_nw > 1 && (force_cs == 2 || force_cs == 4)) *cs_out = force_cs;     // (AGE_LONG_CS=1 or unset: one CTA per pair)
+        if (force_nw > 1 && force_cs >= 2 && force_cs <= 4) *cs_out = force_cs;       // (AGE_LONG_CS=1 or unset: one CTA per pair)
         return;
     }
     if (n_pairs <= 0 || n_pairs >= sms * 16) return;

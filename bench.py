@@ -362,7 +362,7 @@ def main():
     ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="candidates per step per GPU (default 7104 for C2 = 3 pairs per resident warp: 148 SMs x 16 warps, about 125 GB of scratch; "
-                                                          "296 for C4, 72 for C5)")
+                                                          "296 for C4, 74 for C5 = one cluster of two SMs per pair)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cli", action="store_true", help="skip the age_align process leg (FASTA in -> .age out)")
@@ -393,7 +393,7 @@ def main():
     from asmvar_b200 import capi, engine
 
     if args.batch <= 0:
-        args.batch = {"c2": 7104, "c4": 296, "c5": 72}[args.workload]
+        args.batch = {"c2": 7104, "c4": 296, "c5": 74}[args.workload]
     cands, jobs, aligners, mode_opts = workload_jobs(args.workload, args.batch, rank)
     cu = cell_updates(cands, aligners)
     eng = engine.Engine([local])
@@ -491,7 +491,7 @@ def main():
 
     if rank == 0 and not args.no_extra and args.workload == "c2":
         extra = {}
-        for name, batch in (("c4", 296), ("c5", 72)):
+        for name, batch in (("c4", 296), ("c5", 74)):
             try:
                 xc, xj, xa, xm = workload_jobs(name, batch)
                 with engine.Engine([local]) as xe:
