@@ -475,10 +475,6 @@ size_t device_count()
     return n ? n : 1;
 }
 const size_t CHUNK = []{ const char *e = getenv("AGE_CHUNK"); const long v = e ? atol(e) : 0; return (size_t)(v > 0 ? v : 7104 * device_count()); }();
-// A chunk is closed by DP area as well (window length x contig length summed over its candidates): the default is what 7104
-// candidates of 5 kb x 1.5 kb come to per device, so that chunks of short candidates hold proportionally more of them (a batch
-// of a few thousand 1 kb x 500 bp candidates leaves the GPU idle most of the time) -- at most 16 x CHUNK candidates.
-const double CHUNK_AREA = []{ const char *e = getenv("AGE_CHUNK_AREA"); const double v = e ? atof(e) : 0; return v > 0 ? v : (getenv("AGE_CHUNK") ? 0.0 : 5.3e10 * device_count()); }();
 
 // ---------------------------------------------------------------------------------------------------------
 // batch dialect (age_align.cpp)
@@ -602,7 +598,6 @@ int batch_main(int argc, char **argv)
     const bool all = usel == "ALL";
     struct Pick { const Reg *r; const string *t, *q; };
     vector<Pick> picks;
-    double pick_area = 0;
     vector<Candidate> cands;
     auto cut = [&]() {
         cands.resize(picks.size());
@@ -633,8 +628,7 @@ int batch_main(int argc, char **argv)
         const auto qi = qfa.find(r.qid);
         if (qi == qfa.end()) { cut(); drain_candidates(); cerr << "# [ERROR] " << r.qid << " is not in " << qfile << "\n"; die(1); }
         picks.push_back(Pick{&r, &ti->second, &qi->second});
-        pick_area += (double)max(0LL, r.te - r.ts + 1) * (double)max(0LL, r.qe - r.qs + 1);
-        if ((picks.size() >= CHUNK && pick_area >= CHUNK_AREA) || picks.size() >= 16 * CHUNK) { cut(); pick_area = 0; }
+        if (picks.size() >= CHUNK) cut();
     }
     cut();
     prof("all windows cut");

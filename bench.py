@@ -300,9 +300,7 @@ def inproc_leg(devices, single_device_results=None):
     gen_s = time.perf_counter() - t0
     kinds = {"indel": capi.INDEL_FLAG, "tdup": capi.TDUPLICATION_FLAG}
     nd = len(devices)
-    # batches are closed by DP area (window length x contig length summed over the candidates), about one default C2 batch per
-    # device, so that the batches of the short bins hold proportionally more candidates (the product CLI cuts its chunks alike)
-    area_target, max_batch = 5.3e10 * nd, 65536 * nd
+    per_batch = 4096 * nd
     summary = {}
     total_s = 0.0
     total_c = 0
@@ -314,17 +312,10 @@ def inproc_leg(devices, single_device_results=None):
             # length-binned: candidates of similar DP area share a batch, so no warp is left with one long pair while the
             # others run out of short ones (the caller owns the order of its results; nothing is printed here)
             cands.sort(key=lambda c: len(c[0]) * len(c[1]), reverse=True)
-            total_area = float(sum(len(w) * len(q) for w, q in cands)) * INPROC_REPEAT
-            area_batch = min(area_target, total_area / 6)           # (a fixed set on many devices: keep a handful of batches to pipeline)
-            batches, cur, area = [], [], 0.0
-            for c in cands:
-                cur.append(c); area += len(c[0]) * len(c[1])
-                if area >= area_batch or len(cur) >= max_batch:
-                    batches.append(cur); cur, area = [], 0.0
-            if cur:
-                batches.append(cur)
+            batches = [cands[i:i + per_batch] for i in range(0, len(cands), per_batch)]
             prepared = [eng.make_jobs(both_jobs(b, flag)) for b in batches] * INPROC_REPEAT      # the same job arrays again: nothing is cached between batches
-            outs = [(capi.AgeResult * max(1, p[2]))() for p in prepared[:2]]
+            n_max = max(p[2] for p in prepared)
+            outs = [(capi.AgeResult * max(1, n_max))() for _ in range(2)]          # batches differ in size: two result arrays of the largest
             # warm-up: first batch once (arena allocation, clocks)
             eng.align_raw(prepared[0][0], prepared[0][2], outs[0])
             t0 = time.perf_counter()
@@ -352,7 +343,7 @@ def inproc_leg(devices, single_device_results=None):
             checks.append((kind, scores))
     return {"value": total_c / total_s, "unit": "realignments/s", "gcups": total_cu / total_s / 1e9, "candidates": total_c, "seconds": total_s,
             "devices": nd, "per_mode": summary, "generate_s": gen_s, "scaling": "strong",
-            "api": f"one age_create over {nd} device(s); age_submit/age_collect, length-binned batches of {area_target:.3g} DP cells (at most {max_batch} candidates), two in flight",
+            "api": f"one age_create over {nd} device(s); age_submit/age_collect, length-binned batches of {per_batch} candidates, two in flight",
             "workload": f"C3-style fixed set ({INPROC_CANDIDATES} candidates x {INPROC_REPEAT}): len1 in {{1,2,4,8}} kb x len2 in {{0.5,1,2}} kb, 70 % indel / 30 % tdup, -both"}, checks
 
 

@@ -149,6 +149,51 @@ def test_homopolymer_and_degenerate(eng):
     check_against_oracle(eng, jobs)
 
 
+def gapped_copy(rng, s, every):
+    """`s` with one base dropped about every `every` bases: an alignment of many short diagonal blocks"""
+    out, i = bytearray(), 0
+    while i < len(s):
+        n = int(rng.integers(max(2, every - 3), every + 4))
+        out += s[i:i + n]
+        i += n + 1
+    return bytes(out)
+
+
+def test_many_blocks_per_fragment(eng):
+    """alignments of 100+ diagonal blocks per fragment (cheap gaps, a base missing every ~9 bases of the flanks): more than the
+    blocks kernel stages in shared memory, so the second traversal that writes straight into the pool runs as well"""
+    rng = np.random.default_rng(21)
+    jobs = []
+    for flag, L in ((capi.INDEL_FLAG, 700), (capi.INDEL_FLAG, 40), (capi.TDUPLICATION_FLAG, 500)):
+        w = rand_seq(rng, 3600, "ACGT")
+        a = 1300
+        if flag == capi.INDEL_FLAG:
+            q = gapped_copy(rng, w[a - 1000:a], 9) + gapped_copy(rng, w[a + L:a + L + 1000], 9)
+        else:
+            q = gapped_copy(rng, w[a + L - 1000:a + L], 9) + gapped_copy(rng, w[a:a + 1000], 9)
+        jobs.append((w, q, flag, 5, -4, -2, -1))
+    res = eng.align(jobs)
+    assert max(len(r["left"]) for r in res) > 64 and max(len(r["right"]) for r in res) > 64, [(len(r["left"]), len(r["right"])) for r in res]
+    check_against_oracle(eng, jobs)
+
+
+def test_long_runs_and_wide_ranges(eng):
+    """walks along the whole excised stretch (3 kb deletion, 1.2 kb insertion: straight runs of the maxima planes read 256
+    cells per pass, look-ahead stops at windows that were never swept) and split columns several cells wide (the last bases
+    of the left flank repeat behind the insertion, so that many rows tie in several columns)"""
+    rng = np.random.default_rng(22)
+    jobs = []
+    w = rand_seq(rng, 6000, "ACGT")
+    jobs.append((w, w[800:1400] + w[4400:5000], capi.INDEL_FLAG, 1, -1, -10, -1))                                # deletion of 3 kb
+    jobs.append((w, w[2000:2600] + rand_seq(rng, 1200, "ACGT") + w[2600:3200], capi.INDEL_FLAG, 1, -1, -10, -1))  # insertion of 1.2 kb
+    rep = w[2588:2600]                                                                                          # micro-homology at the junction
+    jobs.append((w, w[2000:2600] + rep * 3 + rand_seq(rng, 900, "ACGT") + rep + w[2600:3200], capi.INDEL_FLAG, 1, -1, -10, -1))
+    jobs.append((w, mutate(rng, w[1000:1700] + rand_seq(rng, 700, "ACGT") + w[1700:2400], 0.02, 0.004), capi.INDEL_FLAG, 1, -1, -10, -1))
+    jobs.append((w, w[3000:3700] + w[1500:2200], capi.TDUPLICATION_FLAG, 1, -1, -10, -1))                          # tandem duplication junction
+    jobs.append((w, w[1000:1800] + U.revcom_str(w[1800:2600].decode()).encode(), capi.INVERSION_FLAG, 1, -1, -10, -1))
+    check_against_oracle(eng, jobs)
+
+
 def test_not_aligned_and_range(eng):
     res = eng.align([(b"", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1), (b"ACGT", b"ACGT", 0, 1, -1, -10, -1),
                      (b"ACGT", b"ACGT", capi.INDEL_FLAG, 20000, -1, -10, -1), (b"ACGT", b"ACGT", capi.INDEL_FLAG, 1, -1, -10, -1)])
