@@ -47,7 +47,7 @@ SCORE_OPTS = ["-m", str(SCORING[0]), "-M", str(SCORING[1]), "-g", str(SCORING[2]
 ALU_INSTR_PER_CELL_UPDATE = (6 + 8) / 2 / 2
 # DRAM traffic of age_sweep_kernel in the committed `ncu --set full` capture (profiles/r1b_sweep_kernel_ncu_key_metrics.txt):
 # dram__bytes_read.sum 96.09 GB + dram__bytes_write.sum 101.08 GB for one launch over 137.24 G cell updates (5920 C2 candidates)
-NCU_DRAM_BYTES_PER_CELL_UPDATE = (96.086718e9 + 101.077318e9) / 137.23574e9
+NCU_DRAM_BYTES_PER_CELL_UPDATE = (115.267648e9 + 121.262472e9) / 164.6323e9      # profiles/r2u_sweep_key_metrics.txt (7104 candidates); round 1 at 5920: 1.4367 as well
 WORKLOADS = {
     "c2": "C2 synthetic indel candidates: 5 kb windows, 2x500 bp flanks, -indel -both, 1/-1/-10/-1",
     "c4": "C4 synthetic inversions: 20 kb windows, 2 x 2 kb flanks, -inv, 1/-1/-10/-1",
@@ -467,7 +467,7 @@ def main():
         traffic = NCU_DRAM_BYTES_PER_CELL_UPDATE * cu / 1e9 if args.workload == "c2" else None
         line["roofline"] = {
             "bound": "int16x2 SIMD issue (ALU pipe)", "achieved": ach_i, "peak": peak.value if have_peak else None, "unit": "G lane-instr/s",
-            "frac": ach_i / peak.value if have_peak else None, "traffic": traffic, "traffic_unit": "GB of DRAM read+write per launch (ncu capture of round 1, scaled by cell updates)",
+            "frac": ach_i / peak.value if have_peak else None, "traffic": traffic, "traffic_unit": "GB of DRAM read+write per launch (dram__bytes of the ncu capture in profiles/r2u_sweep_key_metrics.txt per cell update, times the cell updates of this launch)",
             "kernel": "age_sweep_kernel", "kernel_ms": fill_ms, "cell_updates_per_launch": cu, "alu_instr_per_cell_update": ALU_INSTR_PER_CELL_UPDATE,
             "note": "achieved = 3.5 ALU-pipe instructions per cell update (6 forward / 8 reverse per packed pair cell; the FMA-pipe multiply-adds are not "
                     "counted) x cell updates of one launch / the kernel's CUDA-event time; peak = age_int16_peak microbenchmark on this GPU "
