@@ -45,9 +45,9 @@ SCORE_OPTS = ["-m", str(SCORING[0]), "-M", str(SCORING[1]), "-g", str(SCORING[2]
 # (VIMNMX, PRMT, VIADDMNMX.RELU, LOP3, VIADD, VIMNMX3), 8 in the reverse one (+ offset decode, VIADDMNMX.U16x2 for the split
 # sum); a pair cell is two cell updates.  The two multiply-adds per pair cell run on the FMA pipe and are not counted.
 ALU_INSTR_PER_CELL_UPDATE = (6 + 8) / 2 / 2
-# DRAM traffic of age_sweep_kernel in the committed `ncu --set full` capture (profiles/r1b_sweep_kernel_ncu_key_metrics.txt):
-# dram__bytes_read.sum 96.09 GB + dram__bytes_write.sum 101.08 GB for one launch over 137.24 G cell updates (5920 C2 candidates)
-NCU_DRAM_BYTES_PER_CELL_UPDATE = (115.267648e9 + 121.262472e9) / 164.6323e9      # profiles/r2u_sweep_key_metrics.txt (7104 candidates); round 1 at 5920: 1.4367 as well
+# DRAM traffic of age_sweep_kernel in the committed `ncu --set full` capture (profiles/r2u_sweep_key_metrics.txt):
+# dram__bytes_read.sum 115.27 GB + dram__bytes_write.sum 121.26 GB for one launch over 164.63 G cell updates (7104 C2 candidates)
+NCU_DRAM_BYTES_PER_CELL_UPDATE = (115.267648e9 + 121.262472e9) / 164.6323e9      # (round 1, 5920 candidates: the same 1.437 B per cell update)
 WORKLOADS = {
     "c2": "C2 synthetic indel candidates: 5 kb windows, 2x500 bp flanks, -indel -both, 1/-1/-10/-1",
     "c4": "C4 synthetic inversions: 20 kb windows, 2 x 2 kb flanks, -inv, 1/-1/-10/-1",
