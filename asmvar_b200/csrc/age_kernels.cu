@@ -606,7 +606,7 @@ static void launch_pass2_t(const Pass2Params &p, cudaStream_t st)
             const int i = order[k];
             AlignerOut ao[2] = {};
             for (int h = 0; h < 2; ++h) if (pt[i].out[h] >= 0) cudaMemcpy(&ao[h], p.outs + pt[i].out[h], 32, cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[p2 prof]   pair %5d: len1 %d len2 %d, enumerate %.2f M + path queueing %.2f M, blocks %.2f M cycles; K6: %u hot windows, ranges %.2f M, forward scan %.2f M, %u narrow passes, %u wide rows, %u walks taking %.2f M; on demand %u + %u windows; n_bp %d / %d, score %d / %d\n",
+            fprintf(stderr, "[p2 prof]   pair %5d: len1 %d len2 %d, enumerate %.2f M + path queueing %.2f M, blocks %.2f M cycles; K6: %u hot windows, ranges (K7: start cells) %.2f M, forward scan (K7: ensure_rm) %.2f M, %u narrow passes (K7: tie rows), %u wide rows (K7: start cells), %u walks taking %.2f M; on demand %u + %u windows; n_bp %d / %d, score %d / %d\n",
                     i, pt[i].len1, pt[i].len2, cyc[i] / 1e6, cyc[PROF_PAIRS + i] / 1e6, cyc[2 * PROF_PAIRS + i] / 1e6, cyc[6 * PROF_PAIRS + i], cyc[5 * PROF_PAIRS + i] / 1e6, cyc[7 * PROF_PAIRS + i] / 1e6, cyc[8 * PROF_PAIRS + i], cyc[9 * PROF_PAIRS + i], cyc[10 * PROF_PAIRS + i], cyc[11 * PROF_PAIRS + i] / 1e6,
                     cyc[3 * PROF_PAIRS + i], cyc[4 * PROF_PAIRS + i],
                     ao[0].n_bp, ao[1].n_bp, ao[0].score, ao[1].score);

@@ -719,9 +719,11 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
       while (tie_rows && !stop) {
         const int r = rb + __ffs(tie_rows) - 1; tie_rows &= tie_rows - 1;
         P2_PROF2_ADD(0, 1);
+        P2_OD(V, 4, 1);
         P2_PROF_T0(ec);
         if (r + 1 <= len2) V.ensure_rm(r >> 8);                           // row r+1 of Rmax and RM
         P2_PROF2_ADD(5, clock64() - ec);
+        P2_OD(V, 3, clock64() - ec);
         if (r == 0) {                                                     // border row: only (0, 0) has FM = 0 (:874-882)
             fwd_start(0, 0);
             continue;
@@ -754,7 +756,7 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
                     const int b = __ffs(h) - 1; h &= h - 1;
                     P2_PROF_T0(sc0);
                     fwd_start(r, 4 * (g0 + 4 * src + (b >> 2)) + 1 + (b & 3));
-                    P2_PROF2_ADD(1, 1); P2_PROF2_ADD(3, clock64() - sc0);
+                    P2_PROF2_ADD(1, 1); P2_PROF2_ADD(3, clock64() - sc0); P2_OD(V, 5, 1); P2_OD(V, 1, clock64() - sc0);
                 }
             }
         }
@@ -795,9 +797,12 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
       unsigned tie_rows = __ballot_sync(0xFFFFFFFFu, rb + lane >= 1 && rb + lane <= len2 + 1 && A(rb + lane - 1) + B(rb + lane) == max2);
       while (tie_rows && !stop) {
         const int i2 = rb + 31 - __clz(tie_rows); tie_rows &= ~(1u << (i2 - rb));
+        P2_OD(V, 4, 1);
+        P2_PROF_T0(ec2);
         if (i2 <= len2) V.ensure_rm((i2 - 1) >> 8);
+        P2_OD(V, 3, clock64() - ec2);
         if (i2 > len2) {                                                  // border row: RM is 0 in every column (:924-932)
-            for (int j2 = len1 + 1; j2 >= 1 && !stop; --j2) rev_start(i2, j2);
+            for (int j2 = len1 + 1; j2 >= 1 && !stop; --j2) { P2_PROF_T0(sc0); rev_start(i2, j2); P2_OD(V, 5, 1); P2_OD(V, 1, clock64() - sc0); }
             continue;
         }
         rev_start(i2, len1 + 1);                                          // border column
@@ -828,7 +833,7 @@ __device__ void invtdup_enumerate(const View<WIDE> &V, BpList &L, int lane)
                     const int b = 31 - __clz(h); h &= ~(1u << b);
                     P2_PROF_T0(sc0);
                     rev_start(i2, 4 * (g0 - 4 * src - (3 - (b >> 2))) + 1 + (b & 3));
-                    P2_PROF2_ADD(2, 1); P2_PROF2_ADD(4, clock64() - sc0);
+                    P2_PROF2_ADD(2, 1); P2_PROF2_ADD(4, clock64() - sc0); P2_OD(V, 5, 1); P2_OD(V, 1, clock64() - sc0);
                 }
             }
         }
