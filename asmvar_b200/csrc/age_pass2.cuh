@@ -7,6 +7,10 @@
 #pragma once
 #include "age_sweep.cuh"
 
+// AGE_K7_LADDER: how many VERTICAL steps merges_into_next follows before it gives up and lets the walk be made (any value is exact)
+#ifndef AGE_K7_LADDER
+#define AGE_K7_LADDER 64
+#endif
 // AGE_V_WIDERUN (build switch for A/B measurements): 1 = straight runs of the maxima planes are read 256 cells per pass, 0 = 32
 #ifndef AGE_V_WIDERUN
 #define AGE_V_WIDERUN 1
@@ -313,14 +317,14 @@ template <bool WIDE> struct View {
         int d0 = 0, d1 = 0;
         uint32_t c0 = T_STOP, c1 = T_STOP;
         bool run0 = in, run1 = in;
-        for (int depth = 0; depth < 64; ++depth) {
+        for (int depth = 0; depth < AGE_K7_LADDER; ++depth) {
             ensure_lanes(plane, run0 ? r + depth * dir : -1, x);
             ensure_lanes(plane, run1 ? r + depth * dir : -1, x + dir);
             if (run0) { c0 = code_nc(plane, r + depth * dir, x); if (c0 == T_VERT) d0 = depth + 1; else run0 = false; }
             if (run1) { c1 = code_nc(plane, r + depth * dir, x + dir); if (c1 == T_VERT) d1 = depth + 1; else run1 = false; }
             if (!__any_sync(0xFFFFFFFFu, run0 || run1)) break;
         }
-        if (!in || run0 || run1) return false;            // deeper ladders than 64 rows are walked one by one
+        if (!in || run0 || run1) return false;            // deeper ladders than AGE_K7_LADDER rows are walked one by one
         return c0 == T_HORI && (d0 == 0 || d0 == d1);
     }
     __device__ uint32_t code_at(int plane, int r, int c) const {      // warp-uniform single read
