@@ -497,7 +497,7 @@ def main():
                                "int_frac": (ALU_INSTR_PER_CELL_UPDATE * xcu * 4 / (ms / 1e3) / 1e9 / peak.value) if have_peak else None,
                                "int_frac_note": "whole step (sweeps + pass 2) against the ALU-pipe peak"}
                 if not args.no_cpu:
-                    extra[name].update(extra_parity(name, xc, xm, str(local), 2 if name == "c4" else 1))
+                    extra[name].update(extra_parity(name, xc, xm, str(local), 8 if name == "c4" else 4))      # reference stdout diffed on 8 C4 / 4 C5 candidates
             except Exception as e:
                 extra[name] = {"value": None, "note": f"unavailable: {e}"}
         line["extra"] = extra
