@@ -29,12 +29,21 @@ char complement(char c)
 
 static inline int up(char c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
 
-bool same_nuc(char a, char b)
-{   // Sequence.hh:182-188
-    int aa = up(a), bb = up(b);
-    if (aa != bb) return false;
-    return aa == 'A' || aa == 'C' || aa == 'T' || aa == 'G' || aa == 'U';
-}
+// Nucleotide classes of Sequence::sameNuc (Sequence.hh:182-188): the five letters it accepts, case-insensitive; 0 = anything
+// else, which never matches (not even itself).
+struct NucTable {
+    unsigned char v[256];
+    constexpr NucTable() : v{}
+    {
+        v[(unsigned char)'A'] = v[(unsigned char)'a'] = 1; v[(unsigned char)'C'] = v[(unsigned char)'c'] = 2;
+        v[(unsigned char)'G'] = v[(unsigned char)'g'] = 3; v[(unsigned char)'T'] = v[(unsigned char)'t'] = 4;
+        v[(unsigned char)'U'] = v[(unsigned char)'u'] = 5;
+    }
+};
+static constexpr NucTable NUC{};
+static inline bool same_nuc_fast(char a, char b) { const unsigned char x = NUC.v[(unsigned char)a]; return x != 0 && x == NUC.v[(unsigned char)b]; }
+
+bool same_nuc(char a, char b) { return same_nuc_fast(a, b); }
 
 static inline bool is_gap(char c) { return c == ' ' || c == '-'; }   // Sequence.hh:175-180
 
@@ -42,8 +51,19 @@ static inline bool is_gap(char c) { return c == ' ' || c == '-'; }   // Sequence
 struct Out {
     char *buf; size_t cap; size_t n;
     void put(char c) { if (n + 1 < cap) buf[n] = c; n++; }
-    void put(const char *s) { while (*s) put(*s++); }
-    void put(const char *s, size_t len) { for (size_t i = 0; i < len; i++) put(s[i]); }
+    void put(const char *s, size_t len)
+    {
+        if (n + len < cap) memcpy(buf + n, s, len);
+        else for (size_t i = 0; i < len; i++) if (n + i + 1 < cap) buf[n + i] = s[i];
+        n += len;
+    }
+    void put(const char *s) { put(s, strlen(s)); }
+    void fill(char c, size_t len)
+    {
+        if (n + len < cap) memset(buf + n, c, len);
+        else for (size_t i = 0; i < len; i++) if (n + i + 1 < cap) buf[n + i] = c;
+        n += len;
+    }
     void num(long v, int width = 0)
     {   // operator<<(int) with setw(width), right aligned, fill ' '
         char tmp[24]; int k = 0; bool neg = v < 0; unsigned long u = neg ? 0ul - (unsigned long)v : (unsigned long)v;
@@ -71,9 +91,17 @@ struct Frag {
     int start1, start2, end1, end2;
 };
 
-struct SeqHdr { const char *seq; int len; int start; bool reverse; };
+struct SeqHdr { const char *seq; int len; int start; bool reverse; const unsigned char *nuc = nullptr; };     // nuc: classes of NUC per position (optional)
 
 static inline char at(const SeqHdr &s, long i) { return (i >= 0 && i < s.len) ? s.seq[i] : '\0'; }
+
+// classes of every base of a sequence for the breakpoint identities (thread-local storage: no allocation per record)
+static void classify(SeqHdr &s, std::vector<unsigned char> &store)
+{
+    store.resize((size_t)std::max(s.len, 1));
+    for (int i = 0; i < s.len; i++) store[(size_t)i] = NUC.v[(unsigned char)s.seq[i]];
+    s.nuc = store.data();
+}
 
 // findAlignment (AGEaligner.cpp:670-750): blocks -> gapped strings + coordinates
 static void build_frags(const SeqHdr &s1, const SeqHdr &s1rc, const SeqHdr &s2, int flag,
@@ -94,14 +122,34 @@ static void build_frags(const SeqHdr &s1, const SeqHdr &s1rc, const SeqHdr &s2, 
         f.start2 = s2.start + inc2 * (bl[0].start2 - 1);
         f.end1 = f.end2 = 0;
         int ind1 = bl[0].start1 - 1, ind2 = bl[0].start2 - 1;
+        // columns of the fragment: every base of either sequence between the first and the last block is one
+        size_t cols = 0;
+        {
+            int i1 = ind1, i2 = ind2;
+            for (int k = 0; k < nb[b]; k++) {
+                cols += (size_t)std::max(0, bl[k].start1 - 1 - i1) + (size_t)std::max(0, bl[k].start2 - 1 - i2) + (size_t)std::max(0, bl[k].length);
+                i1 = std::max(i1, bl[k].start1 - 1) + std::max(0, bl[k].length); i2 = std::max(i2, bl[k].start2 - 1) + std::max(0, bl[k].length);
+            }
+        }
+        f.a1.resize(cols); f.a2.resize(cols);
+        char *p1 = &f.a1[0], *p2 = &f.a2[0];
+        size_t w = 0;
+        // (blocks inside both sequences: plain copies; anything else goes through at(), which yields '\0' outside)
+        auto copy1 = [&](char *dst, const SeqHdr &q, int from, int len) {
+            if (from >= 0 && from + len <= q.len) memcpy(dst, q.seq + from, (size_t)len);
+            else for (int i = 0; i < len; i++) dst[i] = at(q, (long)from + i);
+        };
         for (int k = 0; k < nb[b]; k++) {
             f.end1 = q1.start + inc1 * (bl[k].start1 + bl[k].length - 2);
             f.end2 = s2.start + inc2 * (bl[k].start2 + bl[k].length - 2);
             int st1 = bl[k].start1 - 1, st2 = bl[k].start2 - 1;
-            while (ind1 < st1) { f.a1 += at(q1, ind1++); f.a2 += '-'; }
-            while (ind2 < st2) { f.a1 += '-'; f.a2 += at(s2, ind2++); }
-            for (int i = 0; i < bl[k].length; i++) { f.a1 += at(q1, ind1++); f.a2 += at(s2, ind2++); }
+            if (ind1 < st1) { const int g = st1 - ind1; copy1(p1 + w, q1, ind1, g); memset(p2 + w, '-', (size_t)g); w += (size_t)g; ind1 = st1; }
+            if (ind2 < st2) { const int g = st2 - ind2; memset(p1 + w, '-', (size_t)g); copy1(p2 + w, s2, ind2, g); w += (size_t)g; ind2 = st2; }
+            const int len = std::max(0, bl[k].length);
+            copy1(p1 + w, q1, ind1, len); copy1(p2 + w, s2, ind2, len);
+            w += (size_t)len; ind1 += len; ind2 += len;
         }
+        f.a1.resize(w); f.a2.resize(w);
         if (!f.a1.empty() && f.a1.size() == f.a2.size()) frags.push_back(std::move(f));
     }
 }
@@ -133,14 +181,36 @@ static bool excised_range(int flag, bool rev1, const Frag &f, const Frag &nx, in
 static int head_tail_overlap(const SeqHdr &q, long head, long tail, int n)
 {
     if (n <= 0) return 0;
+    // Nearly every candidate length fails at its first or second base, so the lengths are simply tried from the longest down
+    // (what the reference does), on the nucleotide classes of the sequence (SeqHdr::nuc: one table look-up per base, made once
+    // per record; then plain byte compares) -- but only with a budget of comparisons: a repetitive stretch that makes many lengths fail
+    // late falls through to the prefix function below, which is linear whatever the sequence.
+    if (q.nuc && head >= 0 && tail - n + 1 >= 0 && head + n <= q.len && tail < q.len) {
+        const unsigned char *hd = q.nuc + head, *tl = q.nuc + tail;
+        const unsigned char h0 = hd[0];
+        if (h0 == 0) return 0;                                                                 // no length can match at its first base
+        long budget = 8L * n + 64;
+        int m = n;
+        for (; m >= 1 && budget > 0; --m) {
+            const unsigned char *t0 = tl - m + 1;
+            if (t0[0] != h0) continue;
+            int k = 1;
+            while (k < m && hd[k] != 0 && hd[k] == t0[k]) ++k;
+            budget -= k;
+            if (k == m) return m;
+        }
+        if (m < 1) return 0;
+    }
     auto norm = [&](long i, char bad) {
-        const char c = (char)up(at(q, i));
-        return (c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'U') ? c : bad;
+        const unsigned char c = NUC.v[(unsigned char)at(q, i)];
+        return c ? (char)(c + 8) : bad;
     };
-    std::vector<char> t((size_t)2 * n + 1);
+    thread_local std::vector<char> t;
+    thread_local std::vector<int> pf;
+    t.assign((size_t)2 * n + 1, 0);
     for (int i = 0; i < n; i++) { t[i] = norm(head + i, 1); t[n + 1 + i] = norm(tail - n + 1 + i, 2); }
     t[n] = 3;
-    std::vector<int> pf(t.size(), 0);
+    pf.assign(t.size(), 0);
     for (size_t i = 1; i < t.size(); i++) {
         int k = pf[i - 1];
         while (k > 0 && t[i] != t[k]) k = pf[k - 1];
@@ -172,8 +242,8 @@ static int at_identity(const SeqHdr &q, int bp1, int bp2, int &left, int &right)
     if (bp1 >= bp2) return 0;
     const long shift = (long)bp2 - bp1;
     int down = 0, up = 0;
-    for (long i = bp1 - 1; i >= 0 && same_nuc(at(q, i), at(q, i + shift)); --i) ++down;
-    for (long i = bp1; i < q.len && same_nuc(at(q, i), at(q, i + shift)); ++i) ++up;
+    for (long i = bp1 - 1; i >= 0 && same_nuc_fast(at(q, i), at(q, i + shift)); --i) ++down;
+    for (long i = bp1; i < q.len && same_nuc_fast(at(q, i), at(q, i + shift)); ++i) ++up;
     left = -down; right = up;
     return up + down;
 }
@@ -214,7 +284,7 @@ static void print_frag(Out &o, const Frag &f)
         const char *a1 = f.a1.data() + i, *a2 = f.a2.data() + i;
         int nuc1 = 0, nuc2 = 0;
         for (int j = 0; j < w; j++) {
-            if (same_nuc(a1[j], a2[j])) match[j] = '|';
+            if (same_nuc_fast(a1[j], a2[j])) match[j] = '|';
             else if (!is_gap(a1[j]) && !is_gap(a2[j])) match[j] = '.';
             else match[j] = ' ';
             if (!is_gap(a1[j])) { nuc1++; ind1 += inc1; }
@@ -222,11 +292,11 @@ static void print_frag(Out &o, const Frag &f)
         }
         o.put('\n');
         if (nuc1 > 0) { o.num(st1, MARGIN); o.put(' '); o.put(a1, w); o.put(' '); o.num(ind1 - inc1); o.put('\n'); }
-        else { for (int k = 0; k <= MARGIN; k++) o.put(' '); o.put(a1, w); o.put('\n'); }
-        for (int k = 0; k <= MARGIN; k++) o.put(' ');
+        else { o.fill(' ', MARGIN + 1); o.put(a1, w); o.put('\n'); }
+        o.fill(' ', MARGIN + 1);
         o.put(match, w); o.put('\n');
         if (nuc2 > 0) { o.num(st2, MARGIN); o.put(' '); o.put(a2, w); o.put(' '); o.num(ind2 - inc2); o.put('\n'); }
-        else { for (int k = 0; k <= MARGIN; k++) o.put(' '); o.put(a2, w); o.put('\n'); }
+        else { o.fill(' ', MARGIN + 1); o.put(a2, w); o.put('\n'); }
     }
 }
 
@@ -275,7 +345,7 @@ size_t format_alignment(const age_seqview *v1, const age_seqview *v2, const age_
         const Frag &f = frags[k];
         for (size_t i = 0; i < f.a1.size(); i++) {
             n_ali[k + 1]++;
-            if (same_nuc(f.a1[i], f.a2[i])) n_id[k + 1]++;
+            if (same_nuc_fast(f.a1[i], f.a2[i])) n_id[k + 1]++;
             if (is_gap(f.a1[i]) || is_gap(f.a2[i])) n_gap[k + 1]++;
         }
         n_ali[0] += n_ali[k + 1]; n_id[0] += n_id[k + 1]; n_gap[0] += n_gap[k + 1];
@@ -317,6 +387,8 @@ size_t format_alignment(const age_seqview *v1, const age_seqview *v2, const age_
     }
 
     if (n_frg > 1) {
+        thread_local std::vector<unsigned char> cls1, cls2;
+        classify(s1, cls1); classify(s2, cls2);
         o.put("\nEXCISED REGION(S):\n");
         excised_lines(o, flag, s1.reverse, s2.reverse, frags);
 
