@@ -372,21 +372,35 @@ bool print_chunk(Chunk &ch)
                 age_seqview v1{c.s1.seq.data(), (int32_t)c.s1.seq.size(), c.s1.name.c_str(), c.s1.start, c.s1.reverse ? 1 : 0};
                 age_seqview v2{q.seq.data(), (int32_t)q.seq.size(), q.name.c_str(), q.start, q.reverse ? 1 : 0};
                 const age_job &j = ch.jobs[c.job[pick]];
-                const size_t h = out.size();
-                out.resize(h + 8192 + 8 * (c.s1.seq.size() + q.seq.size()));
-                size_t m = age_format_alignment(&v1, &v2, &j, r, &out[h], out.size() - h);
-                if (m >= out.size() - h) { out.resize(h + m + 1); m = age_format_alignment(&v1, &v2, &j, r, &out[h], out.size() - h); }
-                out.resize(h + m);
+                // formatted into a scratch buffer that the worker thread keeps (sizing and zero-filling a worst-case string per
+                // record cost several times the formatting itself), then appended
+                thread_local string scratch;
+                const size_t need = 8192 + 8 * (c.s1.seq.size() + q.seq.size());
+                if (scratch.size() < need) scratch.resize(need);
+                size_t m = age_format_alignment(&v1, &v2, &j, r, &scratch[0], scratch.size());
+                if (m >= scratch.size()) { scratch.resize(m + 1); m = age_format_alignment(&v1, &v2, &j, r, &scratch[0], scratch.size()); }
+                out.append(scratch.data(), m);
             }
         }
         else if (g_binary) { Bytes b; binary_record(b, c, 255, ch.per, nullptr); out.swap(b.b); return; }
         if (ch.age_time) { char t[64]; snprintf(t, sizeof t, "\nAlignment time is %g s\n\n", ch.per); out += t; }
     });
+    // one write per chunk (the records of a chunk are tens of megabytes: one call instead of thousands); a record with a
+    // message for stderr ends the run that is written before it, so that the two streams interleave as in the serial loop
+    FILE *dst = g_binary ? g_binary : stdout;
+    string run;
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) total += text[i].size();
+    run.reserve(total);
     for (size_t i = 0; i < n; ++i) {
-        fwrite(text[i].data(), 1, text[i].size(), g_binary ? g_binary : stdout);
-        if (!note[i].empty()) { fflush(stdout); cerr << note[i] << flush; }
-        if (bad[i]) return false;
+        run += text[i];
+        if (!note[i].empty() || bad[i]) {
+            fwrite(run.data(), 1, run.size(), dst); run.clear();
+            if (!note[i].empty()) { fflush(stdout); cerr << note[i] << flush; }
+            if (bad[i]) return false;
+        }
     }
+    fwrite(run.data(), 1, run.size(), dst);
     fflush(stdout);
     return true;
 }
@@ -854,11 +868,12 @@ int age2text_main(int argc, char **argv)
             j.flag = flag; j.match = sc[0]; j.mismatch = sc[1]; j.gap_open = sc[2]; j.gap_extend = sc[3]; j.partner = -1;
             age_seqview v1{s1.seq.data(), (int32_t)s1.seq.size(), s1.name.c_str(), s1.start, s1.reverse ? 1 : 0};
             age_seqview v2{s2.seq.data(), (int32_t)s2.seq.size(), s2.name.c_str(), s2.start, s2.reverse ? 1 : 0};
-            const size_t h = out.size();
-            out.resize(h + 8192 + 8 * (s1.seq.size() + s2.seq.size()));
-            size_t m = age_format_alignment(&v1, &v2, &j, &r, &out[h], out.size() - h);
-            if (m >= out.size() - h) { out.resize(h + m + 1); m = age_format_alignment(&v1, &v2, &j, &r, &out[h], out.size() - h); }
-            out.resize(h + m);
+            thread_local string scratch;
+            const size_t need = 8192 + 8 * (s1.seq.size() + s2.seq.size());
+            if (scratch.size() < need) scratch.resize(need);
+            size_t m = age_format_alignment(&v1, &v2, &j, &r, &scratch[0], scratch.size());
+            if (m >= scratch.size()) { scratch.resize(m + 1); m = age_format_alignment(&v1, &v2, &j, &r, &scratch[0], scratch.size()); }
+            out.append(scratch.data(), m);
         }
         if (age_time) { char t[64]; snprintf(t, sizeof t, "\nAlignment time is %g s\n\n", per); out += t; }
         fwrite(out.data(), 1, out.size(), stdout);
